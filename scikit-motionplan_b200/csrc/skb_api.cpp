@@ -1,0 +1,181 @@
+// skb_api.cpp -- extern "C" hot-path entry points (device-pointer and host-pointer variants).
+// See include/skmp_b200.h for the reference call site each one replaces.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <string>
+
+#include "skb_internal.h"
+
+using namespace skb;
+
+#define CUDA_OK(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+    } while (0)
+
+static size_t esize(int dtype) { return dtype == SKB_F64 ? 8 : 4; }
+
+// ------------------------------------------------------------------ host pipeline scratch
+struct skb_stream_ctx {
+    static const int NS = 3;
+    cudaStream_t st[NS] = {nullptr, nullptr, nullptr};
+    void *dq[NS] = {nullptr, nullptr, nullptr};
+    void *dv[NS] = {nullptr, nullptr, nullptr};
+    void *dj[NS] = {nullptr, nullptr, nullptr};
+    uint8_t *dvalid[NS] = {nullptr, nullptr, nullptr};
+    size_t cap_q = 0, cap_v = 0, cap_j = 0, cap_valid = 0;
+};
+
+static int ensure_ctx(skb_plan *p, size_t bq, size_t bv, size_t bj, size_t bvalid) {
+    if (!p->hostpipe) {
+        p->hostpipe = new skb_stream_ctx();
+        for (int i = 0; i < skb_stream_ctx::NS; ++i) CUDA_OK(cudaStreamCreateWithFlags(&p->hostpipe->st[i], cudaStreamNonBlocking));
+    }
+    skb_stream_ctx *c = p->hostpipe;
+    auto grow = [&](void **arr, size_t &cap, size_t need) -> int {
+        if (need <= cap) return 0;
+        for (int i = 0; i < skb_stream_ctx::NS; ++i) {
+            if (arr[i]) CUDA_OK(cudaFree(arr[i]));
+            arr[i] = nullptr;
+            CUDA_OK(cudaMalloc(&arr[i], need));
+        }
+        cap = need;
+        return 0;
+    };
+    for (int i = 0; i < skb_stream_ctx::NS; ++i) CUDA_OK(cudaStreamSynchronize(c->st[i]));
+    if (grow(c->dq, c->cap_q, bq)) return -1;
+    if (grow(c->dv, c->cap_v, bv)) return -1;
+    if (grow(c->dj, c->cap_j, bj)) return -1;
+    if (grow(reinterpret_cast<void **>(c->dvalid), c->cap_valid, bvalid)) return -1;
+    return 0;
+}
+
+extern "C" void skb_plan_destroy_hostpipe(skb_plan *p) {
+    if (!p || !p->hostpipe) return;
+    skb_stream_ctx *c = p->hostpipe;
+    for (int i = 0; i < skb_stream_ctx::NS; ++i) {
+        if (c->st[i]) { cudaStreamSynchronize(c->st[i]); cudaStreamDestroy(c->st[i]); }
+        if (c->dq[i]) cudaFree(c->dq[i]);
+        if (c->dv[i]) cudaFree(c->dv[i]);
+        if (c->dj[i]) cudaFree(c->dj[i]);
+        if (c->dvalid[i]) cudaFree(c->dvalid[i]);
+    }
+    delete c;
+    p->hostpipe = nullptr;
+}
+
+// generic chunked H2D -> launch -> D2H driver.  `launch(q_dev, n, vals_dev, jac_dev, valid_dev, stream)`
+template <typename Launch>
+static int host_pipeline(skb_plan *p, int dtype, const void *q_host, int64_t N, size_t vals_per_cfg, size_t jac_per_cfg,
+                         void *out_vals, void *out_jac, uint8_t *out_valid, Launch launch) {
+    if (N <= 0) return 0;
+    const size_t es = esize(dtype);
+    const size_t per_cfg = (out_vals ? vals_per_cfg : 0) + (out_jac ? jac_per_cfg : 0) + (size_t)p->D;
+    int64_t chunk = (int64_t)std::max<size_t>(1024, (48u << 20) / std::max<size_t>(1, per_cfg * es));
+    chunk = std::min<int64_t>(chunk, N);
+    chunk = (chunk + 31) / 32 * 32;
+    if (ensure_ctx(p, chunk * p->D * es, out_vals ? chunk * vals_per_cfg * es : 0, out_jac ? chunk * jac_per_cfg * es : 0,
+                   out_valid ? (size_t)chunk : 0))
+        return -1;
+    skb_stream_ctx *c = p->hostpipe;
+    int k = 0;
+    for (int64_t n0 = 0; n0 < N; n0 += chunk, k = (k + 1) % skb_stream_ctx::NS) {
+        const int64_t n = std::min<int64_t>(chunk, N - n0);
+        cudaStream_t st = c->st[k];
+        CUDA_OK(cudaMemcpyAsync(c->dq[k], (const char *)q_host + n0 * p->D * es, n * p->D * es, cudaMemcpyHostToDevice, st));
+        if (launch(c->dq[k], n, out_vals ? c->dv[k] : nullptr, out_jac ? c->dj[k] : nullptr, out_valid ? c->dvalid[k] : nullptr, st))
+            return -1;
+        if (out_vals)
+            CUDA_OK(cudaMemcpyAsync((char *)out_vals + n0 * vals_per_cfg * es, c->dv[k], n * vals_per_cfg * es, cudaMemcpyDeviceToHost, st));
+        if (out_jac)
+            CUDA_OK(cudaMemcpyAsync((char *)out_jac + n0 * jac_per_cfg * es, c->dj[k], n * jac_per_cfg * es, cudaMemcpyDeviceToHost, st));
+        if (out_valid) CUDA_OK(cudaMemcpyAsync(out_valid + n0, c->dvalid[k], n, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < skb_stream_ctx::NS; ++i) CUDA_OK(cudaStreamSynchronize(c->st[i]));
+    return 0;
+}
+
+extern "C" {
+
+int skb_sdf_eval(const skb_sdf *s, int32_t dtype, const void *pts_dev, int64_t M, void *out_vals_dev, void *out_grads_dev,
+                 void *stream) {
+    if (!s || !pts_dev || !out_vals_dev) return set_error("sdf_eval: bad arguments");
+    if (s->prims.empty()) return set_error("sdf_eval: the SDF has no primitive");
+    const void *dp = get_dev_prims(const_cast<skb_sdf *>(s), dtype);
+    if (!dp) return -1;
+    return launch_sdf_eval(dp, (int)s->prims.size(), dtype, pts_dev, M, out_vals_dev, out_grads_dev, stream);
+}
+
+int skb_fk(const skb_plan *p, int32_t dtype, const void *q_dev, int64_t N, int32_t with_jacobian, void *out_pts_dev,
+           void *out_jac_dev, void *stream) {
+    if (!p || N < 0 || (N > 0 && (!q_dev || !out_pts_dev))) return set_error("fk: bad arguments");
+    if (with_jacobian && !out_jac_dev) return set_error("fk: with_jacobian set but out_jac is NULL");
+    const skb_schedule *sch = get_schedule(const_cast<skb_plan *>(p), p->T);
+    if (!sch) return -1;
+    return launch_tree(p, sch, KIND_MAP, dtype, q_dev, N, nullptr, 0, 0.0, SKB_MODE_ALL, out_pts_dev,
+                       with_jacobian ? out_jac_dev : nullptr, nullptr, stream);
+}
+
+int skb_collfree(const skb_plan *p, const skb_sdf *s, int32_t dtype, const void *q_dev, int64_t N, double margin,
+                 int32_t mode, void *out_vals_dev, void *out_jac_dev, uint8_t *out_valid_dev, void *stream) {
+    if (!p || !s || N < 0 || (N > 0 && !q_dev)) return set_error("collfree: bad arguments");
+    if (mode != SKB_MODE_ALL && mode != SKB_MODE_CLOSEST) return set_error("collfree: bad mode");
+    if (s->prims.empty()) return set_error("collfree: the SDF has no primitive");
+    if (p->rot_type != SKB_ROT_IGNORE) return set_error("collfree: the plan must be built with rot_type IGNORE");
+    if (s->prims.size() > 64) return set_error("collfree: more than 64 SDF primitives");
+    const skb_schedule *sch = get_schedule(const_cast<skb_plan *>(p), 1);
+    if (!sch) return -1;
+    const void *dp = get_dev_prims(const_cast<skb_sdf *>(s), dtype);
+    if (!dp) return -1;
+    return launch_tree(p, sch, KIND_COLLFREE, dtype, q_dev, N, dp, (int)s->prims.size(), margin, mode, out_vals_dev,
+                       out_jac_dev, out_valid_dev, stream);
+}
+
+int skb_pairwise(const skb_plan *p, int32_t dtype, const void *q_dev, int64_t N, int32_t mode, void *out_vals_dev,
+                 void *out_jac_dev, uint8_t *out_valid_dev, void *stream) {
+    if (!p || N < 0 || (N > 0 && !q_dev)) return set_error("pairwise: bad arguments");
+    if (mode != SKB_MODE_ALL && mode != SKB_MODE_CLOSEST) return set_error("pairwise: bad mode");
+    const skb_pair_program *pp = get_pair_program(const_cast<skb_plan *>(p));
+    if (!pp) return -1;
+    return launch_pairwise(p, pp, dtype, q_dev, N, mode, out_vals_dev, out_jac_dev, out_valid_dev, stream);
+}
+
+int skb_fk_host(const skb_plan *p_, int32_t dtype, const void *q_host, int64_t N, int32_t with_jacobian, void *out_pts_host,
+                void *out_jac_host) {
+    skb_plan *p = const_cast<skb_plan *>(p_);
+    if (!p || N < 0 || (N > 0 && (!q_host || !out_pts_host))) return set_error("fk_host: bad arguments");
+    if (with_jacobian && !out_jac_host) return set_error("fk_host: with_jacobian set but out_jac is NULL");
+    const size_t vpc = (size_t)p->F * p->T, jpc = vpc * p->D;
+    return host_pipeline(p, dtype, q_host, N, vpc, jpc, out_pts_host, with_jacobian ? out_jac_host : nullptr, nullptr,
+                         [&](void *dq, int64_t n, void *dv, void *dj, uint8_t *, cudaStream_t st) {
+                             return skb_fk(p, dtype, dq, n, dj != nullptr, dv, dj, st);
+                         });
+}
+
+int skb_collfree_host(const skb_plan *p_, const skb_sdf *s, int32_t dtype, const void *q_host, int64_t N, double margin,
+                      int32_t mode, void *out_vals_host, void *out_jac_host, uint8_t *out_valid_host) {
+    skb_plan *p = const_cast<skb_plan *>(p_);
+    if (!p || !s || N < 0 || (N > 0 && !q_host)) return set_error("collfree_host: bad arguments");
+    const size_t M = mode == SKB_MODE_CLOSEST ? 1 : (size_t)p->F;
+    return host_pipeline(p, dtype, q_host, N, M, M * p->D, out_vals_host, out_jac_host, out_valid_host,
+                         [&](void *dq, int64_t n, void *dv, void *dj, uint8_t *dvalid, cudaStream_t st) {
+                             return skb_collfree(p, s, dtype, dq, n, margin, mode, dv, dj, dvalid, st);
+                         });
+}
+
+int skb_pairwise_host(const skb_plan *p_, int32_t dtype, const void *q_host, int64_t N, int32_t mode, void *out_vals_host,
+                      void *out_jac_host, uint8_t *out_valid_host) {
+    skb_plan *p = const_cast<skb_plan *>(p_);
+    if (!p || N < 0 || (N > 0 && !q_host)) return set_error("pairwise_host: bad arguments");
+    if (!p->pairs_set) return set_error("pairwise: skb_plan_set_pairs was not called");
+    const size_t M = mode == SKB_MODE_CLOSEST ? 1 : p->pair_thr.size();
+    return host_pipeline(p, dtype, q_host, N, M, M * p->D, out_vals_host, out_jac_host, out_valid_host,
+                         [&](void *dq, int64_t n, void *dv, void *dj, uint8_t *dvalid, cudaStream_t st) {
+                             return skb_pairwise(p, dtype, dq, n, mode, dv, dj, dvalid, st);
+                         });
+}
+
+}  // extern "C"

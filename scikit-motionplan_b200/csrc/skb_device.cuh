@@ -1,0 +1,176 @@
+// skb_device.cuh -- device-side building blocks shared by the kernels:
+// real-type traits, SDF primitives (value + analytic gradient), bulk-store (TMA 1-D) helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "skb_internal.h"
+
+namespace skb {
+
+template <typename T> struct Real;
+template <> struct Real<float> {
+    static __device__ __forceinline__ void sincos(float x, float *s, float *c) { sincosf(x, s, c); }
+    static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float rsqrt(float x) { return rsqrtf(x); }
+    static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float floor(float x) { return floorf(x); }
+    static __device__ __forceinline__ float atan2(float y, float x) { return atan2f(y, x); }
+    static __device__ __forceinline__ float asin(float x) { return asinf(x); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+};
+template <> struct Real<double> {
+    static __device__ __forceinline__ void sincos(double x, double *s, double *c) { ::sincos(x, s, c); }
+    static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+    static __device__ __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+    static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
+    static __device__ __forceinline__ double floor(double x) { return ::floor(x); }
+    static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
+    static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+};
+
+// ------------------------------------------------------------------ SDF primitives (local frame)
+// Each returns the signed distance and writes the analytic gradient (local frame).
+// Tie-breaking (>= / first index) mirrors oracle/skmp_oracle.c so kinks resolve identically.
+template <typename T>
+__device__ __forceinline__ T sdf_box_local(const T *h, T x, T y, T z, T &gx, T &gy, T &gz) {
+    using R = Real<T>;
+    T sx = R::abs(x) - h[0], sy = R::abs(y) - h[1], sz = R::abs(z) - h[2];
+    T sgx = x >= T(0) ? T(1) : T(-1), sgy = y >= T(0) ? T(1) : T(-1), sgz = z >= T(0) ? T(1) : T(-1);
+    if (sx > T(0) || sy > T(0) || sz > T(0)) {
+        T qx = sx > T(0) ? sx : T(0), qy = sy > T(0) ? sy : T(0), qz = sz > T(0) ? sz : T(0);
+        T d = R::sqrt(qx * qx + qy * qy + qz * qz);
+        T inv = T(1) / d;
+        gx = sgx * qx * inv; gy = sgy * qy * inv; gz = sgz * qz * inv;
+        return d;
+    }
+    int k = 0; T m = sx;
+    if (sy > m) { m = sy; k = 1; }
+    if (sz > m) { m = sz; k = 2; }
+    gx = k == 0 ? sgx : T(0); gy = k == 1 ? sgy : T(0); gz = k == 2 ? sgz : T(0);
+    return m;
+}
+
+template <typename T>
+__device__ __forceinline__ T sdf_cylinder_local(T radius, T hh, T x, T y, T z, T &gx, T &gy, T &gz) {
+    using R = Real<T>;
+    T rho = R::sqrt(x * x + y * y);
+    T s0 = rho - radius, s1 = R::abs(z) - hh;
+    T ux = rho > T(0) ? x / rho : T(0), uy = rho > T(0) ? y / rho : T(0);
+    T sgz = z >= T(0) ? T(1) : T(-1);
+    if (s0 > T(0) || s1 > T(0)) {
+        T q0 = s0 > T(0) ? s0 : T(0), q1 = s1 > T(0) ? s1 : T(0);
+        T d = R::sqrt(q0 * q0 + q1 * q1);
+        T inv = T(1) / d;
+        gx = ux * q0 * inv; gy = uy * q0 * inv; gz = sgz * q1 * inv;
+        return d;
+    }
+    if (s0 >= s1) { gx = ux; gy = uy; gz = T(0); return s0; }
+    gx = T(0); gy = T(0); gz = sgz;
+    return s1;
+}
+
+template <typename T>
+__device__ __forceinline__ T sdf_sphere_local(T radius, T x, T y, T z, T &gx, T &gy, T &gz) {
+    using R = Real<T>;
+    T n = R::sqrt(x * x + y * y + z * z);
+    T inv = n > T(0) ? T(1) / n : T(0);
+    gx = x * inv; gy = y * inv; gz = z * inv;
+    return n - radius;
+}
+
+template <typename T>
+__device__ __forceinline__ T grid_fetch(const void *grid, bool f64, int64_t idx) {
+    if (f64) return (T)__ldg(reinterpret_cast<const double *>(grid) + idx);
+    return (T)__ldg(reinterpret_cast<const float *>(grid) + idx);
+}
+
+// trilinear voxel grid: value + analytic gradient; `fill`, zero gradient outside the sample box
+template <typename T>
+__device__ __forceinline__ T sdf_grid_local(const DevPrim<T> &pr, T x, T y, T z, T &gx, T &gy, T &gz) {
+    using R = Real<T>;
+    const T ux = (x - pr.par[0]) * pr.par[3], uy = (y - pr.par[1]) * pr.par[4], uz = (z - pr.par[2]) * pr.par[5];
+    const T tx = T(pr.dims[0] - 1), ty = T(pr.dims[1] - 1), tz = T(pr.dims[2] - 1);
+    if (!(ux >= T(0) && ux <= tx && uy >= T(0) && uy <= ty && uz >= T(0) && uz <= tz)) {
+        gx = gy = gz = T(0);
+        return pr.par[6];
+    }
+    int ix = min((int)R::floor(ux), pr.dims[0] - 2);
+    int iy = min((int)R::floor(uy), pr.dims[1] - 2);
+    int iz = min((int)R::floor(uz), pr.dims[2] - 2);
+    const T fx = ux - T(ix), fy = uy - T(iy), fz = uz - T(iz);
+    const int64_t sy = pr.dims[2], sx = (int64_t)pr.dims[1] * pr.dims[2];
+    const int64_t b = ix * sx + iy * sy + iz;
+    const bool f64 = (pr.flags & PF_GRID_F64) != 0;
+    const T c000 = grid_fetch<T>(pr.grid, f64, b), c001 = grid_fetch<T>(pr.grid, f64, b + 1);
+    const T c010 = grid_fetch<T>(pr.grid, f64, b + sy), c011 = grid_fetch<T>(pr.grid, f64, b + sy + 1);
+    const T c100 = grid_fetch<T>(pr.grid, f64, b + sx), c101 = grid_fetch<T>(pr.grid, f64, b + sx + 1);
+    const T c110 = grid_fetch<T>(pr.grid, f64, b + sx + sy), c111 = grid_fetch<T>(pr.grid, f64, b + sx + sy + 1);
+    // lerp along x, then y, then z (same association as the oracle)
+    const T c00 = c000 + fx * (c100 - c000), c01 = c001 + fx * (c101 - c001);
+    const T c10 = c010 + fx * (c110 - c010), c11 = c011 + fx * (c111 - c011);
+    const T c0 = c00 + fy * (c10 - c00), c1 = c01 + fy * (c11 - c01);
+    const T val = c0 + fz * (c1 - c0);
+    const T dx0 = (c100 - c000) + fy * ((c110 - c010) - (c100 - c000));
+    const T dx1 = (c101 - c001) + fy * ((c111 - c011) - (c101 - c001));
+    gx = (dx0 + fz * (dx1 - dx0)) * pr.par[3];
+    const T dy0 = c10 - c00, dy1 = c11 - c01;
+    gy = (dy0 + fz * (dy1 - dy0)) * pr.par[4];
+    gz = (c1 - c0) * pr.par[5];
+    return val;
+}
+
+// union (min) of primitives: world point -> distance + world gradient of the closest primitive
+template <typename T>
+__device__ __forceinline__ T sdf_union(const DevPrim<T> *prims, int np, T px, T py, T pz, T &gx, T &gy, T &gz) {
+    T best = Real<T>::inf();
+    gx = gy = gz = T(0);
+    for (int i = 0; i < np; ++i) {
+        const DevPrim<T> &pr = prims[i];
+        T dx = px - pr.pos[0], dy = py - pr.pos[1], dz = pz - pr.pos[2];
+        T lx, ly, lz;
+        const bool ident = (pr.flags & PF_IDENTITY) != 0;
+        if (ident) { lx = dx; ly = dy; lz = dz; }
+        else {   // local = R^T d
+            lx = pr.rot[0] * dx + pr.rot[3] * dy + pr.rot[6] * dz;
+            ly = pr.rot[1] * dx + pr.rot[4] * dy + pr.rot[7] * dz;
+            lz = pr.rot[2] * dx + pr.rot[5] * dy + pr.rot[8] * dz;
+        }
+        T ax, ay, az, d;
+        if (pr.type == PRIM_BOX) d = sdf_box_local<T>(pr.par, lx, ly, lz, ax, ay, az);
+        else if (pr.type == PRIM_GRID) d = sdf_grid_local<T>(pr, lx, ly, lz, ax, ay, az);
+        else if (pr.type == PRIM_CYLINDER) d = sdf_cylinder_local<T>(pr.par[0], pr.par[1], lx, ly, lz, ax, ay, az);
+        else d = sdf_sphere_local<T>(pr.par[0], lx, ly, lz, ax, ay, az);
+        if (d < best) {
+            best = d;
+            if (ident) { gx = ax; gy = ay; gz = az; }
+            else {
+                gx = pr.rot[0] * ax + pr.rot[1] * ay + pr.rot[2] * az;
+                gy = pr.rot[3] * ax + pr.rot[4] * ay + pr.rot[5] * az;
+                gz = pr.rot[6] * ax + pr.rot[7] * ay + pr.rot[8] * az;
+            }
+        }
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------ bulk async store helpers (sm_90+/sm_100a)
+// cp.async.bulk shared::cta -> global (1-D TMA): SASS UBLKCP.  16-byte aligned src/dst/size.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy before a bulk store reads them
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+}  // namespace skb

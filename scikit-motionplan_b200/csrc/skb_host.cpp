@@ -1,0 +1,811 @@
+// skb_host.cpp -- host side of the engine: kinematic model, SDF descriptors, and the plan
+// compiler that turns (tree, sticky state, features, control joints, base type) into the flat
+// program the CUDA kernels interpret.  Native replacement for the bookkeeping half of tinyfk
+// (URDF tree, add_new_link, set_q, relevance tables) -- see include/skmp_b200.h for the
+// reference call sites.  No kernel code in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+
+#include "skb_internal.h"
+
+namespace skb {
+
+static thread_local std::string g_err;
+int64_t g_launch_count = 0;
+
+int set_error(const std::string &msg) {
+    g_err = msg;
+    return -1;
+}
+
+#define CUDA_OK(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+    } while (0)
+
+// ------------------------------------------------------------------ fp64 rigid-transform algebra
+static void qmul(const double *a, const double *b, double *o) {
+    double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    double y = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+    double z = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3];
+    double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+static void qrot(const double *q, const double *v, double *o) {
+    double tx = 2 * (q[1] * v[2] - q[2] * v[1]), ty = 2 * (q[2] * v[0] - q[0] * v[2]),
+           tz = 2 * (q[0] * v[1] - q[1] * v[0]);
+    o[0] = v[0] + q[3] * tx + (q[1] * tz - q[2] * ty);
+    o[1] = v[1] + q[3] * ty + (q[2] * tx - q[0] * tz);
+    o[2] = v[2] + q[3] * tz + (q[0] * ty - q[1] * tx);
+}
+static Xf xf_identity() { return Xf{{0, 0, 0, 1}, {0, 0, 0}}; }
+static Xf xf_mul(const Xf &a, const Xf &b) {
+    Xf r;
+    double t[3];
+    qrot(a.q, b.t, t);
+    for (int i = 0; i < 3; ++i) r.t[i] = a.t[i] + t[i];
+    qmul(a.q, b.q, r.q);
+    return r;
+}
+static Xf xf_inv(const Xf &a) {
+    Xf r;
+    r.q[0] = -a.q[0]; r.q[1] = -a.q[1]; r.q[2] = -a.q[2]; r.q[3] = a.q[3];
+    double t[3];
+    qrot(r.q, a.t, t);
+    for (int i = 0; i < 3; ++i) r.t[i] = -t[i];
+    return r;
+}
+static void quat_from_rpy(double r, double p, double y, double *q) {
+    double phi = r / 2, the = p / 2, psi = y / 2;
+    q[0] = sin(phi) * cos(the) * cos(psi) - cos(phi) * sin(the) * sin(psi);
+    q[1] = cos(phi) * sin(the) * cos(psi) + sin(phi) * cos(the) * sin(psi);
+    q[2] = cos(phi) * cos(the) * sin(psi) - sin(phi) * sin(the) * cos(psi);
+    q[3] = cos(phi) * cos(the) * cos(psi) + sin(phi) * sin(the) * sin(psi);
+}
+static Xf xf_from_xyzrpy(const double *o) {
+    Xf r;
+    r.t[0] = o[0]; r.t[1] = o[1]; r.t[2] = o[2];
+    quat_from_rpy(o[3], o[4], o[5], r.q);
+    return r;
+}
+static void quat_to_matrix(const double *q, double *R) {
+    double x = q[0], y = q[1], z = q[2], w = q[3];
+    double n = x * x + y * y + z * z + w * w;
+    double s = n > 0 ? 2.0 / n : 0.0;
+    R[0] = 1 - s * (y * y + z * z); R[1] = s * (x * y - z * w);     R[2] = s * (x * z + y * w);
+    R[3] = s * (x * y + z * w);     R[4] = 1 - s * (x * x + z * z); R[5] = s * (y * z - x * w);
+    R[6] = s * (x * z - y * w);     R[7] = s * (y * z + x * w);     R[8] = 1 - s * (x * x + y * y);
+}
+static Xf xf_motion(int jtype, const double *axis, double v) {
+    Xf r = xf_identity();
+    if (jtype == SKB_JOINT_REVOLUTE) {
+        double h = 0.5 * v, sh = sin(h);
+        r.q[0] = axis[0] * sh; r.q[1] = axis[1] * sh; r.q[2] = axis[2] * sh; r.q[3] = cos(h);
+    } else if (jtype == SKB_JOINT_PRISMATIC) {
+        r.t[0] = axis[0] * v; r.t[1] = axis[1] * v; r.t[2] = axis[2] * v;
+    }
+    return r;
+}
+// rotation A with A * e_z = a  (a unit)
+static Xf xf_z_to_axis(const double *a) {
+    Xf r = xf_identity();
+    double n = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    if (n == 0) return r;
+    double az = a[2] / n;
+    if (az > 1.0 - 1e-14) return r;
+    if (az < -1.0 + 1e-14) { r.q[0] = 1; r.q[1] = 0; r.q[2] = 0; r.q[3] = 0; return r; }
+    // rotation axis = e_z x a, angle = acos(az)
+    double kx = -a[1] / n, ky = a[0] / n, kn = sqrt(kx * kx + ky * ky);
+    kx /= kn; ky /= kn;
+    double ang = acos(az), sh = sin(0.5 * ang);
+    r.q[0] = kx * sh; r.q[1] = ky * sh; r.q[2] = 0; r.q[3] = cos(0.5 * ang);
+    return r;
+}
+
+// ------------------------------------------------------------------ plan compiler
+static int compile_tree(const skb_model *m, const int32_t *feat_links, int nf, const int32_t *joint_links, int nj,
+                        int base_type, int rot_type, skb_plan *p) {
+    const int n = (int)m->parent.size();
+    if (n == 0) return set_error("plan: empty model");
+    if (base_type < 0 || base_type > 2) return set_error("plan: bad base_type");
+    if (rot_type < 0 || rot_type > 2) return set_error("plan: bad rot_type");
+    for (int f = 0; f < nf; ++f)
+        if (feat_links[f] < 0 || feat_links[f] >= n) return set_error("plan: feature link id out of range");
+    std::vector<int> ctrl(n, -1);
+    for (int j = 0; j < nj; ++j) {
+        int l = joint_links[j];
+        if (l <= 0 || l >= n) return set_error("plan: joint id out of range (the root link has no joint)");
+        if (ctrl[l] >= 0) return set_error("plan: duplicated control joint");
+        ctrl[l] = j;
+    }
+    p->D = nj + (base_type == SKB_BASE_PLANER ? 3 : (base_type == SKB_BASE_FLOATING ? 6 : 0));
+    p->F = nf;
+    p->rot_type = rot_type;
+    p->base_type = base_type;
+    p->T = rot_type == SKB_ROT_IGNORE ? 3 : (rot_type == SKB_ROT_RPY ? 6 : 7);
+
+    struct Raw { int type, col, parent; Xf pre; double axis[3]; };
+    std::vector<Raw> raw;
+    raw.push_back(Raw{NODE_NONE, -1, -1, xf_identity(), {0, 0, 1}});
+    int base_node = 0;
+    Xf base_const = xf_identity();
+    auto add_raw = [&](int type, int col, int parent, const Xf &pre, double ax, double ay, double az) {
+        raw.push_back(Raw{type, col, parent, pre, {ax, ay, az}});
+        return (int)raw.size() - 1;
+    };
+    if (base_type == SKB_BASE_FIXED) {
+        base_const = xf_from_xyzrpy(m->base_pose);
+    } else if (base_type == SKB_BASE_PLANER) {
+        // T_base = Trans(x, y, 0) Rz(theta)                       skmp/robot/utils.py:45-50
+        int a = add_raw(NODE_PRISMATIC, nj + 0, 0, xf_identity(), 1, 0, 0);
+        int b = add_raw(NODE_PRISMATIC, nj + 1, a, xf_identity(), 0, 1, 0);
+        base_node = add_raw(NODE_REVOLUTE, nj + 2, b, xf_identity(), 0, 0, 1);
+    } else {
+        // T_base = Trans(x, y, z) Rz(yaw) Ry(pitch) Rx(roll); q tail = [x y z roll pitch yaw]
+        //                                                          skmp/robot/utils.py:51-56
+        int a = add_raw(NODE_PRISMATIC, nj + 0, 0, xf_identity(), 1, 0, 0);
+        int b = add_raw(NODE_PRISMATIC, nj + 1, a, xf_identity(), 0, 1, 0);
+        int c = add_raw(NODE_PRISMATIC, nj + 2, b, xf_identity(), 0, 0, 1);
+        int y = add_raw(NODE_REVOLUTE, nj + 5, c, xf_identity(), 0, 0, 1);
+        int pt = add_raw(NODE_REVOLUTE, nj + 4, y, xf_identity(), 0, 1, 0);
+        base_node = add_raw(NODE_REVOLUTE, nj + 3, pt, xf_identity(), 1, 0, 0);
+    }
+
+    std::vector<char> needed(n, 0);
+    for (int f = 0; f < nf; ++f)
+        for (int l = feat_links[f]; l >= 0 && !needed[l]; l = m->parent[l]) needed[l] = 1;
+    std::vector<int> node_of(n, -1);
+    std::vector<Xf> C(n, xf_identity());
+    for (int l = 0; l < n; ++l) {
+        if (!needed[l]) continue;
+        int par = m->parent[l];
+        if (par < 0) { node_of[l] = base_node; C[l] = base_const; continue; }
+        if (par >= l) return set_error("plan: links are not topologically sorted");
+        Xf org = xf_from_xyzrpy(&m->origin[6 * l]);
+        if (ctrl[l] >= 0 && m->jtype[l] != SKB_JOINT_FIXED) {
+            const double *a = &m->axis[3 * l];
+            node_of[l] = add_raw(m->jtype[l] == SKB_JOINT_REVOLUTE ? NODE_REVOLUTE : NODE_PRISMATIC, ctrl[l],
+                                 node_of[par], xf_mul(C[par], org), a[0], a[1], a[2]);
+            C[l] = xf_identity();
+        } else {
+            node_of[l] = node_of[par];
+            C[l] = xf_mul(xf_mul(C[par], org), xf_motion(m->jtype[l], &m->axis[3 * l], m->angle[l]));
+        }
+    }
+    // drop movable nodes that carry no feature below them (e.g. unused base chain never happens, but
+    // control joints outside every feature's ancestry do): they contribute only zero columns.
+    const int nr = (int)raw.size();
+    std::vector<char> used(nr, 0);
+    used[0] = 1;
+    for (int f = 0; f < nf; ++f)
+        for (int k = node_of[feat_links[f]]; k >= 0 && !used[k]; k = raw[k].parent) used[k] = 1;
+    std::vector<int> remap(nr, -1);
+    std::vector<Xf> A;   // z-normalising rotation per kept node
+    p->nodes.clear();
+    for (int k = 0; k < nr; ++k) {
+        if (!used[k]) continue;
+        remap[k] = (int)p->nodes.size();
+        skb_plan::Node nd;
+        nd.type = raw[k].type; nd.col = raw[k].col;
+        nd.parent = raw[k].parent < 0 ? -1 : remap[raw[k].parent];
+        nd.di = nd.parent < 0 ? -1 : p->nodes[nd.parent].di + 1;
+        Xf a = (raw[k].type == NODE_NONE) ? xf_identity() : xf_z_to_axis(raw[k].axis);
+        Xf apar = nd.parent < 0 ? xf_identity() : A[nd.parent];
+        nd.pre = xf_mul(xf_mul(xf_inv(apar), raw[k].pre), a);
+        A.push_back(a);
+        if (nd.parent >= 0) p->nodes[nd.parent].children.push_back(remap[k]);
+        p->nodes.push_back(nd);
+    }
+    p->feat_node.resize(nf);
+    p->feat_off.resize(nf);
+    for (int f = 0; f < nf; ++f) {
+        int k = remap[node_of[feat_links[f]]];
+        p->feat_node[f] = k;
+        p->feat_off[f] = xf_mul(xf_inv(A[k]), C[feat_links[f]]);
+    }
+    // DFS preorder
+    p->order.clear();
+    std::function<void(int)> dfs = [&](int k) {
+        p->order.push_back(k);
+        for (int c : p->nodes[k].children) dfs(c);
+    };
+    dfs(0);
+    p->max_active = 0;
+    for (auto &nd : p->nodes) p->max_active = std::max(p->max_active, nd.di + 1);
+    p->radii.assign(nf, 0.0);
+    return 0;
+}
+
+static int pad_run(int floats) {   // multiple of 4 with an odd quotient: conflict-free 16-byte lanes
+    int q = (floats + 3) / 4;
+    if (q % 2 == 0) q += 1;
+    return q * 4;
+}
+
+static int build_schedule(skb_plan *p, int rows, skb_schedule *s) {
+    const int D = p->D, nf = p->F;
+    const int per_feat = rows * D;
+    int C = p->tune_chunk, nbuf = p->tune_nbuf;
+    if (nbuf <= 0) nbuf = 2;
+    if (C <= 0) {
+        C = std::max(1, 64 / std::max(1, per_feat));
+        if (C >= 4) C = (C / 4) * 4;
+        C = std::min(C, 16);
+        if (rows == 1 && C < 4) C = 4;
+    }
+    // keep one warp's staging under ~48 KB
+    while (C > 1 && (size_t)nbuf * 32 * pad_run(C * per_feat) * 8 > 96 * 1024) C = std::max(1, C / 2);
+    s->rows = rows; s->chunk_cap = C; s->n_buf = nbuf; s->runp = pad_run(C * per_feat);
+    s->max_active = p->max_active;
+
+    const int n_nodes = (int)p->nodes.size();
+    // slots: a node is saved when it has a child that does not directly follow it in preorder
+    std::vector<int> pos(n_nodes), save(n_nodes, -1), src(n_nodes, SRC_IDENTITY), saved_above(n_nodes, 0);
+    for (int i = 0; i < n_nodes; ++i) pos[p->order[i]] = i;
+    int n_slots = 0;
+    for (int i = 0; i < n_nodes; ++i) {
+        int k = p->order[i];
+        const auto &nd = p->nodes[k];
+        saved_above[k] = nd.parent < 0 ? 0 : saved_above[nd.parent] + (save[nd.parent] >= 0 ? 1 : 0);
+        bool need_save = false;
+        for (int c : nd.children)
+            if (pos[c] != i + 1) need_save = true;
+        if (need_save && k != 0) { save[k] = saved_above[k]; n_slots = std::max(n_slots, save[k] + 1); }
+        if (nd.parent < 0) src[k] = SRC_IDENTITY;
+        else if (nd.parent == 0) src[k] = SRC_IDENTITY;     // world node is the identity frame
+        else if (pos[nd.parent] == i - 1) src[k] = SRC_CURRENT;
+        else src[k] = save[nd.parent];
+    }
+    if (n_slots > MAX_SLOTS) return set_error("plan: kinematic tree branches too deeply (more than 8 nested branch points)");
+
+    // chunks per node, in preorder
+    struct Chunk { int feat_begin, count, out0, active, node; std::vector<int> zero; int buf; };
+    std::vector<Chunk> chunks;
+    std::vector<int> feat_order;   // processing order -> output feature index
+    std::vector<std::vector<int>> node_feats(n_nodes);
+    for (int f = 0; f < nf; ++f) node_feats[p->feat_node[f]].push_back(f);
+    std::vector<int> chunk_begin(n_nodes, 0), chunk_end(n_nodes, 0);
+    for (int i = 0; i < n_nodes; ++i) {
+        int k = p->order[i];
+        auto &fs = node_feats[k];   // ascending output index by construction
+        chunk_begin[k] = (int)chunks.size();
+        size_t a = 0;
+        while (a < fs.size()) {
+            size_t b = a + 1;
+            while (b < fs.size() && fs[b] == fs[b - 1] + 1) ++b;
+            // run [fs[a], fs[b-1]] -> chunks cut at multiples of the alignment quantum
+            int s0 = fs[a], e = fs[b - 1] + 1;
+            const int quantum = (C >= 4) ? 4 : 1;
+            while (s0 < e) {
+                int cut;
+                if (s0 % quantum != 0) cut = std::min(e, (s0 / quantum + 1) * quantum);   // misaligned head
+                else {
+                    cut = std::min(e, s0 + C);
+                    if (cut < e || (cut - s0) % quantum == 0) { /* full or aligned */ }
+                    else if (cut - s0 > quantum) cut = s0 + ((cut - s0) / quantum) * quantum;  // leave tail
+                }
+                Chunk ch;
+                ch.feat_begin = (int)feat_order.size();
+                ch.count = cut - s0; ch.out0 = s0; ch.active = p->nodes[k].di + 1; ch.node = k; ch.buf = 0;
+                for (int f = s0; f < cut; ++f) feat_order.push_back(f);
+                chunks.push_back(ch);
+                s0 = cut;
+            }
+            a = b;
+        }
+        chunk_end[k] = (int)chunks.size();
+    }
+    // ancestor column lists
+    std::vector<int> anc_begin(n_nodes, 0), anc;
+    for (int k = 0; k < n_nodes; ++k) {
+        anc_begin[k] = (int)anc.size();
+        std::vector<int> cols;
+        for (int a = k; a > 0; a = p->nodes[a].parent) cols.push_back(p->nodes[a].col);
+        std::reverse(cols.begin(), cols.end());
+        for (int c : cols) anc.push_back(c);
+    }
+    // zero-fill schedule: simulate two tiles; the second tile's lists are the steady state
+    std::vector<std::vector<std::vector<char>>> dirty(nbuf, std::vector<std::vector<char>>(C, std::vector<char>(D, 0)));
+    for (int pass = 0; pass < 2; ++pass) {
+        int b = 0;
+        for (auto &ch : chunks) {
+            ch.buf = b;
+            std::vector<char> act(D, 0);
+            for (int i = 0; i < ch.active; ++i) act[anc[anc_begin[ch.node] + i]] = 1;
+            std::vector<char> z(D, 0);
+            for (int r = 0; r < ch.count; ++r)
+                for (int c = 0; c < D; ++c)
+                    if (dirty[b][r][c] && !act[c]) z[c] = 1;
+            std::vector<int> zl;
+            for (int c = 0; c < D; ++c) if (z[c]) zl.push_back(c);
+            if (pass == 0) ch.zero = zl;
+            else { for (int c : zl) if (std::find(ch.zero.begin(), ch.zero.end(), c) == ch.zero.end()) ch.zero.push_back(c); }
+            for (int r = 0; r < ch.count; ++r)
+                for (int c = 0; c < D; ++c) dirty[b][r][c] = act[c];
+            b = (b + 1) % nbuf;
+        }
+    }
+    int max_zero = 0;
+    std::vector<int> zero_begin(chunks.size()), zeros;
+    for (size_t i = 0; i < chunks.size(); ++i) {
+        zero_begin[i] = (int)zeros.size();
+        for (int c : chunks[i].zero) zeros.push_back(c);
+        max_zero = std::max(max_zero, (int)chunks[i].zero.size());
+    }
+    (void)max_zero;
+
+    const bool pose = p->rot_type != SKB_ROT_IGNORE;
+    const int feat_stride = pose ? FEAT_F_POSE : FEAT_F_POINT;
+    // ---- pack
+    std::vector<int32_t> &I = s->I;
+    std::vector<double> &Fv = s->F;
+    I.assign(HDR_WORDS, 0);
+    I[H_N_NODES] = n_nodes; I[H_N_CHUNKS] = (int)chunks.size(); I[H_N_FEAT] = nf; I[H_D] = D; I[H_ROWS] = rows;
+    I[H_ROT_TYPE] = p->rot_type; I[H_MAX_ACTIVE] = p->max_active; I[H_N_SLOTS] = n_slots;
+    I[H_CHUNK_CAP] = C; I[H_N_BUF] = nbuf; I[H_RUNP] = s->runp; I[H_FEAT_STRIDE] = feat_stride;
+    I[H_NODE_I] = (int)I.size();
+    I.resize(I.size() + (size_t)n_nodes * NODE_I);
+    I[H_CHUNK_I] = (int)I.size();
+    I.resize(I.size() + chunks.size() * CHUNK_I);
+    I[H_ANC_I] = (int)I.size();
+    I.insert(I.end(), anc.begin(), anc.end());
+    I[H_ZERO_I] = (int)I.size();
+    I.insert(I.end(), zeros.begin(), zeros.end());
+    I[H_I_TOTAL] = (int)I.size();
+    for (int i = 0; i < n_nodes; ++i) {            // node records in preorder
+        int k = p->order[i];
+        int32_t *r = &I[I[H_NODE_I] + i * NODE_I];
+        r[N_TYPE] = p->nodes[k].type; r[N_COL] = p->nodes[k].col; r[N_DI] = p->nodes[k].di;
+        r[N_SRC] = src[k]; r[N_SAVE] = save[k];
+        r[N_CHUNK_BEGIN] = chunk_begin[k]; r[N_CHUNK_END] = chunk_end[k]; r[N_ANC] = I[H_ANC_I] + anc_begin[k];
+    }
+    const int ROW = nf * rows * D, VROW = nf * rows;
+    int vec_all = 1, vvec_all = 1;
+    for (size_t i = 0; i < chunks.size(); ++i) {
+        int32_t *r = &I[I[H_CHUNK_I] + i * CHUNK_I];
+        const Chunk &ch = chunks[i];
+        r[C_FEAT_BEGIN] = ch.feat_begin; r[C_COUNT] = ch.count; r[C_OUT0] = ch.out0; r[C_ACTIVE] = ch.active;
+        r[C_ZERO_BEGIN] = I[H_ZERO_I] + zero_begin[i]; r[C_ZERO_COUNT] = (int)ch.zero.size(); r[C_BUF] = ch.buf;
+        int jvec = (ROW % 4 == 0) && ((ch.out0 * per_feat) % 4 == 0) && ((ch.count * per_feat) % 4 == 0);
+        int vvec = (VROW % 4 == 0) && ((ch.out0 * rows) % 4 == 0) && ((ch.count * rows) % 4 == 0);
+        r[C_PAD] = jvec | (vvec << 1);
+        vec_all &= jvec; vvec_all &= vvec;
+    }
+    I[H_VEC_OK] = vec_all; I[H_VALS_VEC_OK] = vvec_all;
+    Fv.clear();
+    I[H_NODE_F] = 0;
+    Fv.resize((size_t)n_nodes * NODE_F, 0.0);
+    for (int i = 0; i < n_nodes; ++i) {
+        int k = p->order[i];
+        double *r = &Fv[(size_t)i * NODE_F];
+        quat_to_matrix(p->nodes[k].pre.q, r + NF_R);
+        for (int j = 0; j < 3; ++j) r[NF_T + j] = p->nodes[k].pre.t[j];
+        for (int j = 0; j < 4; ++j) r[NF_Q + j] = p->nodes[k].pre.q[j];
+    }
+    I[H_FEAT_F] = (int)Fv.size();
+    Fv.resize(Fv.size() + (size_t)nf * feat_stride, 0.0);
+    for (int i = 0; i < nf; ++i) {
+        int f = feat_order[i];
+        double *r = &Fv[I[H_FEAT_F] + (size_t)i * feat_stride];
+        for (int j = 0; j < 3; ++j) r[j] = p->feat_off[f].t[j];
+        r[3] = p->radii[f];
+        if (pose) {
+            quat_to_matrix(p->feat_off[f].q, r + 4);
+            for (int j = 0; j < 4; ++j) r[13 + j] = p->feat_off[f].q[j];
+        }
+    }
+    I[H_F_TOTAL] = (int)Fv.size();
+    return 0;
+}
+
+template <typename T>
+static int upload_reals(const std::vector<double> &src, void **dst) {
+    std::vector<T> tmp(src.size() ? src.size() : 1);
+    for (size_t i = 0; i < src.size(); ++i) tmp[i] = (T)src[i];
+    CUDA_OK(cudaMalloc(dst, tmp.size() * sizeof(T)));
+    CUDA_OK(cudaMemcpy(*dst, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static void free_schedule(skb_schedule &s) {
+    if (s.dI) cudaFree(s.dI);
+    if (s.dF32) cudaFree(s.dF32);
+    if (s.dF64) cudaFree(s.dF64);
+    s.dI = s.dF32 = s.dF64 = nullptr;
+}
+
+const skb_schedule *get_schedule(skb_plan *p, int rows) {
+    std::lock_guard<std::mutex> lk(p->mu);
+    auto it = p->schedules.find(rows);
+    if (it != p->schedules.end()) return &it->second;
+    skb_schedule s;
+    if (build_schedule(p, rows, &s) != 0) return nullptr;
+    if (cudaMalloc(&s.dI, s.I.size() * sizeof(int32_t)) != cudaSuccess ||
+        cudaMemcpy(s.dI, s.I.data(), s.I.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("plan upload failed (no CUDA device?)");
+        return nullptr;
+    }
+    if (upload_reals<float>(s.F, &s.dF32) != 0 || upload_reals<double>(s.F, &s.dF64) != 0) return nullptr;
+    auto res = p->schedules.emplace(rows, std::move(s));
+    return &res.first->second;
+}
+
+// pairwise program: every node evaluated, positions + twists kept per lane in shared memory
+static int build_pair_program(skb_plan *p, skb_pair_program *pp) {
+    const int n_nodes = (int)p->nodes.size(), nf = p->F, P = (int)p->pair_idx.size() / 2;
+    std::vector<int> pos(n_nodes), save(n_nodes, -1), src(n_nodes, SRC_IDENTITY), saved_above(n_nodes, 0);
+    for (int i = 0; i < n_nodes; ++i) pos[p->order[i]] = i;
+    int n_slots = 0;
+    for (int i = 0; i < n_nodes; ++i) {
+        int k = p->order[i];
+        const auto &nd = p->nodes[k];
+        saved_above[k] = nd.parent < 0 ? 0 : saved_above[nd.parent] + (save[nd.parent] >= 0 ? 1 : 0);
+        bool need_save = false;
+        for (int c : nd.children) if (pos[c] != i + 1) need_save = true;
+        if (need_save && k != 0) { save[k] = saved_above[k]; n_slots = std::max(n_slots, save[k] + 1); }
+        if (nd.parent <= 0) src[k] = SRC_IDENTITY;
+        else if (pos[nd.parent] == i - 1) src[k] = SRC_CURRENT;
+        else src[k] = save[nd.parent];
+    }
+    if (n_slots > MAX_SLOTS) return set_error("plan: kinematic tree branches too deeply");
+    // classes keyed by (node_i, node_j)
+    std::map<std::pair<int, int>, int> cls_of;
+    std::vector<std::vector<int>> cls_terms;   // flattened (node_pos, col, side)
+    std::vector<int> pair_cls(P);
+    for (int q = 0; q < P; ++q) {
+        int fi = p->pair_idx[2 * q], fj = p->pair_idx[2 * q + 1];
+        if (fi < 0 || fi >= nf || fj < 0 || fj >= nf) return set_error("pairs: feature index out of range");
+        auto key = std::make_pair(p->feat_node[fi], p->feat_node[fj]);
+        auto it = cls_of.find(key);
+        if (it == cls_of.end()) {
+            std::vector<int> ai, aj, terms;
+            for (int a = key.first; a > 0; a = p->nodes[a].parent) ai.push_back(a);
+            for (int a = key.second; a > 0; a = p->nodes[a].parent) aj.push_back(a);
+            for (int a : ai) if (std::find(aj.begin(), aj.end(), a) == aj.end()) { terms.push_back(pos[a]); terms.push_back(p->nodes[a].col); terms.push_back(1); }
+            for (int a : aj) if (std::find(ai.begin(), ai.end(), a) == ai.end()) { terms.push_back(pos[a]); terms.push_back(p->nodes[a].col); terms.push_back(-1); }
+            it = cls_of.emplace(key, (int)cls_terms.size()).first;
+            cls_terms.push_back(terms);
+        }
+        pair_cls[q] = it->second;
+    }
+    std::vector<int32_t> &I = pp->I;
+    std::vector<double> &Fv = pp->F;
+    I.assign(PHDR_WORDS, 0);
+    I[P_N_NODES] = n_nodes; I[P_N_FEAT] = nf; I[P_D] = p->D; I[P_N_PAIRS] = P; I[P_N_CLASSES] = (int)cls_terms.size();
+    I[P_N_SLOTS] = n_slots;
+    // features grouped by node (preorder position): node record holds [begin, end) into this list
+    std::vector<int> featlist, fbegin(n_nodes, 0), fend(n_nodes, 0);
+    for (int i = 0; i < n_nodes; ++i) {
+        fbegin[i] = (int)featlist.size();
+        for (int f = 0; f < nf; ++f) if (p->feat_node[f] == p->order[i]) featlist.push_back(f);
+        fend[i] = (int)featlist.size();
+    }
+    I[P_NODE_I] = (int)I.size();
+    for (int i = 0; i < n_nodes; ++i) {
+        int k = p->order[i];
+        int32_t r[NODE_I] = {p->nodes[k].type, p->nodes[k].col, p->nodes[k].di, src[k], save[k], fbegin[i], fend[i], 0};
+        I.insert(I.end(), r, r + NODE_I);
+    }
+    I[P_FEATNODE_I] = (int)I.size();
+    I.insert(I.end(), featlist.begin(), featlist.end());
+    I[P_PAIR_I] = (int)I.size();
+    for (int q = 0; q < P; ++q) { I.push_back(p->pair_idx[2 * q]); I.push_back(p->pair_idx[2 * q + 1]); I.push_back(pair_cls[q]); I.push_back(0); }
+    I[P_CLASS_I] = (int)I.size();
+    size_t class_base = I.size();
+    I.resize(I.size() + cls_terms.size() * 2);
+    I[P_TERM_I] = (int)I.size();
+    for (size_t c = 0; c < cls_terms.size(); ++c) {
+        I[class_base + 2 * c] = (int)I.size();
+        I[class_base + 2 * c + 1] = (int)cls_terms[c].size() / 3;
+        I.insert(I.end(), cls_terms[c].begin(), cls_terms[c].end());
+    }
+    I[P_I_TOTAL] = (int)I.size();
+    Fv.clear();
+    I[P_NODE_F] = 0;
+    Fv.resize((size_t)n_nodes * NODE_F, 0.0);
+    for (int i = 0; i < n_nodes; ++i) {
+        int k = p->order[i];
+        double *r = &Fv[(size_t)i * NODE_F];
+        quat_to_matrix(p->nodes[k].pre.q, r + NF_R);
+        for (int j = 0; j < 3; ++j) r[NF_T + j] = p->nodes[k].pre.t[j];
+        for (int j = 0; j < 4; ++j) r[NF_Q + j] = p->nodes[k].pre.q[j];
+    }
+    I[P_FEAT_F] = (int)Fv.size();
+    for (int f = 0; f < nf; ++f) { for (int j = 0; j < 3; ++j) Fv.push_back(p->feat_off[f].t[j]); Fv.push_back(p->radii[f]); }
+    I[P_PAIR_F] = (int)Fv.size();
+    for (int q = 0; q < P; ++q) Fv.push_back(p->pair_thr[q]);
+    I[P_F_TOTAL] = (int)Fv.size();
+    pp->n_pairs = P; pp->n_nodes = n_nodes;
+    return 0;
+}
+
+const skb_pair_program *get_pair_program(skb_plan *p) {
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (!p->pairs_set) { set_error("pairwise: skb_plan_set_pairs was not called"); return nullptr; }
+    if (p->pairs.dI) return &p->pairs;
+    if (build_pair_program(p, &p->pairs) != 0) return nullptr;
+    skb_pair_program &pp = p->pairs;
+    if (cudaMalloc(&pp.dI, pp.I.size() * sizeof(int32_t)) != cudaSuccess ||
+        cudaMemcpy(pp.dI, pp.I.data(), pp.I.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("pair program upload failed (no CUDA device?)");
+        return nullptr;
+    }
+    if (upload_reals<float>(pp.F, &pp.dF32) != 0 || upload_reals<double>(pp.F, &pp.dF64) != 0) return nullptr;
+    return &pp;
+}
+
+template <typename T>
+static int upload_prims(skb_sdf *s, void **dst) {
+    std::vector<DevPrim<T>> v(s->prims.size() ? s->prims.size() : 1);
+    for (size_t i = 0; i < s->prims.size(); ++i) {
+        const skb_host_prim &h = s->prims[i];
+        DevPrim<T> &d = v[i];
+        memset(&d, 0, sizeof(d));
+        d.type = h.type;
+        bool ident = true;
+        for (int k = 0; k < 9; ++k) {
+            d.rot[k] = (T)h.rot[k];
+            if (fabs(h.rot[k] - ((k % 4 == 0) ? 1.0 : 0.0)) > 0) ident = false;
+        }
+        d.flags = (ident ? PF_IDENTITY : 0) | (h.grid_is_f64 ? PF_GRID_F64 : 0);
+        for (int k = 0; k < 3; ++k) { d.pos[k] = (T)h.pos[k]; d.dims[k] = h.dims[k]; }
+        for (int k = 0; k < 8; ++k) d.par[k] = (T)h.par[k];
+        if (h.type == PRIM_GRID) for (int k = 0; k < 3; ++k) d.par[3 + k] = (T)(1.0 / h.par[3 + k]);
+        d.grid = h.dev_grid;
+    }
+    CUDA_OK(cudaMalloc(dst, v.size() * sizeof(DevPrim<T>)));
+    CUDA_OK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(DevPrim<T>), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+const void *get_dev_prims(skb_sdf *s, int dtype) {
+    if (s->dev_count != (int)s->prims.size()) {
+        if (s->dev_f32) cudaFree(s->dev_f32);
+        if (s->dev_f64) cudaFree(s->dev_f64);
+        s->dev_f32 = s->dev_f64 = nullptr;
+        s->dev_count = (int)s->prims.size();
+    }
+    if (dtype == SKB_F32) {
+        if (!s->dev_f32 && upload_prims<float>(s, &s->dev_f32) != 0) return nullptr;
+        return s->dev_f32;
+    }
+    if (!s->dev_f64 && upload_prims<double>(s, &s->dev_f64) != 0) return nullptr;
+    return s->dev_f64;
+}
+
+}  // namespace skb
+
+using namespace skb;
+
+// ------------------------------------------------------------------ C ABI: misc
+extern "C" {
+
+int skb_version(void) { return 100; }
+const char *skb_last_error(void) { return g_err.c_str(); }
+int64_t skb_launch_count(void) { return g_launch_count; }
+
+int skb_device_count(int32_t *out_count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        if (out_count) *out_count = 0;
+        return set_error(std::string("no CUDA device: ") + cudaGetErrorString(e));
+    }
+    if (out_count) *out_count = n;
+    return 0;
+}
+
+// ------------------------------------------------------------------ model
+int skb_model_create(int32_t n_links, const int32_t *parent, const int32_t *joint_type, const double *origin,
+                     const double *axis, skb_model **out) {
+    if (!out || n_links <= 0 || !parent || !joint_type || !origin || !axis) return set_error("model_create: bad arguments");
+    if (parent[0] != -1) return set_error("model_create: link 0 must be the root (parent -1)");
+    for (int i = 1; i < n_links; ++i)
+        if (parent[i] < 0 || parent[i] >= i) return set_error("model_create: links must be topologically sorted");
+    skb_model *m = new skb_model();
+    m->parent.assign(parent, parent + n_links);
+    m->jtype.assign(joint_type, joint_type + n_links);
+    m->origin.assign(origin, origin + 6 * (size_t)n_links);
+    m->axis.assign(axis, axis + 3 * (size_t)n_links);
+    m->angle.assign(n_links, 0.0);
+    for (int k = 0; k < 6; ++k) m->base_pose[k] = 0.0;
+    *out = m;
+    return 0;
+}
+
+int skb_model_add_link(skb_model *m, int32_t parent, const double xyz[3], const double rpy[3], int32_t *out_link_id) {
+    if (!m || parent < 0 || parent >= (int)m->parent.size()) return set_error("add_link: bad parent link id");
+    m->parent.push_back(parent);
+    m->jtype.push_back(SKB_JOINT_FIXED);
+    for (int k = 0; k < 3; ++k) m->origin.push_back(xyz ? xyz[k] : 0.0);
+    for (int k = 0; k < 3; ++k) m->origin.push_back(rpy ? rpy[k] : 0.0);
+    m->axis.push_back(1.0); m->axis.push_back(0.0); m->axis.push_back(0.0);
+    m->angle.push_back(0.0);
+    if (out_link_id) *out_link_id = (int)m->parent.size() - 1;
+    return 0;
+}
+
+int skb_model_set_q(skb_model *m, const int32_t *joint_links, int32_t nj, const double *q, int32_t base_type) {
+    if (!m || (nj > 0 && (!joint_links || !q))) return set_error("set_q: bad arguments");
+    for (int j = 0; j < nj; ++j) {
+        if (joint_links[j] <= 0 || joint_links[j] >= (int)m->parent.size()) return set_error("set_q: joint id out of range");
+        m->angle[joint_links[j]] = q[j];
+    }
+    if (base_type == SKB_BASE_PLANER) {
+        m->base_pose[0] = q[nj]; m->base_pose[1] = q[nj + 1]; m->base_pose[2] = 0;
+        m->base_pose[3] = 0; m->base_pose[4] = 0; m->base_pose[5] = q[nj + 2];
+    } else if (base_type == SKB_BASE_FLOATING) {
+        for (int k = 0; k < 6; ++k) m->base_pose[k] = q[nj + k];
+    } else if (base_type != SKB_BASE_FIXED) {
+        return set_error("set_q: bad base_type");
+    }
+    return 0;
+}
+
+int skb_model_get_state(const skb_model *m, double *out_angles, double out_base_pose[6]) {
+    if (!m) return set_error("get_state: null model");
+    if (out_angles) memcpy(out_angles, m->angle.data(), m->angle.size() * sizeof(double));
+    if (out_base_pose) memcpy(out_base_pose, m->base_pose, 6 * sizeof(double));
+    return 0;
+}
+
+int skb_model_num_links(const skb_model *m, int32_t *out) {
+    if (!m || !out) return set_error("num_links: bad arguments");
+    *out = (int)m->parent.size();
+    return 0;
+}
+
+int skb_model_clone(const skb_model *m, skb_model **out) {
+    if (!m || !out) return set_error("model_clone: bad arguments");
+    *out = new skb_model(*m);
+    return 0;
+}
+
+void skb_model_destroy(skb_model *m) { delete m; }
+
+// ------------------------------------------------------------------ sdf
+int skb_sdf_create(skb_sdf **out) {
+    if (!out) return set_error("sdf_create: bad arguments");
+    *out = new skb_sdf();
+    return 0;
+}
+
+static void fill_pose(skb_host_prim &h, const double pos[3], const double rot[9]) {
+    static const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int k = 0; k < 3; ++k) h.pos[k] = pos ? pos[k] : 0.0;
+    for (int k = 0; k < 9; ++k) h.rot[k] = rot ? rot[k] : I3[k];
+    for (int k = 0; k < 8; ++k) h.par[k] = 0.0;
+    h.dims[0] = h.dims[1] = h.dims[2] = 0;
+}
+
+int skb_sdf_add_box(skb_sdf *s, const double pos[3], const double rot[9], const double half[3]) {
+    if (!s || !half) return set_error("sdf_add_box: bad arguments");
+    skb_host_prim h; h.type = PRIM_BOX; fill_pose(h, pos, rot);
+    for (int k = 0; k < 3; ++k) h.par[k] = half[k];
+    s->prims.push_back(h);
+    return 0;
+}
+
+int skb_sdf_add_cylinder(skb_sdf *s, const double pos[3], const double rot[9], double radius, double half_height) {
+    if (!s) return set_error("sdf_add_cylinder: bad arguments");
+    skb_host_prim h; h.type = PRIM_CYLINDER; fill_pose(h, pos, rot);
+    h.par[0] = radius; h.par[1] = half_height;
+    s->prims.push_back(h);
+    return 0;
+}
+
+int skb_sdf_add_sphere(skb_sdf *s, const double pos[3], double radius) {
+    if (!s) return set_error("sdf_add_sphere: bad arguments");
+    skb_host_prim h; h.type = PRIM_SPHERE; fill_pose(h, pos, nullptr);
+    h.par[0] = radius;
+    s->prims.push_back(h);
+    return 0;
+}
+
+int skb_sdf_add_grid(skb_sdf *s, const double pos[3], const double rot[9], const double lb[3], const double spacing[3],
+                     const int32_t dims[3], double fill, const void *host_values, int32_t values_dtype) {
+    if (!s || !lb || !spacing || !dims || !host_values) return set_error("sdf_add_grid: bad arguments");
+    if (dims[0] < 2 || dims[1] < 2 || dims[2] < 2) return set_error("sdf_add_grid: every grid dimension must be >= 2");
+    if (!std::isfinite(fill)) return set_error("sdf_add_grid: fill value must be finite");
+    skb_host_prim h; h.type = PRIM_GRID; fill_pose(h, pos, rot);
+    for (int k = 0; k < 3; ++k) { h.par[k] = lb[k]; h.par[3 + k] = spacing[k]; h.dims[k] = dims[k]; }
+    h.par[6] = fill;
+    h.grid_is_f64 = values_dtype == SKB_F64;
+    size_t count = (size_t)dims[0] * dims[1] * dims[2];
+    h.grid_bytes = count * (h.grid_is_f64 ? 8 : 4);
+    CUDA_OK(cudaMalloc(&h.dev_grid, h.grid_bytes));
+    CUDA_OK(cudaMemcpy(h.dev_grid, host_values, h.grid_bytes, cudaMemcpyHostToDevice));
+    s->prims.push_back(h);
+    return 0;
+}
+
+int skb_sdf_num_prims(const skb_sdf *s, int32_t *out) {
+    if (!s || !out) return set_error("sdf_num_prims: bad arguments");
+    *out = (int)s->prims.size();
+    return 0;
+}
+
+void skb_sdf_destroy(skb_sdf *s) {
+    if (!s) return;
+    for (auto &h : s->prims) if (h.dev_grid) cudaFree(h.dev_grid);
+    if (s->dev_f32) cudaFree(s->dev_f32);
+    if (s->dev_f64) cudaFree(s->dev_f64);
+    delete s;
+}
+
+// ------------------------------------------------------------------ plan
+int skb_plan_create(const skb_model *m, const int32_t *feature_links, int32_t nf, const int32_t *joint_links, int32_t nj,
+                    int32_t base_type, int32_t rot_type, skb_plan **out) {
+    if (!m || !out || nf <= 0 || !feature_links || (nj > 0 && !joint_links)) return set_error("plan_create: bad arguments");
+    skb_plan *p = new skb_plan();
+    if (compile_tree(m, feature_links, nf, joint_links, nj, base_type, rot_type, p) != 0) { delete p; return -1; }
+    if (p->max_active > 48) { delete p; return set_error("plan_create: more than 48 controlled ancestors on one chain is not supported"); }
+    cudaGetDevice(&p->device);
+    *out = p;
+    return 0;
+}
+
+int skb_plan_dims(const skb_plan *p, int32_t *D, int32_t *F, int32_t *T) {
+    if (!p) return set_error("plan_dims: null plan");
+    if (D) *D = p->D;
+    if (F) *F = p->F;
+    if (T) *T = p->T;
+    return 0;
+}
+
+static void drop_schedules(skb_plan *p) {
+    for (auto &kv : p->schedules) free_schedule(kv.second);
+    p->schedules.clear();
+}
+static void drop_pairs(skb_plan *p) {
+    if (p->pairs.dI) cudaFree(p->pairs.dI);
+    if (p->pairs.dF32) cudaFree(p->pairs.dF32);
+    if (p->pairs.dF64) cudaFree(p->pairs.dF64);
+    p->pairs = skb_pair_program();
+}
+
+int skb_plan_set_radii(skb_plan *p, const double *radii) {
+    if (!p || !radii) return set_error("set_radii: bad arguments");
+    std::lock_guard<std::mutex> lk(p->mu);
+    p->radii.assign(radii, radii + p->F);
+    drop_schedules(p);
+    drop_pairs(p);
+    return 0;
+}
+
+int skb_plan_set_pairs(skb_plan *p, const int32_t *pairs, int32_t n_pairs, const double *rsum_sq) {
+    if (!p || n_pairs <= 0 || !pairs || !rsum_sq) return set_error("set_pairs: bad arguments");
+    std::lock_guard<std::mutex> lk(p->mu);
+    p->pair_idx.assign(pairs, pairs + 2 * (size_t)n_pairs);
+    p->pair_thr.assign(rsum_sq, rsum_sq + n_pairs);
+    p->pairs_set = true;
+    drop_pairs(p);
+    return 0;
+}
+
+int skb_plan_set_tuning(skb_plan *p, int32_t chunk, int32_t nbuf, int32_t warps, int32_t ctas) {
+    if (!p) return set_error("set_tuning: null plan");
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (nbuf < 0 || nbuf > 4 || chunk < 0 || chunk > 32) return set_error("set_tuning: out of range");
+    p->tune_chunk = chunk; p->tune_nbuf = nbuf; p->tune_warps = warps; p->tune_ctas = ctas;
+    drop_schedules(p);
+    return 0;
+}
+
+void skb_plan_destroy_hostpipe(skb_plan *p);   // skb_api.cpp
+
+void skb_plan_destroy(skb_plan *p) {
+    if (!p) return;
+    skb_plan_destroy_hostpipe(p);
+    drop_schedules(p);
+    drop_pairs(p);
+    delete p;
+}
+
+}  // extern "C"

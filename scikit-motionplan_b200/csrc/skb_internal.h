@@ -1,0 +1,171 @@
+// skb_internal.h -- shared between the host-side plan compiler and the CUDA kernels.
+// Not part of the public ABI (that is include/skmp_b200.h).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <map>
+#include <mutex>
+
+#include "../../include/skmp_b200.h"
+
+namespace skb {
+
+// ------------------------------------------------------------------ device program layout
+// A plan is uploaded as two flat arrays: int32 words I[] and real words F[] (float or double).
+// The kernels stage both into shared memory once per CTA.  All indices below are in words.
+//
+// I[0 .. HDR_WORDS)            header (enum Hdr)
+// I[node_i + n*NODE_I ..]      node records   (enum NodeI)
+// I[chunk_i + c*CHUNK_I ..]    chunk records  (enum ChunkI)
+// I[anc_i ..]                  ancestor column lists (one per node, di+1 entries)
+// I[zero_i ..]                 zero-fill column lists (one per chunk)
+// F[node_f + n*NODE_F ..]      node constants: pre-transform R(9) t(3) quat(4)
+// F[feat_f + f*feat_stride ..] feature constants in processing order: off(3) radius [R(9) quat(4) pad(3)]
+enum Hdr {
+    H_N_NODES = 0, H_N_CHUNKS, H_N_FEAT, H_D, H_ROWS, H_ROT_TYPE, H_MAX_ACTIVE, H_N_SLOTS,
+    H_CHUNK_CAP, H_N_BUF, H_RUNP, H_FEAT_STRIDE,
+    H_NODE_I, H_CHUNK_I, H_ANC_I, H_ZERO_I, H_I_TOTAL,
+    H_NODE_F, H_FEAT_F, H_F_TOTAL,
+    H_VEC_OK,      // 1 when every chunk run is 16-byte aligned in the output (bulk-store path)
+    H_VALS_VEC_OK, // 1 when per-chunk value rows are 16-byte aligned
+    HDR_WORDS = 24
+};
+enum NodeI { N_TYPE = 0, N_COL, N_DI, N_SRC, N_SAVE, N_CHUNK_BEGIN, N_CHUNK_END, N_ANC, NODE_I = 8 };
+enum NodeF { NF_R = 0, NF_T = 9, NF_Q = 12, NODE_F = 16 };
+enum ChunkI { C_FEAT_BEGIN = 0, C_COUNT, C_OUT0, C_ACTIVE, C_ZERO_BEGIN, C_ZERO_COUNT, C_BUF, C_PAD, CHUNK_I = 8 };
+enum { FEAT_F_POINT = 4, FEAT_F_POSE = 20 };
+enum { SRC_IDENTITY = -1, SRC_CURRENT = -2 };   // >= 0: restore from slot
+enum { MAX_SLOTS = 8 };
+enum { NODE_NONE = 0, NODE_REVOLUTE = 1, NODE_PRISMATIC = 2 };
+
+// pairwise program (separate upload): all-node evaluation order + per-feature node binding
+// PI header (enum PHdr), node records reuse NodeI/NodeF (chunk fields unused),
+// feature records: I: node index ; F: off(3) radius
+// pair records: I: fi, fj, cls ; F: threshold
+// class records: I: begin, count into term list ; terms: I: node, col, side(+1: use xi, -1: use xj)
+enum PHdr {
+    P_N_NODES = 0, P_N_FEAT, P_D, P_N_PAIRS, P_N_CLASSES, P_N_SLOTS,
+    P_NODE_I, P_FEATNODE_I, P_PAIR_I, P_CLASS_I, P_TERM_I, P_I_TOTAL,
+    P_NODE_F, P_FEAT_F, P_PAIR_F, P_F_TOTAL,
+    PHDR_WORDS = 16
+};
+
+// device SDF primitive, staged to shared memory by the kernels
+template <typename T>
+struct DevPrim {
+    int32_t type;        // SKB sdf type
+    int32_t flags;       // bit0: rotation is identity; bit1: grid data is f64
+    int32_t dims[3];
+    int32_t pad;
+    T pos[3];
+    T rot[9];
+    T par[8];            // box: half[3]; cyl: radius, half height; sphere: radius; grid: lb[3], inv_spacing[3], fill
+    const void *grid;    // device pointer (float or double values)
+};
+enum { PRIM_BOX = 0, PRIM_CYLINDER = 1, PRIM_SPHERE = 2, PRIM_GRID = 3 };
+enum { PF_IDENTITY = 1, PF_GRID_F64 = 2 };
+
+struct Xf {              // rigid transform, quaternion (x,y,z,w) + translation, host fp64
+    double q[4];
+    double t[3];
+};
+
+}  // namespace skb
+
+// ------------------------------------------------------------------ opaque handle definitions
+struct skb_model {
+    std::vector<int32_t> parent, jtype;
+    std::vector<double> origin;   // 6 per link
+    std::vector<double> axis;     // 3 per link
+    std::vector<double> angle;    // sticky joint value per link
+    double base_pose[6];
+};
+
+struct skb_host_prim {
+    int32_t type;
+    int32_t dims[3];
+    double pos[3], rot[9], par[8];
+    void *dev_grid = nullptr;
+    int32_t grid_is_f64 = 0;
+    size_t grid_bytes = 0;
+};
+
+struct skb_sdf {
+    std::vector<skb_host_prim> prims;
+    int device = -1;
+    // device copies of the primitive table, built lazily per dtype
+    void *dev_f32 = nullptr;
+    void *dev_f64 = nullptr;
+    int dev_count = -1;
+};
+
+struct skb_schedule {            // one staged-output schedule for a given rows-per-feature
+    int rows = 0;
+    std::vector<int32_t> I;
+    std::vector<double> F;
+    void *dI = nullptr;
+    void *dF32 = nullptr;
+    void *dF64 = nullptr;
+    int max_active = 0;
+    int chunk_cap = 0, n_buf = 0, runp = 0;
+};
+
+struct skb_pair_program {
+    std::vector<int32_t> I;
+    std::vector<double> F;
+    void *dI = nullptr;
+    void *dF32 = nullptr;
+    void *dF64 = nullptr;
+    int n_pairs = 0;
+    int n_nodes = 0;
+};
+
+struct skb_stream_ctx;           // host-pipeline scratch (skb_hostpipe.cpp)
+
+struct skb_plan {
+    int device = 0;
+    int D = 0, F = 0, T = 3, rot_type = 0, base_type = 0;
+    // compiled tree (host, fp64), shared by all schedules
+    struct Node {
+        int type, col, parent, di;
+        skb::Xf pre;                 // parent-node frame -> joint frame (z-axis normalised)
+        std::vector<int> children;
+    };
+    std::vector<Node> nodes;         // node 0 = pseudo world node
+    std::vector<int> order;          // DFS preorder of node indices
+    std::vector<int> feat_node;      // per feature (output order)
+    std::vector<skb::Xf> feat_off;   // per feature: node frame -> feature frame
+    std::vector<double> radii;       // per feature
+    int max_active = 0;
+    // tuning
+    int tune_chunk = 0, tune_nbuf = 0, tune_warps = 0, tune_ctas = 0;
+    std::map<int, skb_schedule> schedules;   // keyed by rows-per-feature
+    skb_pair_program pairs;
+    bool pairs_set = false;
+    std::vector<int32_t> pair_idx;
+    std::vector<double> pair_thr;
+    skb_stream_ctx *hostpipe = nullptr;
+    std::mutex mu;
+};
+
+namespace skb {
+
+int set_error(const std::string &msg);           // returns -1
+const skb_schedule *get_schedule(skb_plan *p, int rows);   // builds + uploads lazily; nullptr on error
+const skb_pair_program *get_pair_program(skb_plan *p);
+const void *get_dev_prims(skb_sdf *s, int dtype);
+
+// kernel launchers (skb_kernels.cu)
+int launch_tree(const skb_plan *p, const skb_schedule *sch, int kind, int dtype, const void *q, int64_t N,
+                const void *dev_prims, int n_prims, double margin, int mode, void *out_vals, void *out_jac,
+                uint8_t *out_valid, void *stream);
+int launch_pairwise(const skb_plan *p, const skb_pair_program *pp, int dtype, const void *q, int64_t N, int mode,
+                    void *out_vals, void *out_jac, uint8_t *out_valid, void *stream);
+int launch_sdf_eval(const void *dev_prims, int n_prims, int dtype, const void *pts, int64_t M, void *out_vals,
+                    void *out_grads, void *stream);
+enum { KIND_MAP = 0, KIND_COLLFREE = 1 };
+
+extern int64_t g_launch_count;
+
+}  // namespace skb

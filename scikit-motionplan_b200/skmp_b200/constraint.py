@@ -1,0 +1,487 @@
+"""Constraints evaluated on the GPU:  evaluate(qs) -> (values (N, M), jacobians (N, M, D)).
+
+Mirror of the hot-path part of skmp/constraint.py (same class / method names, argument order,
+shapes and error behaviour):
+  AbstractConst.evaluate / evaluate_single / dummy_jacobian      :41-56
+  AbstractIneqConst.is_valid                                     :89-91   all(value > 0)
+  _CompositeConst / IneqCompositeConst / EqCompositeConst        :116-180 (is_valid: not any(value < 0))
+  BoxConst                                                       :183-263
+  CollFreeConst (all spheres / only closest)                     :266-378
+  ConfigPointConst                                               :408-429
+  PoseConstraint                                                 :432-505
+  RelativePoseConstraint / FixedZAxisConstraint                  :508-607
+  PairWiseSelfCollFreeConst                                      :681-782
+Differences that are deliberate and documented in DESIGN.md: SDF gradients are analytic (the
+reference uses forward differences with eps=1e-7, :320-331,:362-369); arrays may be numpy (host
+path) or CUDA torch tensors (device-resident path); ``sdf`` must be an ``skmp_b200.sdf`` descriptor;
+batched ``is_valid_batch`` is added for planners that validate many configurations at once.
+Mesh / FCL / neural self-collision constraints (:610-678,:785-842) are out of scope (no Jacobian,
+per-configuration Python loops, third-party engines).
+"""
+import copy
+import itertools
+import uuid
+from abc import ABC, abstractmethod
+from pathlib import Path
+from typing import Generic, List, Optional, Protocol, Sequence, Tuple, TypeVar, Union, runtime_checkable
+
+import numpy as np
+
+from . import _lib
+from ._array import Batch, _is_torch, torch
+from .kinematics import CollSpheresKinematicsMapBase, EndEffectorKinematicsMap
+from .rotmath import matrix2quaternion, rpy_angle, wxyz2xyzw
+from .sdf import SignedDistanceFunction, as_descriptor
+from .tinyfk import RotationType
+from .urdf import parse_urdf
+
+
+def _to_kind(ref, arr: np.ndarray):
+    """numpy constant -> same array kind / dtype / device as ``ref``."""
+    if _is_torch(ref):
+        return torch.as_tensor(arr, dtype=ref.dtype, device=ref.device)
+    return arr
+
+
+def _cat(arrays, axis: int):
+    if _is_torch(arrays[0]):
+        return torch.cat(list(arrays), dim=axis)
+    return np.concatenate(list(arrays), axis=axis)
+
+
+class AbstractConst(ABC):
+    reflect_robot_flag: bool = False
+    id_value: str
+
+    def assign_id_value(self):
+        self.id_value = str(uuid.uuid4())
+
+    def evaluate(self, qs, with_jacobian: bool):
+        if not self.reflect_robot_flag:
+            raise RuntimeError("{}: you need to call reflect_skrobot_model beforehand".format(type(self).__name__))
+        return self._evaluate(qs, with_jacobian)
+
+    def evaluate_single(self, q, with_jacobian: bool):
+        assert q.ndim == 1
+        f, jac = self.evaluate(q[None, :], with_jacobian)
+        return f[0], jac[0]
+
+    def dummy_jacobian(self) -> np.ndarray:
+        return np.array([[np.nan]])
+
+    @abstractmethod
+    def _evaluate(self, qs, with_jacobian: bool):
+        ...
+
+    def reflect_skrobot_model(self, robot_model) -> None:
+        self._reflect_skrobot_model(robot_model)
+        self.reflect_robot_flag = True
+
+    @abstractmethod
+    def _reflect_skrobot_model(self, robot_model) -> None:
+        ...
+
+    @classmethod
+    @abstractmethod
+    def is_equality(cls) -> bool:
+        ...
+
+
+class AbstractIneqConst(AbstractConst):
+    @classmethod
+    def is_equality(cls) -> bool:
+        return False
+
+    def is_valid(self, q) -> bool:
+        value, _ = self.evaluate_single(q, False)
+        return bool((value > 0).all())
+
+    def is_valid_batch(self, qs):
+        """all(values > 0) per configuration, for many configurations at once -> (N,) bool."""
+        values, _ = self.evaluate(qs, False)
+        return (values > 0).all(axis=1) if not _is_torch(values) else (values > 0).all(dim=1)
+
+
+class AbstractEqConst(AbstractConst):
+    @classmethod
+    def is_equality(cls) -> bool:
+        return True
+
+    def is_approx_satisfied(self, q, eps: float = 0.01) -> bool:
+        values, _ = self.evaluate_single(q, False)
+        return bool((abs(values) < eps).all())
+
+
+@runtime_checkable
+class VectorDescriptable(Protocol):
+    def get_description(self) -> np.ndarray:
+        ...
+
+
+InnerConstT = TypeVar("InnerConstT", bound=Union[AbstractIneqConst, AbstractEqConst])
+
+
+class _CompositeConst(AbstractConst, Generic[InnerConstT]):
+    const_list: List[InnerConstT]
+
+    def __init__(self, const_list: List[InnerConstT]) -> None:
+        for const in const_list:
+            assert const.is_equality() == self.is_equality()
+        # members already reflected the robot state; dedupe by id keeping first-seen order
+        self.const_list = list({const.id_value: const for const in const_list}.values())
+        self.reflect_robot_flag = True
+        self.assign_id_value()
+
+    def _evaluate(self, qs, with_jacobian: bool):
+        parts = [const.evaluate(qs, with_jacobian=with_jacobian) for const in self.const_list]
+        values = _cat([p[0] for p in parts], axis=1)
+        if not with_jacobian:
+            return values, self.dummy_jacobian()
+        return values, _cat([p[1] for p in parts], axis=1)
+
+    def _reflect_skrobot_model(self, robot_model) -> None:
+        for const in self.const_list:
+            const.reflect_skrobot_model(robot_model)
+
+
+class IneqCompositeConst(AbstractIneqConst, _CompositeConst[AbstractIneqConst]):
+    """Order matters: ``is_valid`` returns at the first violated member."""
+
+    def is_valid(self, q) -> bool:
+        for const in self.const_list:
+            values, _ = const.evaluate_single(q, False)
+            if bool((values < 0.0).any()):
+                return False
+        return True
+
+    def is_valid_batch(self, qs):
+        ok = None
+        for const in self.const_list:
+            values, _ = const.evaluate(qs, False)
+            good = ~((values < 0.0).any(axis=1)) if not _is_torch(values) else ~((values < 0.0).any(dim=1))
+            ok = good if ok is None else (ok & good)
+        return ok
+
+
+class EqCompositeConst(AbstractEqConst, _CompositeConst[AbstractEqConst]):
+    ...
+
+
+class BoxConst(AbstractIneqConst):
+    lb: np.ndarray
+    ub: np.ndarray
+    names: Optional[List[str]]
+
+    def __init__(self, lb: np.ndarray, ub: np.ndarray, names: Optional[List[str]] = None) -> None:
+        self.lb, self.ub = np.asarray(lb, dtype=np.float64), np.asarray(ub, dtype=np.float64)
+        self.names = ["<unnamed>"] * len(self.lb) if names is None else names
+        assert len(self.names) == len(self.lb)
+        self.reflect_skrobot_model(None)
+        self.assign_id_value()
+
+    @classmethod
+    def from_urdf(cls, urdf_path: Path, joint_names: List[str],
+                  base_bounds: Optional[Tuple[np.ndarray, np.ndarray]] = None):
+        joint_map = parse_urdf(Path(urdf_path).expanduser()).joint_map
+        b_min, b_max, names = [], [], list(joint_names)
+        for name in joint_names:
+            lim = joint_map[name].limit
+            b_min.append(-2 * np.pi if lim.lower is None or not np.isfinite(lim.lower) else lim.lower)
+            b_max.append(2 * np.pi if lim.upper is None or not np.isfinite(lim.upper) else lim.upper)
+        if base_bounds is not None:
+            lb, ub = base_bounds
+            assert len(lb) in (3, 6)
+            names += ["x", "y", "z", "roll", "pitch", "yaw"][: len(lb)] if len(lb) == 6 else ["x", "y", "theta"]
+            b_min += list(lb)
+            b_max += list(ub)
+        return cls(np.array(b_min), np.array(b_max), names)
+
+    def _evaluate(self, qs, with_jacobian: bool):
+        n_point, dim = qs.shape
+        lb, ub = _to_kind(qs, self.lb), _to_kind(qs, self.ub)
+        f = _cat([qs - lb, ub - qs], axis=1)
+        if not with_jacobian:
+            return f, self.dummy_jacobian()
+        single = _to_kind(qs, np.vstack((np.eye(dim), -np.eye(dim))))
+        jac = single[None].expand(n_point, -1, -1).clone() if _is_torch(qs) else np.tile(single, (n_point, 1, 1))
+        return f, jac
+
+    def _reflect_skrobot_model(self, robot_model) -> None:
+        pass
+
+    def sample(self) -> np.ndarray:
+        w = self.ub - self.lb
+        return np.random.rand(len(w)) * w + self.lb
+
+
+class CollFreeConst(AbstractIneqConst):
+    """values[n, s] = sdf(x_s(q_n)) - radius_s - distance_margin, one fused FK + SDF kernel launch."""
+
+    colkin: CollSpheresKinematicsMapBase
+    sdf: SignedDistanceFunction
+    only_closest_feature: bool
+    distance_margin: float
+
+    def __init__(self, colkin: CollSpheresKinematicsMapBase, sdf, robot_model,
+                 only_closest_feature: bool = False, distance_margin: float = 0.0) -> None:
+        self.colkin = colkin
+        self.sdf = as_descriptor(sdf)
+        self.reflect_skrobot_model(robot_model)
+        self.only_closest_feature = only_closest_feature
+        self.distance_margin = distance_margin
+        self.assign_id_value()
+
+    def _plan(self):
+        k = self.colkin
+        return k.fksolver.get_plan(k.tinyfk_feature_ids, k.tinyfk_joint_ids, k.base_type, RotationType.IGNORE,
+                                   radii=k.get_radius_list())
+
+    def _run(self, qs, want_vals: bool, with_jacobian: bool, want_valid: bool):
+        assert self.sdf is not None
+        plan = self._plan()
+        b = Batch(qs, plan.dim_cspace)
+        m = 1 if self.only_closest_feature else plan.n_feature
+        vals = b.empty((b.n, m)) if want_vals else None
+        jac = b.empty((b.n, m, plan.dim_cspace)) if with_jacobian else None
+        valid = b.empty_bytes(b.n) if want_valid else None
+        mode = _lib.MODE_CLOSEST if self.only_closest_feature else _lib.MODE_ALL
+        L = _lib.lib()
+        with b.device_ctx():
+            if b.on_device:
+                _lib.check(L.skb_collfree(plan.handle, self.sdf.native(), b.dtype_code, b.q_ptr, b.n,
+                                          float(self.distance_margin), mode, b.ptr(vals), b.ptr(jac), b.ptr(valid), b.stream))
+            else:
+                _lib.check(L.skb_collfree_host(plan.handle, self.sdf.native(), b.dtype_code, b.q_ptr, b.n,
+                                               float(self.distance_margin), mode, b.ptr(vals), b.ptr(jac), b.ptr(valid)))
+        return b, vals, jac, valid
+
+    def _evaluate(self, qs, with_jacobian: bool):
+        b, vals, jac, _ = self._run(qs, True, with_jacobian, False)
+        return b.out(vals), (b.out(jac) if with_jacobian else self.dummy_jacobian())
+
+    def is_valid_batch(self, qs):
+        """Validity bytes straight from the kernel (1 byte per configuration leaves the GPU)."""
+        if not self.reflect_robot_flag:
+            raise RuntimeError("{}: you need to call reflect_skrobot_model beforehand".format(type(self).__name__))
+        b, _, _, valid = self._run(qs, False, False, True)
+        out = b.out(valid)
+        return out.bool() if _is_torch(out) else out.astype(bool)
+
+    def _reflect_skrobot_model(self, robot_model) -> None:
+        assert robot_model, "robot_model must not be None"
+        self.colkin.reflect_skrobot_model(robot_model)
+
+
+class ConfigPointConst(AbstractEqConst):
+    desired_angles: np.ndarray
+
+    def __init__(self, desired_angles: np.ndarray) -> None:
+        self.desired_angles = np.asarray(desired_angles, dtype=np.float64)
+        self.reflect_skrobot_model(None)
+        self.assign_id_value()
+
+    def _evaluate(self, qs, with_jacobian: bool):
+        n_point, dim = qs.shape
+        val = qs - _to_kind(qs, self.desired_angles)
+        if not with_jacobian:
+            return val, self.dummy_jacobian()
+        eye = _to_kind(qs, np.eye(dim))
+        jac = eye[None].expand(n_point, -1, -1).clone() if _is_torch(qs) else np.tile(eye, (n_point, 1, 1))
+        return val, jac
+
+    def _reflect_skrobot_model(self, robot_model) -> None:
+        pass
+
+    def get_description(self) -> np.ndarray:
+        return self.desired_angles
+
+
+class PoseConstraint(AbstractEqConst):
+    """values = flatten(efkin.map(qs)) - hstack(desired_poses): raw component-wise residual, no angle
+    wrapping and no quaternion sign handling, like the reference (:460-461)."""
+
+    efkin: EndEffectorKinematicsMap
+    desired_poses: List[np.ndarray]
+    debug_rank_deficiency: bool = False
+
+    def __init__(self, desired_poses: List[np.ndarray], efkin: EndEffectorKinematicsMap, robot_model,
+                 debug_rank_deficiency: bool = False) -> None:
+        assert len(desired_poses) == efkin.n_feature
+        self.desired_poses = desired_poses
+        self.efkin = efkin
+        self.reflect_skrobot_model(robot_model)
+        self.debug_rank_deficiency = debug_rank_deficiency
+        self.assign_id_value()
+
+    def _evaluate(self, qs, with_jacobian: bool = False):
+        n_point, n_dim = qs.shape
+        xs, jacs = self.efkin.map(qs)       # always with jacobian, like the reference (:455)
+        values = xs.reshape(n_point, -1) - _to_kind(xs, np.hstack(self.desired_poses))
+        jacs = jacs.reshape(n_point, -1, n_dim)
+        if self.debug_rank_deficiency:
+            jn = jacs.cpu().numpy() if _is_torch(jacs) else jacs
+            for jac in jn:
+                rank_diff = jac.shape[0] - np.linalg.matrix_rank(jac)
+                assert rank_diff <= 0, "rank diference: {}, row sums: {}".format(rank_diff, np.sum(jac, axis=1))
+        return values, jacs
+
+    @classmethod
+    def from_skrobot_coords(cls, co_list, efkin: EndEffectorKinematicsMap, robot_model,
+                            debug_rank_deficiency: bool = False) -> "PoseConstraint":
+        vectors = []
+        for co in co_list:
+            pos = co.worldpos()
+            if efkin.rot_type == RotationType.RPY:
+                vectors.append(np.hstack([pos, np.flip(rpy_angle(co.worldrot())[0])]))
+            elif efkin.rot_type == RotationType.XYZW:
+                vectors.append(np.hstack([pos, wxyz2xyzw(matrix2quaternion(co.worldrot()))]))
+            elif efkin.rot_type == RotationType.IGNORE:
+                vectors.append(pos)
+            else:
+                assert False
+        return cls(vectors, efkin, robot_model, debug_rank_deficiency)
+
+    def _reflect_skrobot_model(self, robot_model) -> None:
+        assert robot_model is not None
+        self.efkin.reflect_skrobot_model(robot_model)
+
+    def get_description(self) -> np.ndarray:
+        return np.hstack(self.desired_poses)
+
+
+class RelativePoseConstraint(AbstractEqConst):
+    """Feature 2 must coincide with feature 1 displaced by ``desired_relative_position`` (in feature
+    1's frame).  Works on a private deep copy of ``efkin`` with the displaced point added."""
+
+    desired_relative_position: np.ndarray
+    efkin: EndEffectorKinematicsMap
+
+    def __init__(self, desired_relative_position: np.ndarray, efkin: EndEffectorKinematicsMap, robot_model):
+        efkin = copy.deepcopy(efkin)
+        assert efkin.n_feature == 2
+        efkin.add_new_feature_point(efkin.tinyfk_feature_ids[0], desired_relative_position, None)
+        assert efkin.n_feature == 3
+        self.desired_relative_position = desired_relative_position
+        self.efkin = efkin
+        self.reflect_skrobot_model(robot_model)
+        self.assign_id_value()
+
+    def _evaluate(self, qs, with_jacobian: bool):
+        xs, jacs = self.efkin.map(qs)
+        diffs = xs[:, 1, :] - xs[:, 2, :]
+        if not with_jacobian:
+            return diffs, self.dummy_jacobian()
+        return diffs, jacs[:, 1, :, :] - jacs[:, 2, :, :]
+
+    def _reflect_skrobot_model(self, robot_model) -> None:
+        assert robot_model is not None
+        self.efkin.reflect_skrobot_model(robot_model)
+
+
+class FixedZAxisConstraint(AbstractEqConst):
+    """Keeps each end-effector's local x and y axes horizontal: z(p + x_hat) - z(p) = 0 and
+    z(p + y_hat) - z(p) = 0, via two extra feature points per end effector."""
+
+    efkin: EndEffectorKinematicsMap
+    n_feature: int
+
+    def __init__(self, efkin: EndEffectorKinematicsMap, robot_model):
+        efkin = copy.deepcopy(efkin)
+        base_ids = list(efkin.tinyfk_feature_ids)
+        for fid in base_ids:
+            efkin.add_new_feature_point(fid, np.array([1, 0, 0]), None)
+        for fid in base_ids:
+            efkin.add_new_feature_point(fid, np.array([0, 1, 0]), None)
+        self.n_feature = len(base_ids)
+        self.efkin = efkin
+        self.reflect_skrobot_model(robot_model)
+        self.assign_id_value()
+
+    def _evaluate(self, qs, with_jacobian: bool):
+        n_point, n_dim = qs.shape
+        nf = self.n_feature
+        xs, jacs = self.efkin.map(qs)
+        z = xs[:, :, 2]                                   # (N, 3*nf): origins, +x points, +y points
+        diffs = _cat([z[:, nf:2 * nf] - z[:, :nf], z[:, 2 * nf:] - z[:, :nf]], axis=1)
+        if not with_jacobian:
+            return diffs, self.dummy_jacobian()
+        jz = jacs[:, :, 2, :]                             # (N, 3*nf, D)
+        return diffs, _cat([jz[:, nf:2 * nf] - jz[:, :nf], jz[:, 2 * nf:] - jz[:, :nf]], axis=1)
+
+    def _reflect_skrobot_model(self, robot_model) -> None:
+        assert robot_model is not None
+        self.efkin.reflect_skrobot_model(robot_model)
+
+
+class PairWiseSelfCollFreeConst(AbstractIneqConst):
+    """values[n, p] = |x_i - x_j|^2 - (r_i + r_j)^2 over the checked sphere pairs (squared metres).
+
+    ``check_sphere_id_pairs`` (tinyfk link-id tuples) is the single source of truth for the column
+    order.  With ``id_pairs=None`` every pair is taken except those closer than 3 (r_i + r_j) at
+    q = 0; the reference builds that list through ``list(set(...))`` (:732-733) whose order is
+    unspecified -- here the surviving pairs keep itertools.combinations order.
+    """
+
+    colkin: CollSpheresKinematicsMapBase
+    check_sphere_id_pairs: List[Tuple[int, int]]
+    check_sphere_pair_sqdists: np.ndarray
+    only_closest_feature: bool
+
+    def __init__(self, colkin: CollSpheresKinematicsMapBase, robot_model,
+                 id_pairs: Optional[List[Tuple[int, int]]] = None, only_closest_feature: bool = False) -> None:
+        radius_of = dict(zip(colkin.tinyfk_feature_ids, colkin.get_radius_list()))
+        if id_pairs is None:
+            all_pairs = list(itertools.combinations(colkin.tinyfk_feature_ids, 2))
+            rs = np.array([radius_of[a] + radius_of[b] for a, b in all_pairs])
+            sqdists, _ = colkin.fksolver.compute_inter_link_sqdists(
+                np.zeros((1, colkin.dim_cspace)), all_pairs, colkin.tinyfk_joint_ids, base_type=colkin.base_type)
+            keep = np.sqrt(np.asarray(sqdists)) - 3.0 * rs >= 0
+            id_pairs = [p for p, k in zip(all_pairs, keep) if k]
+            pair_dists = rs[keep]
+        else:
+            id_pairs = [tuple(p) for p in id_pairs]
+            pair_dists = np.array([radius_of[a] + radius_of[b] for a, b in id_pairs])
+        self.colkin = colkin
+        self.check_sphere_id_pairs = id_pairs
+        self.check_sphere_pair_sqdists = pair_dists**2
+        self.reflect_skrobot_model(robot_model)
+        self.only_closest_feature = only_closest_feature
+        self.assign_id_value()
+
+    def _plan(self):
+        k = self.colkin
+        local = {fid: i for i, fid in enumerate(k.tinyfk_feature_ids)}
+        pairs = np.array([[local[a], local[b]] for a, b in self.check_sphere_id_pairs], dtype=np.int32)
+        return k.fksolver.get_plan(k.tinyfk_feature_ids, k.tinyfk_joint_ids, k.base_type, RotationType.IGNORE,
+                                   radii=None, pairs=pairs, pair_sqdists=self.check_sphere_pair_sqdists)
+
+    def _run(self, qs, want_vals: bool, with_jacobian: bool, want_valid: bool):
+        plan = self._plan()
+        b = Batch(qs, plan.dim_cspace)
+        m = 1 if self.only_closest_feature else len(self.check_sphere_id_pairs)
+        vals = b.empty((b.n, m)) if want_vals else None
+        jac = b.empty((b.n, m, plan.dim_cspace)) if with_jacobian else None
+        valid = b.empty_bytes(b.n) if want_valid else None
+        mode = _lib.MODE_CLOSEST if self.only_closest_feature else _lib.MODE_ALL
+        L = _lib.lib()
+        with b.device_ctx():
+            if b.on_device:
+                _lib.check(L.skb_pairwise(plan.handle, b.dtype_code, b.q_ptr, b.n, mode, b.ptr(vals), b.ptr(jac), b.ptr(valid), b.stream))
+            else:
+                _lib.check(L.skb_pairwise_host(plan.handle, b.dtype_code, b.q_ptr, b.n, mode, b.ptr(vals), b.ptr(jac), b.ptr(valid)))
+        return b, vals, jac, valid
+
+    def _evaluate(self, qs, with_jacobian: bool):
+        b, vals, jac, _ = self._run(qs, True, with_jacobian, False)
+        return b.out(vals), (b.out(jac) if with_jacobian else self.dummy_jacobian())
+
+    def is_valid_batch(self, qs):
+        if not self.reflect_robot_flag:
+            raise RuntimeError("{}: you need to call reflect_skrobot_model beforehand".format(type(self).__name__))
+        b, _, _, valid = self._run(qs, False, False, True)
+        out = b.out(valid)
+        return out.bool() if _is_torch(out) else out.astype(bool)
+
+    def _reflect_skrobot_model(self, robot_model) -> None:
+        assert robot_model is not None
+        self.colkin.reflect_skrobot_model(robot_model)

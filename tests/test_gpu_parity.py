@@ -1,0 +1,238 @@
+"""GPU parity: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp32 within 1e-5 relative (scale = max(1, |ref|)), fp64 within
+1e-10; validity identical outside a +-1e-6 m band around 0.  Gradient kinks of the SDF (box medial axis,
+voxel cell faces, union switch-over) are measure-zero sets where fp32 and fp64 may legitimately pick
+different sides; the oracle reports each sample's distance to the nearest kink and samples closer than
+KINK_BAND are excluded from the *Jacobian* comparison only.
+"""
+import numpy as np
+import pytest
+
+from helpers import BASE, ROT, oracle_args, sample_q
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+KINK_BAND = {np.float32: 2e-5, np.float64: 1e-9}
+TOL = {np.float32: 1e-5, np.float64: 1e-10}
+VALID_BAND = 1e-6
+
+
+def close(a, b, tol):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    err = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    return err.max() if err.size else 0.0
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+@pytest.fixture(scope="module")
+def pr2():
+    from skmp_b200.robot_model import PR2
+
+    r = PR2()
+    r.reset_manip_pose()
+    return r
+
+
+def box_scene():
+    from skmp_b200.sdf import Box
+
+    box = Box([0.7, 0.5, 1.2])
+    box.translate([0.85, -0.2, 0.9])
+    return box
+
+
+def run_collfree(const, qs, dtype, device):
+    torch = _torch()
+    if device:
+        q = torch.as_tensor(qs.astype(dtype), device="cuda")
+        v, j = const.evaluate(q, True)
+        torch.cuda.synchronize()
+        return v.cpu().numpy(), j.cpu().numpy()
+    v, j = const.evaluate(qs.astype(dtype), True)
+    return np.asarray(v), np.asarray(j)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("device", [True, False])
+@pytest.mark.parametrize("margin", [0.0, 0.05])
+def test_collfree_box_config1(pr2, dtype, device, margin):
+    """BASELINE config 1: PR2 right arm 7-DoF vs box, 1k random configs, values + Jacobians."""
+    from skmp_b200.constraint import CollFreeConst
+    from skmp_b200.robot.pr2 import PR2Config
+
+    colkin = PR2Config().get_collision_kin()
+    box = box_scene()
+    rng = np.random.default_rng(1)
+    qs = sample_q(colkin, 1000, rng).astype(dtype).astype(np.float64)
+    for closest in (False, True):
+        const = CollFreeConst(colkin, box.sdf, pr2, only_closest_feature=closest, distance_margin=margin)
+        v, j = run_collfree(const, qs, dtype, device)
+        tree, feat, jl, base = oracle_args(colkin)
+        rv, rj, kink = oracle.collfree(tree, qs, feat, jl, oracle.Sdf(box.primitives()), colkin.get_radius_list(),
+                                       margin=margin, only_closest=closest, with_kink=True)
+        assert v.shape == rv.shape and j.shape == rj.shape
+        assert close(v, rv, TOL[dtype]) < TOL[dtype]
+        ok = kink > KINK_BAND[dtype]
+        assert ok.mean() > 0.999
+        assert close(j[ok], rj[ok], TOL[dtype]) < TOL[dtype] * 4
+        band = np.abs(rv) > VALID_BAND
+        assert ((v > 0) == (rv > 0))[band].all()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_validity_bytes(pr2, dtype):
+    from skmp_b200.constraint import CollFreeConst
+    from skmp_b200.robot.pr2 import PR2Config
+
+    torch = _torch()
+    colkin = PR2Config(control_arm="dual").get_collision_kin()
+    box = box_scene()
+    const = CollFreeConst(colkin, box.sdf, pr2)
+    rng = np.random.default_rng(2)
+    qs = sample_q(colkin, 4099, rng).astype(dtype).astype(np.float64)
+    valid = const.is_valid_batch(torch.as_tensor(qs.astype(dtype), device="cuda")).cpu().numpy()
+    tree, feat, jl, base = oracle_args(colkin)
+    rv, _ = oracle.collfree(tree, qs, feat, jl, oracle.Sdf(box.primitives()), colkin.get_radius_list(), with_jacobian=False)
+    decisive = np.abs(rv).min(axis=1) > VALID_BAND
+    assert decisive.mean() > 0.99
+    assert (valid == (rv > 0).all(axis=1))[decisive].all()
+    assert 0.05 < valid.mean() < 0.95          # the scene produces both outcomes
+    for i in range(5):                          # N = 1 path agrees with the batch
+        assert const.is_valid(qs[i].astype(dtype)) == bool(valid[i]) or not decisive[i]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("base_type", ["FIXED", "PLANER", "FLOATING"])
+def test_map_positions(pr2, dtype, base_type):
+    """KinematicsMapBase.map, IGNORE rotation, all base types (whole-body spheres when the base moves)."""
+    from skmp_b200.robot.pr2 import PR2Config
+    from skmp_b200.tinyfk import BaseType
+
+    torch = _torch()
+    kin = PR2Config(control_arm="dual", base_type=BaseType[base_type], use_torso=True).get_collision_kin()
+    kin.reflect_skrobot_model(pr2)
+    rng = np.random.default_rng(3)
+    qs = sample_q(kin, 333, rng).astype(dtype).astype(np.float64)
+    pts, jac = kin.map(torch.as_tensor(qs.astype(dtype), device="cuda"))
+    tree, feat, jl, base = oracle_args(kin)
+    rp, rj = oracle.solve_fk(tree, qs, feat, jl, base)
+    assert pts.shape == rp.shape and jac.shape == rj.shape
+    assert close(pts.cpu().numpy(), rp, TOL[dtype]) < TOL[dtype]
+    assert close(jac.cpu().numpy(), rj, TOL[dtype]) < TOL[dtype]
+    pts2, jac2 = kin.map(qs.astype(dtype), with_jacobian=False)     # host path, no jacobian
+    assert close(pts2, rp, TOL[dtype]) < TOL[dtype] and np.asarray(jac2).size == 0
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("rot", ["IGNORE", "RPY", "XYZW"])
+def test_map_pose_features(pr2, dtype, rot):
+    """EndEffectorKinematicsMap (K4 epilogue): PR2 dual arm fixed base and JAXON floating base."""
+    from skmp_b200.robot.jaxon import JaxonConfig
+    from skmp_b200.robot.pr2 import PR2Config
+    from skmp_b200.robot_model import Jaxon
+    from skmp_b200.tinyfk import RotationType
+
+    torch = _torch()
+    rt = RotationType[rot]
+    jaxon = Jaxon()
+    jaxon.reset_manip_pose()
+    cases = [(PR2Config(control_arm="dual").get_endeffector_kin(rt), pr2, 1.0),
+             (JaxonConfig().get_endeffector_kin(rot_type=rt), jaxon, 0.5)]
+    for kin, robot, scale in cases:
+        kin.reflect_skrobot_model(robot)
+        rng = np.random.default_rng(4)
+        qs = (sample_q(kin, 257, rng) * scale).astype(dtype).astype(np.float64)
+        pts, jac = kin.map(torch.as_tensor(qs.astype(dtype), device="cuda"))
+        tree, feat, jl, base = oracle_args(kin)
+        rp, rj = oracle.solve_fk(tree, qs, feat, jl, base, ROT[rt])
+        tol = TOL[dtype] * (3 if dtype == np.float32 else 1)   # atan2/asin of fp32 rotation entries
+        assert close(pts.cpu().numpy(), rp, tol) < tol
+        assert close(jac.cpu().numpy(), rj, tol) < tol * 3
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_collfree_union_and_grid(pr2, dtype):
+    """Union of rotated primitives, and a voxel-grid SDF (BASELINE config 3 scene at reduced N)."""
+    from skmp_b200.constraint import CollFreeConst
+    from skmp_b200.robot.pr2 import PR2Config
+    from skmp_b200.rotmath import rotation_matrix
+    from skmp_b200.sdf import Box, Cylinder, GridSDF, Sphere, UnionSDF
+
+    colkin = PR2Config(control_arm="dual").get_collision_kin()
+    b1 = box_scene()
+    b2 = Box([0.4, 0.4, 0.3]); b2.translate([0.5, 0.5, 0.6]); b2.rotate_with_matrix(rotation_matrix(0.5, [0.2, 1.0, 0.1]))
+    cy = Cylinder(0.15, 0.8); cy.translate([0.4, -0.6, 1.0]); cy.rotate_with_matrix(rotation_matrix(1.0, [1.0, 0.0, 0.0]))
+    sp = Sphere(0.2, pos=[0.6, 0.0, 1.6])
+    union = UnionSDF([b1, b2, cy, sp])
+    grid = GridSDF.from_sdf(union, lb=[-0.5, -1.5, 0.0], ub=[1.5, 1.5, 2.0], dims=(64, 80, 64), dtype=np.float32)
+    rng = np.random.default_rng(5)
+    qs = sample_q(colkin, 600, rng).astype(dtype).astype(np.float64)
+    tree, feat, jl, base = oracle_args(colkin)
+    for sdf in (union, grid):
+        const = CollFreeConst(colkin, sdf, pr2)
+        v, j = run_collfree(const, qs, dtype, True)
+        rv, rj, kink = oracle.collfree(tree, qs, feat, jl, oracle.Sdf(sdf.primitives()), colkin.get_radius_list(), with_kink=True)
+        tol = TOL[dtype] * (4 if (sdf is grid and dtype == np.float32) else 1)
+        assert close(v, rv, tol) < tol
+        band = KINK_BAND[dtype] * (5 if sdf is grid else 1)
+        ok = kink > band
+        assert ok.mean() > 0.99
+        # trilinear gradient = differences of fp32-interpolated corner values / 3 cm voxels
+        jtol = 2e-4 if (sdf is grid and dtype == np.float32) else tol * 4
+        assert close(j[ok], rj[ok], jtol) < jtol
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_pairwise_fetch_config2(dtype):
+    """BASELINE config 2 at reduced N: Fetch 8-DoF PairWiseSelfCollFreeConst, pair list from the q=0 filter."""
+    from skmp_b200.robot.fetch import FetchConfig
+    from skmp_b200.robot_model import Fetch
+
+    torch = _torch()
+    fetch = Fetch()
+    fetch.reset_pose()
+    conf = FetchConfig()
+    const = conf.get_pairwise_selcol_consts(fetch)
+    colkin = const.colkin
+    P = len(const.check_sphere_id_pairs)
+    assert 100 < P <= 1275
+    v0, _ = const.evaluate_single(np.zeros(8), False)
+    assert (np.asarray(v0) > 0).all()                      # tests/test_constraint.py:178-180
+    rng = np.random.default_rng(6)
+    qs = sample_q(colkin, 500, rng).astype(dtype).astype(np.float64)
+    v, j = const.evaluate(torch.as_tensor(qs.astype(dtype), device="cuda"), True)
+    tree, _, jl, base = oracle_args(colkin)
+    sq, gr = oracle.inter_link_sqdists(tree, qs, np.array(const.check_sphere_id_pairs), jl, base)
+    rv = sq - const.check_sphere_pair_sqdists
+    assert close(v.cpu().numpy(), rv, TOL[dtype]) < TOL[dtype]
+    assert close(j.cpu().numpy(), gr, TOL[dtype]) < TOL[dtype] * 2
+    closest = conf.get_pairwise_selcol_consts(fetch, only_closest_feature=True)
+    closest.check_sphere_id_pairs, closest.check_sphere_pair_sqdists = const.check_sphere_id_pairs, const.check_sphere_pair_sqdists
+    vc, jc = closest.evaluate(qs.astype(dtype), True)
+    idx = rv.argmin(axis=1)
+    assert close(np.asarray(vc)[:, 0], rv.min(axis=1), TOL[dtype]) < TOL[dtype]
+    decided = np.sort(rv, axis=1)[:, 1] - np.sort(rv, axis=1)[:, 0] > 1e-4
+    assert close(np.asarray(jc)[decided, 0], gr[np.arange(len(qs)), idx][decided], TOL[dtype]) < TOL[dtype] * 2
+
+
+def test_min_all_equals_closest(pr2):
+    """tests/test_constraint.py:85-89: np.min(values_all) == value_closest, exact."""
+    from skmp_b200.constraint import CollFreeConst
+    from skmp_b200.robot.pr2 import PR2Config
+
+    torch = _torch()
+    colkin = PR2Config().get_collision_kin()
+    box = box_scene()
+    a = CollFreeConst(colkin, box.sdf, pr2, only_closest_feature=False, distance_margin=0.05)
+    c = CollFreeConst(colkin, box.sdf, pr2, only_closest_feature=True, distance_margin=0.05)
+    q = torch.randn(777, 7, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    va, _ = a.evaluate(q, False)
+    vc, _ = c.evaluate(q, False)
+    assert torch.equal(va.min(dim=1).values, vc[:, 0])
