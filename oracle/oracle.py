@@ -185,12 +185,27 @@ def collfree(tree: Tree, qs, feat_ids, joint_links, sdf: Sdf, radii, margin=0.0,
     return (vals, jac, kink) if with_kink else (vals, jac)
 
 
-def collfree_threaded(n_threads: int, tree: Tree, qs, *args, **kw):
-    """Shard rows over ``n_threads`` host threads (ctypes releases the GIL): the all-cores CPU baseline."""
+def collfree_threaded(n_threads: int, tree: Tree, qs, *args, keep: bool = True, block: int = 2048, **kw):
+    """Shard rows over ``n_threads`` host threads (ctypes releases the GIL): the all-cores CPU baseline.
+    With keep=False each thread walks its shard in blocks and drops the outputs (timing only; a 1M-config
+    Jacobian set would not fit in host memory), returning the number of rows processed."""
     qs = np.ascontiguousarray(qs, dtype=np.float64)
-    if n_threads <= 1 or len(qs) < 2 * n_threads:
-        return collfree(tree, qs, *args, **kw)
-    shards = np.array_split(qs, n_threads)
-    with ThreadPoolExecutor(n_threads) as ex:
-        parts = list(ex.map(lambda s: collfree(tree, s, *args, **kw), shards))
+    shards = np.array_split(qs, max(1, n_threads))
+
+    def work(shard):
+        if keep:
+            return collfree(tree, shard, *args, **kw)
+        done = 0
+        for i in range(0, len(shard), block):
+            collfree(tree, shard[i:i + block], *args, **kw)
+            done += len(shard[i:i + block])
+        return done
+
+    if n_threads <= 1:
+        parts = [work(qs)]
+    else:
+        with ThreadPoolExecutor(n_threads) as ex:
+            parts = list(ex.map(work, shards))
+    if not keep:
+        return int(sum(parts))
     return tuple(np.concatenate([p[i] for p in parts], axis=0) for i in range(len(parts[0])))

@@ -14,7 +14,7 @@ from oracle import oracle
 
 pytestmark = pytest.mark.gpu
 
-KINK_BAND = {np.float32: 2e-5, np.float64: 1e-9}
+KINK_BAND = {np.float32: 2e-5, np.float64: 1e-9}   # metres
 TOL = {np.float32: 1e-5, np.float64: 1e-10}
 VALID_BAND = 1e-6
 
@@ -181,7 +181,7 @@ def test_collfree_union_and_grid(pr2, dtype):
         rv, rj, kink = oracle.collfree(tree, qs, feat, jl, oracle.Sdf(sdf.primitives()), colkin.get_radius_list(), with_kink=True)
         tol = TOL[dtype] * (4 if (sdf is grid and dtype == np.float32) else 1)
         assert close(v, rv, tol) < tol
-        band = KINK_BAND[dtype] * (5 if sdf is grid else 1)
+        band = KINK_BAND[dtype]
         ok = kink > band
         assert ok.mean() > 0.99
         # trilinear gradient = differences of fp32-interpolated corner values / 3 cm voxels
