@@ -113,6 +113,11 @@ int skb_fk(const skb_plan *p, int32_t dtype, const void *q_dev, int64_t N, int32
            void *out_jac_dev, void *stream) {
     if (!p || N < 0 || (N > 0 && (!q_dev || !out_pts_dev))) return set_error("fk: bad arguments");
     if (with_jacobian && !out_jac_dev) return set_error("fk: with_jacobian set but out_jac is NULL");
+    if (p->rot_type == SKB_ROT_IGNORE) {   // point features: lane-per-feature kernel (skb_sphere.cu)
+        const skb_sphere_program *sp = get_sphere_program(const_cast<skb_plan *>(p));
+        if (sp) return launch_sphere(p, sp, KIND_MAP, dtype, q_dev, N, nullptr, nullptr, 0, 0.0, SKB_MODE_ALL, out_pts_dev,
+                                     with_jacobian ? out_jac_dev : nullptr, nullptr, stream);
+    }
     const skb_schedule *sch = get_schedule(const_cast<skb_plan *>(p), p->T);
     if (!sch) return -1;
     return launch_tree(p, sch, KIND_MAP, dtype, q_dev, N, nullptr, 0, 0.0, SKB_MODE_ALL, out_pts_dev,
@@ -126,10 +131,13 @@ int skb_collfree(const skb_plan *p, const skb_sdf *s, int32_t dtype, const void 
     if (s->prims.empty()) return set_error("collfree: the SDF has no primitive");
     if (p->rot_type != SKB_ROT_IGNORE) return set_error("collfree: the plan must be built with rot_type IGNORE");
     if (s->prims.size() > 64) return set_error("collfree: more than 64 SDF primitives");
-    const skb_schedule *sch = get_schedule(const_cast<skb_plan *>(p), 1);
-    if (!sch) return -1;
     const void *dp = get_dev_prims(const_cast<skb_sdf *>(s), dtype);
     if (!dp) return -1;
+    if (const skb_sphere_program *sp = get_sphere_program(const_cast<skb_plan *>(p)))
+        return launch_sphere(p, sp, KIND_COLLFREE, dtype, q_dev, N, dp, get_host_prims(s, dtype), (int)s->prims.size(), margin, mode, out_vals_dev,
+                             out_jac_dev, out_valid_dev, stream);
+    const skb_schedule *sch = get_schedule(const_cast<skb_plan *>(p), 1);
+    if (!sch) return -1;
     return launch_tree(p, sch, KIND_COLLFREE, dtype, q_dev, N, dp, (int)s->prims.size(), margin, mode, out_vals_dev,
                        out_jac_dev, out_valid_dev, stream);
 }

@@ -88,6 +88,18 @@ __device__ __forceinline__ T grid_fetch(const void *grid, bool f64, int64_t idx)
     return (T)__ldg(reinterpret_cast<const float *>(grid) + idx);
 }
 
+// 32-byte gather of one cell's corner pack (sm_100: LDG.E.256, one L1 wavefront per lane)
+__device__ __forceinline__ void ldg_cell(const float *p, float c[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3]), "=f"(c[4]), "=f"(c[5]), "=f"(c[6]), "=f"(c[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void ldg_cell(const double *p, double c[8]) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + 2), e = __ldg(q + 3);
+    c[0] = a.x; c[1] = a.y; c[2] = b.x; c[3] = b.y; c[4] = d.x; c[5] = d.y; c[6] = e.x; c[7] = e.y;
+}
+
 // trilinear voxel grid: value + analytic gradient; `fill`, zero gradient outside the sample box
 template <typename T>
 __device__ __forceinline__ T sdf_grid_local(const DevPrim<T> &pr, T x, T y, T z, T &gx, T &gy, T &gz) {
@@ -102,13 +114,27 @@ __device__ __forceinline__ T sdf_grid_local(const DevPrim<T> &pr, T x, T y, T z,
     int iy = min((int)R::floor(uy), pr.dims[1] - 2);
     int iz = min((int)R::floor(uz), pr.dims[2] - 2);
     const T fx = ux - T(ix), fy = uy - T(iy), fz = uz - T(iz);
-    const int64_t sy = pr.dims[2], sx = (int64_t)pr.dims[1] * pr.dims[2];
-    const int64_t b = ix * sx + iy * sy + iz;
     const bool f64 = (pr.flags & PF_GRID_F64) != 0;
-    const T c000 = grid_fetch<T>(pr.grid, f64, b), c001 = grid_fetch<T>(pr.grid, f64, b + 1);
-    const T c010 = grid_fetch<T>(pr.grid, f64, b + sy), c011 = grid_fetch<T>(pr.grid, f64, b + sy + 1);
-    const T c100 = grid_fetch<T>(pr.grid, f64, b + sx), c101 = grid_fetch<T>(pr.grid, f64, b + sx + 1);
-    const T c110 = grid_fetch<T>(pr.grid, f64, b + sx + sy), c111 = grid_fetch<T>(pr.grid, f64, b + sx + sy + 1);
+    T c000, c001, c010, c011, c100, c101, c110, c111;
+    if (pr.flags & PF_GRID_CELLS) {
+        const int64_t cell = ((int64_t)ix * (pr.dims[1] - 1) + iy) * (pr.dims[2] - 1) + iz;
+        if (f64) {
+            double c[8];
+            ldg_cell(reinterpret_cast<const double *>(pr.cells) + cell * 8, c);
+            c000 = (T)c[0]; c001 = (T)c[1]; c010 = (T)c[2]; c011 = (T)c[3]; c100 = (T)c[4]; c101 = (T)c[5]; c110 = (T)c[6]; c111 = (T)c[7];
+        } else {
+            float c[8];
+            ldg_cell(reinterpret_cast<const float *>(pr.cells) + cell * 8, c);
+            c000 = (T)c[0]; c001 = (T)c[1]; c010 = (T)c[2]; c011 = (T)c[3]; c100 = (T)c[4]; c101 = (T)c[5]; c110 = (T)c[6]; c111 = (T)c[7];
+        }
+    } else {
+        const int64_t sy = pr.dims[2], sx = (int64_t)pr.dims[1] * pr.dims[2];
+        const int64_t b = ix * sx + iy * sy + iz;
+        c000 = grid_fetch<T>(pr.grid, f64, b); c001 = grid_fetch<T>(pr.grid, f64, b + 1);
+        c010 = grid_fetch<T>(pr.grid, f64, b + sy); c011 = grid_fetch<T>(pr.grid, f64, b + sy + 1);
+        c100 = grid_fetch<T>(pr.grid, f64, b + sx); c101 = grid_fetch<T>(pr.grid, f64, b + sx + 1);
+        c110 = grid_fetch<T>(pr.grid, f64, b + sx + sy); c111 = grid_fetch<T>(pr.grid, f64, b + sx + sy + 1);
+    }
     // lerp along x, then y, then z (same association as the oracle)
     const T c00 = c000 + fx * (c100 - c000), c01 = c001 + fx * (c101 - c001);
     const T c10 = c010 + fx * (c110 - c010), c11 = c011 + fx * (c111 - c011);
@@ -123,36 +149,42 @@ __device__ __forceinline__ T sdf_grid_local(const DevPrim<T> &pr, T x, T y, T z,
     return val;
 }
 
+// one primitive: world point -> distance + WORLD gradient
+template <typename T>
+__device__ __forceinline__ T sdf_prim_world(const DevPrim<T> &pr, T px, T py, T pz, T &gx, T &gy, T &gz) {
+    T dx = px - pr.pos[0], dy = py - pr.pos[1], dz = pz - pr.pos[2];
+    T lx, ly, lz;
+    const bool ident = (pr.flags & PF_IDENTITY) != 0;
+    if (ident) { lx = dx; ly = dy; lz = dz; }
+    else {   // local = R^T d
+        lx = pr.rot[0] * dx + pr.rot[3] * dy + pr.rot[6] * dz;
+        ly = pr.rot[1] * dx + pr.rot[4] * dy + pr.rot[7] * dz;
+        lz = pr.rot[2] * dx + pr.rot[5] * dy + pr.rot[8] * dz;
+    }
+    T ax, ay, az, d;
+    if (pr.type == PRIM_BOX) d = sdf_box_local<T>(pr.par, lx, ly, lz, ax, ay, az);
+    else if (pr.type == PRIM_GRID) d = sdf_grid_local<T>(pr, lx, ly, lz, ax, ay, az);
+    else if (pr.type == PRIM_CYLINDER) d = sdf_cylinder_local<T>(pr.par[0], pr.par[1], lx, ly, lz, ax, ay, az);
+    else d = sdf_sphere_local<T>(pr.par[0], lx, ly, lz, ax, ay, az);
+    if (ident) { gx = ax; gy = ay; gz = az; }
+    else {
+        gx = pr.rot[0] * ax + pr.rot[1] * ay + pr.rot[2] * az;
+        gy = pr.rot[3] * ax + pr.rot[4] * ay + pr.rot[5] * az;
+        gz = pr.rot[6] * ax + pr.rot[7] * ay + pr.rot[8] * az;
+    }
+    return d;
+}
+
 // union (min) of primitives: world point -> distance + world gradient of the closest primitive
+// (first index wins ties, like np.argmin over the members)
 template <typename T>
 __device__ __forceinline__ T sdf_union(const DevPrim<T> *prims, int np, T px, T py, T pz, T &gx, T &gy, T &gz) {
     T best = Real<T>::inf();
     gx = gy = gz = T(0);
     for (int i = 0; i < np; ++i) {
-        const DevPrim<T> &pr = prims[i];
-        T dx = px - pr.pos[0], dy = py - pr.pos[1], dz = pz - pr.pos[2];
-        T lx, ly, lz;
-        const bool ident = (pr.flags & PF_IDENTITY) != 0;
-        if (ident) { lx = dx; ly = dy; lz = dz; }
-        else {   // local = R^T d
-            lx = pr.rot[0] * dx + pr.rot[3] * dy + pr.rot[6] * dz;
-            ly = pr.rot[1] * dx + pr.rot[4] * dy + pr.rot[7] * dz;
-            lz = pr.rot[2] * dx + pr.rot[5] * dy + pr.rot[8] * dz;
-        }
-        T ax, ay, az, d;
-        if (pr.type == PRIM_BOX) d = sdf_box_local<T>(pr.par, lx, ly, lz, ax, ay, az);
-        else if (pr.type == PRIM_GRID) d = sdf_grid_local<T>(pr, lx, ly, lz, ax, ay, az);
-        else if (pr.type == PRIM_CYLINDER) d = sdf_cylinder_local<T>(pr.par[0], pr.par[1], lx, ly, lz, ax, ay, az);
-        else d = sdf_sphere_local<T>(pr.par[0], lx, ly, lz, ax, ay, az);
-        if (d < best) {
-            best = d;
-            if (ident) { gx = ax; gy = ay; gz = az; }
-            else {
-                gx = pr.rot[0] * ax + pr.rot[1] * ay + pr.rot[2] * az;
-                gy = pr.rot[3] * ax + pr.rot[4] * ay + pr.rot[5] * az;
-                gz = pr.rot[6] * ax + pr.rot[7] * ay + pr.rot[8] * az;
-            }
-        }
+        T ax, ay, az;
+        const T d = sdf_prim_world<T>(prims[i], px, py, pz, ax, ay, az);
+        if (d < best) { best = d; gx = ax; gy = ay; gz = az; }
     }
     return best;
 }

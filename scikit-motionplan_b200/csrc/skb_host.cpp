@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 
@@ -540,6 +541,121 @@ const skb_pair_program *get_pair_program(skb_plan *p) {
     return &pp;
 }
 
+
+// ------------------------------------------------------------------ sphere program (skb_sphere.cu)
+static int odd_quads(int words) {   // round up to a multiple of 4 words whose quotient is odd (bank-conflict-free rows)
+    int q = (words + 3) / 4;
+    if (q % 2 == 0) q += 1;
+    return q * 4;
+}
+
+static int build_sphere_program(skb_plan *p, skb_sphere_program *sp) {
+    sp->built = true;
+    sp->supported = false;
+    const int n_nodes = (int)p->nodes.size(), nf = p->F, D = p->D;
+    if (p->rot_type != SKB_ROT_IGNORE || D > 64 || D < 1 || n_nodes > 255 || nf > 32 * 32) return 0;
+    // levels: node 0 (world) is level 0, a movable node with di controlled ancestors is level di + 1
+    int n_levels = 0;
+    std::vector<int> level(n_nodes, 0);
+    for (int k = 0; k < n_nodes; ++k) {
+        level[k] = p->nodes[k].parent < 0 ? 0 : level[p->nodes[k].parent] + 1;
+        n_levels = std::max(n_levels, level[k] + 1);
+    }
+    std::vector<std::vector<int>> lv(n_levels);
+    for (int k = 0; k < n_nodes; ++k) lv[level[k]].push_back(k);
+    int max_level_nodes = 0;
+    for (auto &l : lv) max_level_nodes = std::max(max_level_nodes, (int)l.size());
+    // ancestor column masks per node
+    std::vector<uint64_t> nmask(n_nodes, 0);
+    for (int k = 1; k < n_nodes; ++k) {
+        nmask[k] = nmask[p->nodes[k].parent];
+        if (p->nodes[k].col >= 0) nmask[k] |= (uint64_t)1 << p->nodes[k].col;
+    }
+    const int n_rounds = (nf + 31) / 32;
+    std::vector<int32_t> &I = sp->I;
+    std::vector<double> &Fv = sp->F;
+    I.assign(SHDR_WORDS, 0);
+    I[S_N_NODES] = n_nodes; I[S_N_LEVELS] = n_levels; I[S_N_ROUNDS] = n_rounds; I[S_D] = D; I[S_N_FEAT] = nf;
+    I[S_MAX_LEVEL_NODES] = max_level_nodes;
+    sp->frame_stride = odd_quads(n_nodes * 12);
+    sp->tw_stride = odd_quads(D * 8);
+    I[S_FRAME_STRIDE] = sp->frame_stride; I[S_TW_STRIDE] = sp->tw_stride;
+    I[S_NODE_I] = (int)I.size();
+    for (int k = 0; k < n_nodes; ++k) {
+        I.push_back(p->nodes[k].type); I.push_back(p->nodes[k].col); I.push_back(p->nodes[k].parent); I.push_back(0);
+    }
+    I[S_LEVEL_I] = (int)I.size();
+    int cursor = 0;
+    for (auto &l : lv) { I.push_back(cursor); I.push_back((int)l.size()); cursor += (int)l.size(); }
+    I[S_LEVELNODE_I] = (int)I.size();
+    for (auto &l : lv) for (int k : l) I.push_back(k);
+    while (I.size() % 4) I.push_back(0);
+    I[S_ROUND_I] = (int)I.size();
+    for (int r = 0; r < n_rounds; ++r) {
+        const int s0 = r * 32, cnt = std::min(32, nf - s0);
+        uint64_t cm = 0;
+        for (int f = s0; f < s0 + cnt; ++f) cm |= nmask[p->feat_node[f]];
+        I.push_back(s0); I.push_back(cnt); I.push_back((int32_t)(uint32_t)(cm & 0xffffffffu)); I.push_back((int32_t)(uint32_t)(cm >> 32));
+    }
+    I[S_TABB_I] = (int)I.size();
+    for (int r = 0; r < n_rounds; ++r)
+        for (int l = 0; l < 32; ++l) {
+            const int f = r * 32 + l;
+            if (f < nf) {
+                const uint64_t am = nmask[p->feat_node[f]];
+                I.push_back(p->feat_node[f]); I.push_back((int32_t)(uint32_t)(am & 0xffffffffu));
+                I.push_back((int32_t)(uint32_t)(am >> 32)); I.push_back(1);
+            } else { I.push_back(0); I.push_back(0); I.push_back(0); I.push_back(0); }
+        }
+    I[S_I_TOTAL] = (int)I.size();
+    Fv.clear();
+    I[S_NODE_F] = 0;
+    for (int k = 0; k < n_nodes; ++k) {
+        double R[9];
+        quat_to_matrix(p->nodes[k].pre.q, R);
+        for (int r = 0; r < 3; ++r) { Fv.push_back(R[3 * r]); Fv.push_back(R[3 * r + 1]); Fv.push_back(R[3 * r + 2]); Fv.push_back(p->nodes[k].pre.t[r]); }
+    }
+    I[S_TABA_F] = (int)Fv.size();
+    for (int r = 0; r < n_rounds; ++r)
+        for (int l = 0; l < 32; ++l) {
+            const int f = r * 32 + l;
+            if (f < nf) { for (int j = 0; j < 3; ++j) Fv.push_back(p->feat_off[f].t[j]); Fv.push_back(p->radii[f]); }
+            else { for (int j = 0; j < 4; ++j) Fv.push_back(0.0); }
+        }
+    I[S_F_TOTAL] = (int)Fv.size();
+    sp->n_nodes = n_nodes; sp->n_levels = n_levels; sp->n_rounds = n_rounds;
+    sp->supported = true;
+    return 0;
+}
+
+static void free_sphere(skb_sphere_program &sp) {
+    if (sp.dI) cudaFree(sp.dI);
+    if (sp.dF32) cudaFree(sp.dF32);
+    if (sp.dF64) cudaFree(sp.dF64);
+    sp = skb_sphere_program();
+}
+
+const skb_sphere_program *get_sphere_program(skb_plan *p) {
+    std::lock_guard<std::mutex> lk(p->mu);
+    skb_sphere_program &sp = p->sphere;
+    if (!sp.built) {
+        const char *force = getenv("SKB_KERNEL");
+        if (force && std::string(force) == "tree") { sp.built = true; sp.supported = false; }
+        else if (build_sphere_program(p, &sp) != 0) return nullptr;
+    }
+    if (!sp.supported) return nullptr;
+    if (!sp.dI) {
+        if (cudaMalloc(&sp.dI, sp.I.size() * sizeof(int32_t)) != cudaSuccess ||
+            cudaMemcpy(sp.dI, sp.I.data(), sp.I.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("sphere program upload failed (no CUDA device?)");
+            sp.dI = nullptr;
+            return nullptr;
+        }
+        if (upload_reals<float>(sp.F, &sp.dF32) != 0 || upload_reals<double>(sp.F, &sp.dF64) != 0) return nullptr;
+    }
+    return &sp;
+}
+
 template <typename T>
 static int upload_prims(skb_sdf *s, void **dst) {
     std::vector<DevPrim<T>> v(s->prims.size() ? s->prims.size() : 1);
@@ -553,7 +669,8 @@ static int upload_prims(skb_sdf *s, void **dst) {
             d.rot[k] = (T)h.rot[k];
             if (fabs(h.rot[k] - ((k % 4 == 0) ? 1.0 : 0.0)) > 0) ident = false;
         }
-        d.flags = (ident ? PF_IDENTITY : 0) | (h.grid_is_f64 ? PF_GRID_F64 : 0);
+        d.flags = (ident ? PF_IDENTITY : 0) | (h.grid_is_f64 ? PF_GRID_F64 : 0) | (h.dev_cells ? PF_GRID_CELLS : 0);
+        d.cells = h.dev_cells;
         for (int k = 0; k < 3; ++k) { d.pos[k] = (T)h.pos[k]; d.dims[k] = h.dims[k]; }
         for (int k = 0; k < 8; ++k) d.par[k] = (T)h.par[k];
         if (h.type == PRIM_GRID) for (int k = 0; k < 3; ++k) d.par[3 + k] = (T)(1.0 / h.par[3 + k]);
@@ -561,8 +678,12 @@ static int upload_prims(skb_sdf *s, void **dst) {
     }
     CUDA_OK(cudaMalloc(dst, v.size() * sizeof(DevPrim<T>)));
     CUDA_OK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(DevPrim<T>), cudaMemcpyHostToDevice));
+    std::vector<unsigned char> &hc = sizeof(T) == 4 ? s->host_f32 : s->host_f64;
+    hc.assign(reinterpret_cast<unsigned char *>(v.data()), reinterpret_cast<unsigned char *>(v.data()) + v.size() * sizeof(DevPrim<T>));
     return 0;
 }
+
+const void *get_host_prims(const skb_sdf *s, int dtype) { return dtype == SKB_F32 ? (const void *)s->host_f32.data() : (const void *)s->host_f64.data(); }
 
 const void *get_dev_prims(skb_sdf *s, int dtype) {
     if (s->dev_count != (int)s->prims.size()) {
@@ -721,6 +842,23 @@ int skb_sdf_add_grid(skb_sdf *s, const double pos[3], const double rot[9], const
     h.grid_bytes = count * (h.grid_is_f64 ? 8 : 4);
     CUDA_OK(cudaMalloc(&h.dev_grid, h.grid_bytes));
     CUDA_OK(cudaMemcpy(h.dev_grid, host_values, h.grid_bytes, cudaMemcpyHostToDevice));
+    // corner-packed copy: one 32-byte (fp32) gather per trilinear lookup instead of eight 4-byte ones.
+    // 8x the grid's memory, so only while it stays within SKB_GRID_CELLS_MAX_MB (default 1024 MB); SKB_GRID_CELLS=0 disables.
+    {
+        const char *en = getenv("SKB_GRID_CELLS");
+        const char *mx = getenv("SKB_GRID_CELLS_MAX_MB");
+        const double max_mb = mx ? atof(mx) : 1024.0;
+        const size_t n_cells = (size_t)(dims[0] - 1) * (dims[1] - 1) * (dims[2] - 1);
+        const size_t cell_bytes = n_cells * 8 * (h.grid_is_f64 ? 8 : 4);
+        if (!(en && en[0] == '0') && cell_bytes <= (size_t)(max_mb * 1048576.0)) {
+            if (cudaMalloc(&h.dev_cells, cell_bytes) == cudaSuccess) {
+                if (launch_expand_cells(h.dev_grid, h.grid_is_f64, dims, h.dev_cells) != 0) { cudaFree(h.dev_cells); h.dev_cells = nullptr; }
+            } else {
+                h.dev_cells = nullptr;
+                cudaGetLastError();
+            }
+        }
+    }
     s->prims.push_back(h);
     return 0;
 }
@@ -733,7 +871,7 @@ int skb_sdf_num_prims(const skb_sdf *s, int32_t *out) {
 
 void skb_sdf_destroy(skb_sdf *s) {
     if (!s) return;
-    for (auto &h : s->prims) if (h.dev_grid) cudaFree(h.dev_grid);
+    for (auto &h : s->prims) { if (h.dev_grid) cudaFree(h.dev_grid); if (h.dev_cells) cudaFree(h.dev_cells); }
     if (s->dev_f32) cudaFree(s->dev_f32);
     if (s->dev_f64) cudaFree(s->dev_f64);
     delete s;
@@ -762,6 +900,7 @@ int skb_plan_dims(const skb_plan *p, int32_t *D, int32_t *F, int32_t *T) {
 static void drop_schedules(skb_plan *p) {
     for (auto &kv : p->schedules) free_schedule(kv.second);
     p->schedules.clear();
+    free_sphere(p->sphere);
 }
 static void drop_pairs(skb_plan *p) {
     if (p->pairs.dI) cudaFree(p->pairs.dI);

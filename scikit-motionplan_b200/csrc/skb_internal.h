@@ -61,10 +61,12 @@ struct DevPrim {
     T pos[3];
     T rot[9];
     T par[8];            // box: half[3]; cyl: radius, half height; sphere: radius; grid: lb[3], inv_spacing[3], fill
-    const void *grid;    // device pointer (float or double values)
+    const void *grid;    // device pointer (float or double values), C order [nx][ny][nz]
+    const void *cells;   // device pointer or NULL: per-cell corner packs [(nx-1)][(ny-1)][(nz-1)][8]
+                         // {c000,c001,c010,c011,c100,c101,c110,c111} (cXYZ), same value type as `grid`
 };
 enum { PRIM_BOX = 0, PRIM_CYLINDER = 1, PRIM_SPHERE = 2, PRIM_GRID = 3 };
-enum { PF_IDENTITY = 1, PF_GRID_F64 = 2 };
+enum { PF_IDENTITY = 1, PF_GRID_F64 = 2, PF_GRID_CELLS = 4 };
 
 struct Xf {              // rigid transform, quaternion (x,y,z,w) + translation, host fp64
     double q[4];
@@ -87,6 +89,7 @@ struct skb_host_prim {
     int32_t dims[3];
     double pos[3], rot[9], par[8];
     void *dev_grid = nullptr;
+    void *dev_cells = nullptr;       // corner-packed copy (one 32/64-byte gather per lookup), may be NULL
     int32_t grid_is_f64 = 0;
     size_t grid_bytes = 0;
 };
@@ -97,6 +100,7 @@ struct skb_sdf {
     // device copies of the primitive table, built lazily per dtype
     void *dev_f32 = nullptr;
     void *dev_f64 = nullptr;
+    std::vector<unsigned char> host_f32, host_f64;   // host copies of the same DevPrim tables
     int dev_count = -1;
 };
 
@@ -121,6 +125,30 @@ struct skb_pair_program {
     int n_nodes = 0;
 };
 
+// sphere program (skb_sphere.cu): the fused FK + SDF + Jacobian kernel for point features.
+// Phase 1 walks the tree level by level (lane = (configuration, node of the level)), phase 2 assigns
+// one lane per sphere ("round" = up to 32 consecutive output spheres of one configuration).
+//   I: header (enum SHdr) | node records (4 ints) | level records (2) | level node lists |
+//      round records (4) | per-round lane table B: int4 {node, amask_lo, amask_hi, valid}
+//   F: node pre-transforms as 3 rows [R_r0 R_r1 R_r2 t_r] (12) | per-round lane table A: {off xyz, radius}
+enum SHdr {
+    S_N_NODES = 0, S_N_LEVELS, S_N_ROUNDS, S_D, S_N_FEAT, S_FRAME_STRIDE, S_TW_STRIDE,
+    S_NODE_I, S_LEVEL_I, S_LEVELNODE_I, S_ROUND_I, S_TABB_I, S_I_TOTAL,
+    S_NODE_F, S_TABA_F, S_F_TOTAL, S_MAX_LEVEL_NODES,
+    SHDR_WORDS = 20
+};
+
+struct skb_sphere_program {
+    std::vector<int32_t> I;
+    std::vector<double> F;
+    void *dI = nullptr;
+    void *dF32 = nullptr;
+    void *dF64 = nullptr;
+    int n_nodes = 0, n_levels = 0, n_rounds = 0;
+    int frame_stride = 0, tw_stride = 0;     // elements of T per configuration
+    bool built = false, supported = false;
+};
+
 struct skb_stream_ctx;           // host-pipeline scratch (skb_hostpipe.cpp)
 
 struct skb_plan {
@@ -142,6 +170,7 @@ struct skb_plan {
     int tune_chunk = 0, tune_nbuf = 0, tune_warps = 0, tune_ctas = 0;
     std::map<int, skb_schedule> schedules;   // keyed by rows-per-feature
     skb_pair_program pairs;
+    skb_sphere_program sphere;
     bool pairs_set = false;
     std::vector<int32_t> pair_idx;
     std::vector<double> pair_thr;
@@ -154,7 +183,9 @@ namespace skb {
 int set_error(const std::string &msg);           // returns -1
 const skb_schedule *get_schedule(skb_plan *p, int rows);   // builds + uploads lazily; nullptr on error
 const skb_pair_program *get_pair_program(skb_plan *p);
+const skb_sphere_program *get_sphere_program(skb_plan *p);   // nullptr when the plan is not eligible (not an error)
 const void *get_dev_prims(skb_sdf *s, int dtype);
+const void *get_host_prims(const skb_sdf *s, int dtype);   // valid after get_dev_prims succeeded for that dtype
 
 // kernel launchers (skb_kernels.cu)
 int launch_tree(const skb_plan *p, const skb_schedule *sch, int kind, int dtype, const void *q, int64_t N,
@@ -164,6 +195,11 @@ int launch_pairwise(const skb_plan *p, const skb_pair_program *pp, int dtype, co
                     void *out_vals, void *out_jac, uint8_t *out_valid, void *stream);
 int launch_sdf_eval(const void *dev_prims, int n_prims, int dtype, const void *pts, int64_t M, void *out_vals,
                     void *out_grads, void *stream);
+// skb_sphere.cu
+int launch_sphere(const skb_plan *p, const skb_sphere_program *sp, int kind, int dtype, const void *q, int64_t N,
+                  const void *dev_prims, const void *host_prims, int n_prims, double margin, int mode, void *out_vals,
+                  void *out_jac, uint8_t *out_valid, void *stream);
+int launch_expand_cells(const void *grid, int is_f64, const int32_t dims[3], void *cells);
 enum { KIND_MAP = 0, KIND_COLLFREE = 1 };
 
 extern int64_t g_launch_count;

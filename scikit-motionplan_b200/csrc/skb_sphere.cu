@@ -1,0 +1,558 @@
+// skb_sphere.cu -- the fused FK + SDF + Jacobian kernel for point features (collision spheres).
+//
+//   sphere_kernel<T, KIND, WITH_JAC, VW>
+//     KIND_COLLFREE  K1+K2: CollFreeConst._evaluate            (skmp/constraint.py:287-374)
+//     KIND_MAP       K1:    KinematicsMapBase.map, IGNORE rot  (skmp/kinematics.py:43-63)
+//
+// Execution model: one warp owns a tile of G configurations (G = 4..32, chosen from the
+// shared-memory budget) and runs two phases per tile without any block-level barrier.
+//
+//   phase 1  forward kinematics, level by level: lane = (configuration, node of the level).  A lane
+//            composes  parent frame x constant pre-transform x Rz(q)/Tz(q)  (every joint axis is
+//            folded onto +z by the plan compiler) and stores the node frame [R|t] plus the joint's
+//            spatial twist (omega, v = o x omega) in the warp's shared-memory slab.
+//   phase 2  one lane per sphere: a "round" is up to 32 consecutive output spheres of ONE
+//            configuration.  The lane transforms its sphere centre, evaluates the world SDF (value
+//            + analytic gradient; voxel grids through one 32-byte corner-pack gather), forms the
+//            wrench (p x g, g) and contracts it with the twists of all D columns
+//                 J[s][d] = omega_d . (p x g) + v_d . g     if joint d is an ancestor of s, else 0
+//            (twists are warp-broadcast shared loads, so the contraction is warp-amortised).  Rows
+//            are assembled in registers, staged as the dense [cnt][D] block that IS the output
+//            layout, and shipped with coalesced 16-byte streaming stores (evict-first, so the
+//            write stream does not evict the L2-resident grid).  Sphere centres and per-sphere rows
+//            never round-trip through HBM.
+//   closest / validity: warp-shuffle min / arg-min over the spheres of a configuration.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "skb_device.cuh"
+#include "skb_internal.h"
+
+namespace skb {
+
+enum { MAX_ROUNDS = 32 };
+
+template <typename T>
+struct SphereParams {
+    const int32_t *I;
+    const T *F;
+    const T *q;
+    long long N;
+    long long n_tiles;
+    const DevPrim<T> *prims;
+    int n_prims;
+    T margin;
+    T *out_vals;
+    T *out_jac;
+    uint8_t *out_valid;
+    int i_total, f_total;
+    int off_F, off_prims, off_warp, warp_elems;   // bytes, bytes, bytes, elements of T per warp
+    int woff_q, woff_frames, woff_tw, woff_stage; // element offsets inside a warp slab
+    int fstride, tstride;                         // elements of T per configuration: frames, twists
+    int G, logG;                                  // configurations per tile (power of two)
+    int D, S, n_rounds, n_levels;                 // copies of the program header (uniform operands)
+    int copy_vec;                                 // 1: every round block is 16-byte aligned in out_jac
+    // Warp-uniform data the hot loop reads every iteration lives in the kernel parameters (constant bank):
+    // the compiler then keeps mask tests / branches on the uniform datapath and folds the primitive's
+    // constants straight into FFMA operands.
+    unsigned long long round_cm[MAX_ROUNDS];      // per round: columns any of its spheres depends on
+    DevPrim<T> prim0;                             // copy of primitive 0 (single-primitive fast path)
+};
+
+template <typename T> struct alignas(16) Vec4 { T x, y, z, w; };
+
+template <typename T>
+__device__ __forceinline__ void st_stream(T *p, T v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream4(float *p, const float4 &v) { __stcs(reinterpret_cast<float4 *>(p), v); }
+__device__ __forceinline__ void st_stream4(double *p, const double2 &v) { __stcs(reinterpret_cast<double2 *>(p), v); }
+
+// packed fp32x2 FMA (sm_100: SASS FFMA2): both halves in one issue slot
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
+// Twist storage per configuration.  Scalar layout: 8 elements per column [wx wy wz 0 | vx vy vz 0].
+// Pair layout (fp32 collfree, even D): 12 floats per column pair (j, j+1), component-interleaved
+// [wx_j wx_j1 wy_j wy_j1 | wz_j wz_j1 vx_j vx_j1 | vy_j vy_j1 vz_j vz_j1] so that three LDS.128 feed six FFMA2.
+template <typename T, int KIND, int VW>
+struct TwistLayout {
+    static constexpr bool PAIR = (sizeof(T) == 4) && (KIND == KIND_COLLFREE) && (VW >= 2);
+};
+
+template <typename T, int KIND, bool WITH_JAC, bool CLOSEST, bool SINGLE, int VW, typename MaskT>
+__global__ void __launch_bounds__(256, 2) sphere_kernel(const __grid_constant__ SphereParams<T> prm) {
+    using Rl = Real<T>;
+    using V4 = Vec4<T>;
+    constexpr int ROWS = (KIND == KIND_MAP) ? 3 : 1;
+    constexpr bool PAIR = TwistLayout<T, KIND, VW>::PAIR && !CLOSEST;
+    extern __shared__ __align__(16) unsigned char smem[];
+    int32_t *sI = reinterpret_cast<int32_t *>(smem);
+    T *sF = reinterpret_cast<T *>(smem + prm.off_F);
+    DevPrim<T> *sP = reinterpret_cast<DevPrim<T> *>(smem + prm.off_prims);
+
+    // the warp index goes through a shuffle so the compiler treats it (and every loop bound derived from it)
+    // as warp-uniform: mask tests and branches of the hot loop then run on the uniform datapath
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), n_warps = blockDim.x >> 5;
+    for (int i = tid; i < prm.i_total; i += blockDim.x) sI[i] = prm.I[i];
+    for (int i = tid; i < prm.f_total; i += blockDim.x) sF[i] = prm.F[i];
+    if (KIND == KIND_COLLFREE && !SINGLE) {
+        const int words = prm.n_prims * (int)(sizeof(DevPrim<T>) / 4);
+        const int32_t *src = reinterpret_cast<const int32_t *>(prm.prims);
+        int32_t *dst = reinterpret_cast<int32_t *>(sP);
+        for (int i = tid; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    const int n_levels = prm.n_levels, n_rounds = prm.n_rounds, D = prm.D, S = prm.S;
+    const int fstride = prm.fstride, tstride = prm.tstride;
+    const int32_t *nodeI = sI + sI[S_NODE_I];
+    const int32_t *levelI = sI + sI[S_LEVEL_I];
+    const int32_t *levelNodes = sI + sI[S_LEVELNODE_I];
+    const int4 *roundI = reinterpret_cast<const int4 *>(sI + sI[S_ROUND_I]);
+    const int4 *tabB = reinterpret_cast<const int4 *>(sI + sI[S_TABB_I]);
+    const V4 *nodeF = reinterpret_cast<const V4 *>(sF + sI[S_NODE_F]);
+    const V4 *tabA = reinterpret_cast<const V4 *>(sF + sI[S_TABA_F]);
+    const int G = prm.G, logG = prm.logG;
+
+    T *wbase = reinterpret_cast<T *>(smem + prm.off_warp) + (size_t)warp * prm.warp_elems;
+    T *wq = wbase + prm.woff_q;
+    T *wframes = wbase + prm.woff_frames;
+    T *wtw = wbase + prm.woff_tw;
+    T *wstage = wbase + prm.woff_stage;
+
+    for (long long tile = (long long)blockIdx.x * n_warps + warp; tile < prm.n_tiles; tile += (long long)gridDim.x * n_warps) {
+        const long long n0 = tile * G;
+        const int g_live = (int)min((long long)G, prm.N - n0);
+        __syncwarp();
+        for (int i = lane; i < g_live * D; i += 32) wq[i] = prm.q[n0 * D + i];
+        __syncwarp();
+
+        // ------------------------------------------------------------ phase 1: frames + twists
+        {
+            const int cfg = lane & (G - 1), slot = lane >> logG, slots = 32 >> logG;
+            const T *myq = wq + min(cfg, g_live - 1) * D;
+            V4 *fr = reinterpret_cast<V4 *>(wframes + cfg * fstride);
+            T *tw = wtw + cfg * tstride;
+            for (int lv = 0; lv < n_levels; ++lv) {
+                const int lbeg = levelI[2 * lv], lcnt = levelI[2 * lv + 1];
+                for (int k0 = 0; k0 < lcnt; k0 += slots) {
+                    const int k = k0 + slot;
+                    if (k < lcnt) {
+                        const int node = levelNodes[lbeg + k];
+                        const int type = nodeI[4 * node], col = nodeI[4 * node + 1], par = nodeI[4 * node + 2];
+                        const V4 c0 = nodeF[3 * node], c1 = nodeF[3 * node + 1], c2 = nodeF[3 * node + 2];
+                        V4 y0, y1, y2;      // Y = parent * pre, rows [R_r0 R_r1 R_r2 t_r]
+                        if (par < 0) { y0 = c0; y1 = c1; y2 = c2; }
+                        else {
+                            const V4 p0 = fr[3 * par], p1 = fr[3 * par + 1], p2 = fr[3 * par + 2];
+#define SKB_ROW(P, Y)                                                   \
+    Y.x = P.x * c0.x + P.y * c1.x + P.z * c2.x;                         \
+    Y.y = P.x * c0.y + P.y * c1.y + P.z * c2.y;                         \
+    Y.z = P.x * c0.z + P.y * c1.z + P.z * c2.z;                         \
+    Y.w = P.w + P.x * c0.w + P.y * c1.w + P.z * c2.w;
+                            SKB_ROW(p0, y0) SKB_ROW(p1, y1) SKB_ROW(p2, y2)
+#undef SKB_ROW
+                        }
+                        T wx = T(0), wy = T(0), wz = T(0), vx = T(0), vy = T(0), vz = T(0);
+                        if (type == NODE_REVOLUTE) {
+                            T s, c;
+                            Rl::sincos(myq[col], &s, &c);
+                            wx = y0.z; wy = y1.z; wz = y2.z;                 // joint axis = local +z
+                            vx = y1.w * wz - y2.w * wy;                       // v = o x omega
+                            vy = y2.w * wx - y0.w * wz;
+                            vz = y0.w * wy - y1.w * wx;
+                            T a, b;
+                            a = y0.x; b = y0.y; y0.x = c * a + s * b; y0.y = c * b - s * a;
+                            a = y1.x; b = y1.y; y1.x = c * a + s * b; y1.y = c * b - s * a;
+                            a = y2.x; b = y2.y; y2.x = c * a + s * b; y2.y = c * b - s * a;
+                        } else if (type == NODE_PRISMATIC) {
+                            const T th = myq[col];
+                            vx = y0.z; vy = y1.z; vz = y2.z;
+                            y0.w += th * vx; y1.w += th * vy; y2.w += th * vz;
+                        }
+                        fr[3 * node] = y0; fr[3 * node + 1] = y1; fr[3 * node + 2] = y2;
+                        if (WITH_JAC && col >= 0) {
+                            if (PAIR) {
+                                T *t2 = tw + (col >> 1) * 12 + (col & 1);
+                                t2[0] = wx; t2[2] = wy; t2[4] = wz; t2[6] = vx; t2[8] = vy; t2[10] = vz;
+                            } else {
+                                V4 *t2 = reinterpret_cast<V4 *>(tw + col * 8);
+                                V4 a; a.x = wx; a.y = wy; a.z = wz; a.w = T(0);
+                                V4 b; b.x = vx; b.y = vy; b.z = vz; b.w = T(0);
+                                t2[0] = a; t2[1] = b;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ------------------------------------------------------------ phase 2: one lane per sphere
+        for (int c = 0; c < g_live; ++c) {
+            const long long n = n0 + c;
+            const V4 *fr = reinterpret_cast<const V4 *>(wframes + c * fstride);
+            const T *tw = wtw + c * tstride;
+            T vmin = Rl::inf();
+            T best = Rl::inf();
+            int best_idx = 0x7fffffff;
+            T bgx = T(0), bgy = T(0), bgz = T(0), bmx = T(0), bmy = T(0), bmz = T(0);
+            unsigned long long bmask = 0;
+
+            for (int r = 0; r < n_rounds; ++r) {
+                const int4 rd = roundI[r];                     // s0, cnt, -, -
+                const V4 A = tabA[r * 32 + lane];
+                const int4 B = tabB[r * 32 + lane];
+                const bool has = B.w != 0;
+                const V4 f0 = fr[3 * B.x], f1 = fr[3 * B.x + 1], f2 = fr[3 * B.x + 2];
+                const T px = f0.w + f0.x * A.x + f0.y * A.y + f0.z * A.z;
+                const T py = f1.w + f1.x * A.x + f1.y * A.y + f1.z * A.z;
+                const T pz = f2.w + f2.x * A.x + f2.y * A.y + f2.z * A.z;
+                T gx = T(0), gy = T(0), gz = T(0);
+
+                if (KIND == KIND_COLLFREE) {
+                    const T d = SINGLE ? sdf_prim_world<T>(prm.prim0, px, py, pz, gx, gy, gz)
+                                       : sdf_union<T>(sP, prm.n_prims, px, py, pz, gx, gy, gz);
+                    const T val = d - A.w - prm.margin;
+                    if (has) vmin = val < vmin ? val : vmin;
+                    if (CLOSEST) {
+                        // arg-min over spheres of sdf - radius, first index wins ties (np.argmin)
+                        if (has && val < best) {
+                            best = val; best_idx = rd.x + lane;
+                            bmask = ((unsigned long long)(unsigned)B.z << 32) | (unsigned)B.y;
+                            bgx = gx; bgy = gy; bgz = gz;
+                            bmx = py * gz - pz * gy; bmy = pz * gx - px * gz; bmz = px * gy - py * gx;
+                        }
+                        continue;
+                    }
+                    if (prm.out_vals != nullptr && has) st_stream(prm.out_vals + n * S + rd.x + lane, val);
+                } else {
+                    if (has) {
+                        T *g = prm.out_vals + (n * S + rd.x + lane) * 3;
+                        st_stream(g, px); st_stream(g + 1, py); st_stream(g + 2, pz);
+                    }
+                }
+                if (!WITH_JAC || CLOSEST) continue;
+
+                // ---- Jacobian rows of this lane's sphere, all D columns, assembled VW at a time
+                const unsigned long long cm = prm.round_cm[r];               // warp-uniform (constant bank)
+                const MaskT am = sizeof(MaskT) == 8 ? (MaskT)(((unsigned long long)(unsigned)B.z << 32) | (unsigned)B.y) : (MaskT)(unsigned)B.y;
+                const T mx = py * gz - pz * gy, my = pz * gx - px * gz, mz = px * gy - py * gx;   // wrench moment p x g
+                T *row = wstage + lane * (ROWS * D);
+                if (PAIR) {
+                    const float2 mx2 = make_float2((float)mx, (float)mx), my2 = make_float2((float)my, (float)my), mz2 = make_float2((float)mz, (float)mz);
+                    const float2 gx2 = make_float2((float)gx, (float)gx), gy2 = make_float2((float)gy, (float)gy), gz2 = make_float2((float)gz, (float)gz);
+                    for (int j = 0; j < D; j += VW) {
+                        alignas(16) float v0[VW];
+#pragma unroll
+                        for (int u = 0; u < VW; u += 2) {
+                            const int col = j + u;
+                            float2 acc = make_float2(0.f, 0.f);
+                            if ((cm >> col) & 3ull) {                   // uniform: someone in this round needs col or col + 1
+                                const float4 *t4 = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(tw) + (col >> 1) * 12);
+                                const float4 a = t4[0], b = t4[1], cc = t4[2];
+                                acc = mul2(make_float2(a.x, a.y), mx2);
+                                acc = fma2(make_float2(a.z, a.w), my2, acc);
+                                acc = fma2(make_float2(b.x, b.y), mz2, acc);
+                                acc = fma2(make_float2(b.z, b.w), gx2, acc);
+                                acc = fma2(make_float2(cc.x, cc.y), gy2, acc);
+                                acc = fma2(make_float2(cc.z, cc.w), gz2, acc);
+                                const MaskT sh = am >> col;
+                                acc.x = (sh & 1) ? acc.x : 0.f;
+                                acc.y = (sh & 2) ? acc.y : 0.f;
+                            }
+                            v0[u] = acc.x; v0[u + 1] = acc.y;
+                        }
+                        if (VW == 2) *reinterpret_cast<float2 *>(reinterpret_cast<float *>(row) + j) = *reinterpret_cast<float2 *>(v0);
+                        else *reinterpret_cast<float4 *>(reinterpret_cast<float *>(row) + j) = *reinterpret_cast<float4 *>(v0);
+                    }
+                } else {
+                    for (int j = 0; j < D; j += VW) {
+                        alignas(16) T v0[VW], v1[VW], v2[VW];
+#pragma unroll
+                        for (int u = 0; u < VW; ++u) {
+                            const int col = j + u;
+                            v0[u] = T(0); v1[u] = T(0); v2[u] = T(0);
+                            if ((cm >> col) & 1ull) {                   // uniform: someone in this round needs column col
+                                const V4 w = *reinterpret_cast<const V4 *>(tw + col * 8);
+                                const V4 v = *reinterpret_cast<const V4 *>(tw + col * 8 + 4);
+                                const bool mine = (am >> col) & 1;
+                                if (KIND == KIND_COLLFREE) {
+                                    const T jv = w.x * mx + w.y * my + w.z * mz + v.x * gx + v.y * gy + v.z * gz;
+                                    v0[u] = mine ? jv : T(0);
+                                } else {                                // d p / d q_col = omega x p + v
+                                    v0[u] = mine ? (w.y * pz - w.z * py + v.x) : T(0);
+                                    v1[u] = mine ? (w.z * px - w.x * pz + v.y) : T(0);
+                                    v2[u] = mine ? (w.x * py - w.y * px + v.z) : T(0);
+                                }
+                            }
+                        }
+                        if (VW == 1) {
+                            row[j] = v0[0];
+                            if (ROWS == 3) { row[D + j] = v1[0]; row[2 * D + j] = v2[0]; }
+                        } else if (VW * sizeof(T) == 8) {
+                            *reinterpret_cast<float2 *>(row + j) = *reinterpret_cast<float2 *>(v0);
+                            if (ROWS == 3) {
+                                *reinterpret_cast<float2 *>(row + D + j) = *reinterpret_cast<float2 *>(v1);
+                                *reinterpret_cast<float2 *>(row + 2 * D + j) = *reinterpret_cast<float2 *>(v2);
+                            }
+                        } else {
+                            *reinterpret_cast<float4 *>(row + j) = *reinterpret_cast<float4 *>(v0);
+                            if (ROWS == 3) {
+                                *reinterpret_cast<float4 *>(row + D + j) = *reinterpret_cast<float4 *>(v1);
+                                *reinterpret_cast<float4 *>(row + 2 * D + j) = *reinterpret_cast<float4 *>(v2);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                // ---- ship the round: dense [cnt][ROWS*D] block == output layout, coalesced streaming stores
+                {
+                    const int len = rd.y * ROWS * D;
+                    T *g = prm.out_jac + (n * S + rd.x) * (long long)(ROWS * D);
+                    constexpr int PER = 16 / (int)sizeof(T);
+                    if (prm.copy_vec) {
+#pragma unroll 2
+                        for (int i = lane * PER; i < len; i += 32 * PER) {
+                            if (sizeof(T) == 4) st_stream4(reinterpret_cast<float *>(g + i), *reinterpret_cast<const float4 *>(wstage + i));
+                            else st_stream4(reinterpret_cast<double *>(g + i), *reinterpret_cast<const double2 *>(wstage + i));
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int i = lane; i < len; i += 32) st_stream(g + i, wstage[i]);
+                    }
+                }
+                __syncwarp();
+            }   // rounds
+
+            if (KIND == KIND_COLLFREE) {
+                if (prm.out_valid != nullptr) {
+                    T m = vmin;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { const T x = __shfl_xor_sync(0xffffffffu, m, o); m = x < m ? x : m; }
+                    if (lane == 0) prm.out_valid[n] = m > T(0) ? 1 : 0;
+                }
+                if (CLOSEST) {
+                    T m = best; int mi = best_idx;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const T x = __shfl_xor_sync(0xffffffffu, m, o);
+                        const int xi = __shfl_xor_sync(0xffffffffu, mi, o);
+                        if (x < m || (x == m && xi < mi)) { m = x; mi = xi; }
+                    }
+                    if (prm.out_vals != nullptr && lane == 0) prm.out_vals[n] = m;
+                    if (WITH_JAC) {
+                        const int src = __ffs(__ballot_sync(0xffffffffu, best_idx == mi && best == m)) - 1;
+                        const T gx = __shfl_sync(0xffffffffu, bgx, src), gy = __shfl_sync(0xffffffffu, bgy, src), gz = __shfl_sync(0xffffffffu, bgz, src);
+                        const T mx = __shfl_sync(0xffffffffu, bmx, src), my = __shfl_sync(0xffffffffu, bmy, src), mz = __shfl_sync(0xffffffffu, bmz, src);
+                        const unsigned long long am = __shfl_sync(0xffffffffu, bmask, src);
+                        for (int col = lane; col < D; col += 32) {     // one lane per column of the single row
+                            T jv = T(0);
+                            if ((am >> col) & 1ull) {
+                                const V4 w = *reinterpret_cast<const V4 *>(tw + col * 8);
+                                const V4 v = *reinterpret_cast<const V4 *>(tw + col * 8 + 4);
+                                jv = w.x * mx + w.y * my + w.z * mz + v.x * gx + v.y * gy + v.z * gz;
+                            }
+                            prm.out_jac[n * D + col] = jv;
+                        }
+                    }
+                }
+            }
+        }   // configurations of the tile
+    }       // tiles
+}
+
+// ------------------------------------------------------------------ corner-pack expansion of a voxel grid
+template <typename V>
+__global__ void expand_cells_kernel(const V *grid, int nx, int ny, int nz, V *cells) {
+    const long long total = (long long)(nx - 1) * (ny - 1) * (nz - 1);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int iz = (int)(i % (nz - 1));
+        const long long t = i / (nz - 1);
+        const int iy = (int)(t % (ny - 1)), ix = (int)(t / (ny - 1));
+        const long long sy = nz, sx = (long long)ny * nz, b = ix * sx + iy * sy + iz;
+        V *o = cells + i * 8;
+        o[0] = grid[b];           o[1] = grid[b + 1];
+        o[2] = grid[b + sy];      o[3] = grid[b + sy + 1];
+        o[4] = grid[b + sx];      o[5] = grid[b + sx + 1];
+        o[6] = grid[b + sx + sy]; o[7] = grid[b + sx + sy + 1];
+    }
+}
+
+#define CUDA_OK(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+    } while (0)
+
+int launch_expand_cells(const void *grid, int is_f64, const int32_t dims[3], void *cells) {
+    const long long total = (long long)(dims[0] - 1) * (dims[1] - 1) * (dims[2] - 1);
+    const int threads = 256;
+    const int blocks = (int)std::min<long long>((total + threads - 1) / threads, 148 * 16);
+    if (is_f64) expand_cells_kernel<double><<<blocks, threads>>>(reinterpret_cast<const double *>(grid), dims[0], dims[1], dims[2], reinterpret_cast<double *>(cells));
+    else expand_cells_kernel<float><<<blocks, threads>>>(reinterpret_cast<const float *>(grid), dims[0], dims[1], dims[2], reinterpret_cast<float *>(cells));
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
+// ------------------------------------------------------------------ launcher
+static int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+static int sm_count_cached() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+template <typename T, int KIND, bool WITH_JAC, bool CLOSEST, bool SINGLE, int VW, typename MaskT>
+static int launch_sphere_inst(const skb_plan *p, const skb_sphere_program *sp, const void *q, int64_t N, const void *dev_prims,
+                              const void *host_prims, int n_prims, double margin, void *out_vals, void *out_jac,
+                              uint8_t *out_valid, cudaStream_t stream) {
+    constexpr int ROWS = (KIND == KIND_MAP) ? 3 : 1;
+    constexpr bool PAIR = TwistLayout<T, KIND, VW>::PAIR && !CLOSEST;
+    SphereParams<T> prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.I = reinterpret_cast<const int32_t *>(sp->dI);
+    prm.F = reinterpret_cast<const T *>(sizeof(T) == 4 ? sp->dF32 : sp->dF64);
+    prm.q = reinterpret_cast<const T *>(q);
+    prm.N = N;
+    prm.prims = reinterpret_cast<const DevPrim<T> *>(dev_prims);
+    prm.n_prims = n_prims;
+    prm.margin = (T)margin;
+    prm.out_vals = reinterpret_cast<T *>(out_vals);
+    prm.out_jac = reinterpret_cast<T *>(out_jac);
+    prm.out_valid = out_valid;
+    prm.i_total = (int)sp->I.size();
+    prm.f_total = (int)sp->F.size();
+    if (KIND == KIND_COLLFREE && host_prims) prm.prim0 = *reinterpret_cast<const DevPrim<T> *>(host_prims);
+    for (int r = 0; r < sp->n_rounds && r < MAX_ROUNDS; ++r) {
+        const int32_t *rd = &sp->I[sp->I[S_ROUND_I] + 4 * r];
+        prm.round_cm[r] = ((unsigned long long)(uint32_t)rd[3] << 32) | (uint32_t)rd[2];
+    }
+    const int D = p->D, S = p->F;
+    prm.D = D; prm.S = S; prm.n_rounds = sp->n_rounds; prm.n_levels = sp->n_levels;
+    const bool stage = WITH_JAC && !CLOSEST;
+    prm.off_F = align_up(prm.i_total * 4, 16);
+    prm.off_prims = align_up(prm.off_F + prm.f_total * (int)sizeof(T), 16);
+    prm.off_warp = align_up(prm.off_prims + ((KIND == KIND_COLLFREE && !SINGLE) ? n_prims : 0) * (int)sizeof(DevPrim<T>), 128);
+    const int al = 16 / (int)sizeof(T);
+    const int PER = al;
+    // every round block [s0*ROWS*D, +cnt*ROWS*D) of every configuration must be 16-byte aligned for vector copy-out
+    prm.copy_vec = ((S * ROWS * D) % PER == 0 && (32 * ROWS * D) % PER == 0 && ((S % 32) * ROWS * D) % PER == 0 &&
+                    (reinterpret_cast<uintptr_t>(out_jac) % 16 == 0)) ? 1 : 0;
+    prm.fstride = sp->frame_stride;
+    {   // twist slab per configuration, rounded to an odd number of 16-byte quads (conflict-free phase-1 stores)
+        int words = PAIR ? (D / 2) * 12 : D * 8;
+        int qd = (words + 3) / 4;
+        if (qd % 2 == 0) qd += 1;
+        prm.tstride = qd * 4;
+    }
+    const size_t smem_limit = 227 * 1024;
+    int warps = p->tune_warps > 0 ? std::min(p->tune_warps, 8) : 8;
+    int ctas_target = p->tune_ctas > 0 ? p->tune_ctas : 2;
+    int G = p->tune_chunk > 0 ? std::min(p->tune_chunk, 32) : 32;
+    auto layout = [&](int g) {
+        int e = 0;
+        prm.woff_q = e;      e += align_up(g * D, al);
+        prm.woff_frames = e; e += g * prm.fstride;
+        prm.woff_tw = e;     e += WITH_JAC ? g * prm.tstride : 0;
+        prm.woff_stage = e;  e += stage ? align_up(32 * ROWS * D, al) : 0;
+        prm.warp_elems = align_up(e, al);
+        return (size_t)prm.off_warp + (size_t)warps * prm.warp_elems * sizeof(T);
+    };
+    // largest power-of-two tile that still lets `ctas_target` CTAs share one SM's shared memory
+    while (G > 1 && (G & (G - 1))) G &= G - 1;
+    if (p->tune_chunk <= 0)
+        while (G > 4 && (layout(G) + 1024) * ctas_target > smem_limit) G >>= 1;
+    while (layout(G) > smem_limit && G > 1) G >>= 1;
+    while (layout(G) > smem_limit && warps > 1) warps >>= 1;
+    const size_t smem = layout(G);
+    if (smem > smem_limit) return set_error("sphere kernel: shared-memory footprint exceeds 227 KB");
+    prm.G = G;
+    prm.logG = 0;
+    while ((1 << prm.logG) < G) ++prm.logG;
+    prm.n_tiles = (N + G - 1) / G;
+    auto kern = sphere_kernel<T, KIND, WITH_JAC, CLOSEST, SINGLE, VW, MaskT>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) return set_error("sphere kernel: zero occupancy");
+    if (p->tune_ctas > 0) per_sm = std::min(per_sm, p->tune_ctas);
+    const long long want = (prm.n_tiles + warps - 1) / warps;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count_cached() * per_sm));
+    kern<<<grid, warps * 32, smem, stream>>>(prm);
+    CUDA_OK(cudaGetLastError());
+    ++g_launch_count;
+    return 0;
+}
+
+#define SKB_ARGS p, sp, q, N, dev_prims, host_prims, n_prims, margin, out_vals, out_jac, out_valid, stream
+#define SKB_SIG const skb_plan *p, const skb_sphere_program *sp, const void *q, int64_t N, const void *dev_prims, const void *host_prims, \
+                int n_prims, double margin, void *out_vals, void *out_jac, uint8_t *out_valid, cudaStream_t stream
+
+// all-spheres mode with Jacobian: pick the widest row store that keeps each lane's row start aligned, and the mask width
+template <typename T, int KIND, bool SINGLE>
+static int launch_sphere_jac(SKB_SIG) {
+    const int D = p->D;
+    const int bytes = D * (int)sizeof(T);
+    const bool wide = D > 32;
+    if (bytes % 16 == 0 && sizeof(T) == 4)
+        return wide ? launch_sphere_inst<T, KIND, true, false, SINGLE, 4, unsigned long long>(SKB_ARGS)
+                    : launch_sphere_inst<T, KIND, true, false, SINGLE, 4, unsigned>(SKB_ARGS);
+    if ((bytes % 8 == 0 && sizeof(T) == 4) || (bytes % 16 == 0 && sizeof(T) == 8))
+        return wide ? launch_sphere_inst<T, KIND, true, false, SINGLE, 2, unsigned long long>(SKB_ARGS)
+                    : launch_sphere_inst<T, KIND, true, false, SINGLE, 2, unsigned>(SKB_ARGS);
+    return wide ? launch_sphere_inst<T, KIND, true, false, SINGLE, 1, unsigned long long>(SKB_ARGS)
+                : launch_sphere_inst<T, KIND, true, false, SINGLE, 1, unsigned>(SKB_ARGS);
+}
+
+template <typename T, bool SINGLE>
+static int launch_sphere_collfree(SKB_SIG, int mode) {
+    const bool wj = out_jac != nullptr;
+    if (mode == SKB_MODE_CLOSEST)
+        return wj ? launch_sphere_inst<T, KIND_COLLFREE, true, true, SINGLE, 1, unsigned long long>(SKB_ARGS)
+                  : launch_sphere_inst<T, KIND_COLLFREE, false, true, SINGLE, 1, unsigned long long>(SKB_ARGS);
+    if (wj) return launch_sphere_jac<T, KIND_COLLFREE, SINGLE>(SKB_ARGS);
+    return launch_sphere_inst<T, KIND_COLLFREE, false, false, SINGLE, 1, unsigned>(SKB_ARGS);
+}
+
+template <typename T>
+static int launch_sphere_t(SKB_SIG, int kind, int mode) {
+    if (kind == KIND_MAP) {
+        if (out_jac != nullptr) return launch_sphere_jac<T, KIND_MAP, true>(SKB_ARGS);
+        return launch_sphere_inst<T, KIND_MAP, false, false, true, 1, unsigned>(SKB_ARGS);
+    }
+    if (n_prims == 1) return launch_sphere_collfree<T, true>(SKB_ARGS, mode);
+    return launch_sphere_collfree<T, false>(SKB_ARGS, mode);
+}
+
+int launch_sphere(const skb_plan *p, const skb_sphere_program *sp, int kind, int dtype, const void *q, int64_t N,
+                  const void *dev_prims, const void *host_prims, int n_prims, double margin, int mode, void *out_vals,
+                  void *out_jac, uint8_t *out_valid, void *stream_) {
+    if (N <= 0) return 0;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (dtype == SKB_F32) return launch_sphere_t<float>(SKB_ARGS, kind, mode);
+    if (dtype == SKB_F64) return launch_sphere_t<double>(SKB_ARGS, kind, mode);
+    return set_error("bad dtype");
+}
+
+}  // namespace skb
