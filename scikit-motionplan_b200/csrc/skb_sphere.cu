@@ -36,6 +36,11 @@ namespace skb {
 
 enum { MAX_ROUNDS = 32 };
 
+#ifndef SKB_LB_THREADS
+#define SKB_LB_THREADS 256      // max threads per CTA
+#define SKB_LB_BLOCKS 3         // min CTAs per SM (register cap = 65536 / product)
+#endif
+
 template <typename T>
 struct SphereParams {
     const int32_t *I;
@@ -56,6 +61,7 @@ struct SphereParams {
     int G, logG;                                  // configurations per tile (power of two)
     int D, S, n_rounds, n_levels;                 // copies of the program header (uniform operands)
     int copy_vec;                                 // 1: every round block is 16-byte aligned in out_jac
+    int stage_elems;                              // elements of T per staging buffer (two per warp)
     // Warp-uniform data the hot loop reads every iteration lives in the kernel parameters (constant bank):
     // the compiler then keeps mask tests / branches on the uniform datapath and folds the primitive's
     // constants straight into FFMA operands.
@@ -92,7 +98,7 @@ struct TwistLayout {
 };
 
 template <typename T, int KIND, bool WITH_JAC, bool CLOSEST, bool SINGLE, int VW, typename MaskT>
-__global__ void __launch_bounds__(256, 2) sphere_kernel(const __grid_constant__ SphereParams<T> prm) {
+__global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(const __grid_constant__ SphereParams<T> prm) {
     using Rl = Real<T>;
     using V4 = Vec4<T>;
     constexpr int ROWS = (KIND == KIND_MAP) ? 3 : 1;
@@ -131,6 +137,9 @@ __global__ void __launch_bounds__(256, 2) sphere_kernel(const __grid_constant__ 
     T *wframes = wbase + prm.woff_frames;
     T *wtw = wbase + prm.woff_tw;
     T *wstage = wbase + prm.woff_stage;
+    const int stage_elems = prm.stage_elems;
+    int stage_sel = 0;
+    const uint64_t l2_policy = l2_evict_first_policy();
 
     for (long long tile = (long long)blockIdx.x * n_warps + warp; tile < prm.n_tiles; tile += (long long)gridDim.x * n_warps) {
         const long long n0 = tile * G;
@@ -250,7 +259,11 @@ __global__ void __launch_bounds__(256, 2) sphere_kernel(const __grid_constant__ 
                 const unsigned long long cm = prm.round_cm[r];               // warp-uniform (constant bank)
                 const MaskT am = sizeof(MaskT) == 8 ? (MaskT)(((unsigned long long)(unsigned)B.z << 32) | (unsigned)B.y) : (MaskT)(unsigned)B.y;
                 const T mx = py * gz - pz * gy, my = pz * gx - px * gz, mz = px * gy - py * gx;   // wrench moment p x g
-                T *row = wstage + lane * (ROWS * D);
+                T *row0 = wstage + stage_sel * stage_elems;
+                T *row = row0 + lane * (ROWS * D);
+                // the bulk store issued from this buffer two rounds ago must have finished reading it
+                if (lane == 0) bulk_wait_read<1>();
+                __syncwarp();
                 if (PAIR) {
                     const float2 mx2 = make_float2((float)mx, (float)mx), my2 = make_float2((float)my, (float)my), mz2 = make_float2((float)mz, (float)mz);
                     const float2 gx2 = make_float2((float)gx, (float)gx), gy2 = make_float2((float)gy, (float)gy), gz2 = make_float2((float)gz, (float)gz);
@@ -317,24 +330,25 @@ __global__ void __launch_bounds__(256, 2) sphere_kernel(const __grid_constant__ 
                         }
                     }
                 }
-                __syncwarp();
-                // ---- ship the round: dense [cnt][ROWS*D] block == output layout, coalesced streaming stores
+                // ---- ship the round: the dense [cnt][ROWS*D] block IS the output layout and is contiguous in HBM
                 {
                     const int len = rd.y * ROWS * D;
                     T *g = prm.out_jac + (n * S + rd.x) * (long long)(ROWS * D);
-                    constexpr int PER = 16 / (int)sizeof(T);
                     if (prm.copy_vec) {
-#pragma unroll 2
-                        for (int i = lane * PER; i < len; i += 32 * PER) {
-                            if (sizeof(T) == 4) st_stream4(reinterpret_cast<float *>(g + i), *reinterpret_cast<const float4 *>(wstage + i));
-                            else st_stream4(reinterpret_cast<double *>(g + i), *reinterpret_cast<const double2 *>(wstage + i));
+                        // one bulk async store (TMA, SASS UBLKCP) per round, issued by lane 0; no LSU traffic for the copy
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            bulk_store_hint(g, row0, (uint32_t)(len * sizeof(T)), l2_policy);
+                            bulk_commit();
                         }
                     } else {
+                        __syncwarp();
 #pragma unroll 4
-                        for (int i = lane; i < len; i += 32) st_stream(g + i, wstage[i]);
+                        for (int i = lane; i < len; i += 32) st_stream(g + i, row0[i]);
                     }
                 }
-                __syncwarp();
+                stage_sel ^= 1;
             }   // rounds
 
             if (KIND == KIND_COLLFREE) {
@@ -372,6 +386,7 @@ __global__ void __launch_bounds__(256, 2) sphere_kernel(const __grid_constant__ 
             }
         }   // configurations of the tile
     }       // tiles
+    if (WITH_JAC && !CLOSEST) bulk_wait_read<0>();   // shared memory must outlive the last bulk reads
 }
 
 // ------------------------------------------------------------------ corner-pack expansion of a voxel grid
@@ -467,15 +482,16 @@ static int launch_sphere_inst(const skb_plan *p, const skb_sphere_program *sp, c
         prm.tstride = qd * 4;
     }
     const size_t smem_limit = 227 * 1024;
-    int warps = p->tune_warps > 0 ? std::min(p->tune_warps, 8) : 8;
-    int ctas_target = p->tune_ctas > 0 ? p->tune_ctas : 2;
+    int warps = p->tune_warps > 0 ? std::min(p->tune_warps, SKB_LB_THREADS / 32) : SKB_LB_THREADS / 32;
+    int ctas_target = p->tune_ctas > 0 ? p->tune_ctas : SKB_LB_BLOCKS;
     int G = p->tune_chunk > 0 ? std::min(p->tune_chunk, 32) : 32;
     auto layout = [&](int g) {
         int e = 0;
         prm.woff_q = e;      e += align_up(g * D, al);
         prm.woff_frames = e; e += g * prm.fstride;
         prm.woff_tw = e;     e += WITH_JAC ? g * prm.tstride : 0;
-        prm.woff_stage = e;  e += stage ? align_up(32 * ROWS * D, al) : 0;
+        prm.stage_elems = align_up(32 * ROWS * D, al);
+        prm.woff_stage = e;  e += stage ? 2 * prm.stage_elems : 0;
         prm.warp_elems = align_up(e, al);
         return (size_t)prm.off_warp + (size_t)warps * prm.warp_elems * sizeof(T);
     };
