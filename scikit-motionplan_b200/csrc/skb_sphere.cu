@@ -56,7 +56,7 @@ struct SphereParams {
     uint8_t *out_valid;
     int i_total, f_total;
     int off_F, off_prims, off_warp, warp_elems;   // bytes, bytes, bytes, elements of T per warp
-    int woff_q, woff_frames, woff_tw, woff_stage; // element offsets inside a warp slab
+    int woff_q, woff_sc, woff_frames, woff_tw, woff_stage; // element offsets inside a warp slab
     int fstride, tstride;                         // elements of T per configuration: frames, twists
     int G, logG;                                  // configurations per tile (power of two)
     int D, S, n_rounds, n_levels;                 // copies of the program header (uniform operands)
@@ -89,6 +89,40 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
     return *reinterpret_cast<float2 *>(&rd);
 }
 
+// How the kernel reaches the world SDF.
+enum { SDF_UNION = 0,       // any union of primitives, table staged in shared memory
+       SDF_SINGLE = 1,      // one primitive of any type, constants read from the kernel parameters
+       SDF_GRID_FAST = 2 }; // one fp32 corner-packed voxel grid with identity rotation (the cfg3 hot path)
+
+// fp32 corner-packed grid, identity rotation: same arithmetic (and rounding) as sdf_prim_world -> sdf_grid_local,
+// minus the type dispatch, rotation, value-type and 64-bit index generality.
+__device__ __forceinline__ float sdf_grid_fast(const DevPrim<float> &pr, float px, float py, float pz, float &gx, float &gy, float &gz) {
+    const float ux = ((px - pr.pos[0]) - pr.par[0]) * pr.par[3], uy = ((py - pr.pos[1]) - pr.par[1]) * pr.par[4],
+                uz = ((pz - pr.pos[2]) - pr.par[2]) * pr.par[5];
+    const float tx = float(pr.dims[0] - 1), ty = float(pr.dims[1] - 1), tz = float(pr.dims[2] - 1);
+    gx = gy = gz = 0.f;
+    if (!(ux >= 0.f && ux <= tx && uy >= 0.f && uy <= ty && uz >= 0.f && uz <= tz)) return pr.par[6];
+    const int ix = min((int)floorf(ux), pr.dims[0] - 2), iy = min((int)floorf(uy), pr.dims[1] - 2), iz = min((int)floorf(uz), pr.dims[2] - 2);
+    const float fx = ux - float(ix), fy = uy - float(iy), fz = uz - float(iz);
+    const unsigned cell = ((unsigned)ix * (unsigned)(pr.dims[1] - 1) + (unsigned)iy) * (unsigned)(pr.dims[2] - 1) + (unsigned)iz;
+    float c[8];
+    ldg_cell(reinterpret_cast<const float *>(pr.cells) + (size_t)cell * 8, c);
+    const float d00 = c[4] - c[0], d01 = c[5] - c[1], d10 = c[6] - c[2], d11 = c[7] - c[3];
+    const float c00 = c[0] + fx * d00, c01 = c[1] + fx * d01, c10 = c[2] + fx * d10, c11 = c[3] + fx * d11;
+    const float e0 = c10 - c00, e1 = c11 - c01;
+    const float c0 = c00 + fy * e0, c1 = c01 + fy * e1;
+    const float h = c1 - c0;
+    const float dx0 = d00 + fy * (d10 - d00), dx1 = d01 + fy * (d11 - d01);
+    gx = (dx0 + fz * (dx1 - dx0)) * pr.par[3];
+    gy = (e0 + fz * (e1 - e0)) * pr.par[4];
+    gz = h * pr.par[5];
+    return c0 + fz * h;
+}
+template <typename T>
+__device__ __forceinline__ T sdf_grid_fast(const DevPrim<T> &pr, T px, T py, T pz, T &gx, T &gy, T &gz) {
+    return sdf_prim_world<T>(pr, px, py, pz, gx, gy, gz);     // only instantiated for float; keeps templates well-formed
+}
+
 // Twist storage per configuration.  Scalar layout: 8 elements per column [wx wy wz 0 | vx vy vz 0].
 // Pair layout (fp32 collfree, even D): 12 floats per column pair (j, j+1), component-interleaved
 // [wx_j wx_j1 wy_j wy_j1 | wz_j wz_j1 vx_j vx_j1 | vy_j vy_j1 vz_j vz_j1] so that three LDS.128 feed six FFMA2.
@@ -97,7 +131,7 @@ struct TwistLayout {
     static constexpr bool PAIR = (sizeof(T) == 4) && (KIND == KIND_COLLFREE) && (VW >= 2);
 };
 
-template <typename T, int KIND, bool WITH_JAC, bool CLOSEST, bool SINGLE, int VW, typename MaskT>
+template <typename T, int KIND, bool WITH_JAC, bool CLOSEST, int SDFK, int VW, typename MaskT>
 __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(const __grid_constant__ SphereParams<T> prm) {
     using Rl = Real<T>;
     using V4 = Vec4<T>;
@@ -113,7 +147,7 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), n_warps = blockDim.x >> 5;
     for (int i = tid; i < prm.i_total; i += blockDim.x) sI[i] = prm.I[i];
     for (int i = tid; i < prm.f_total; i += blockDim.x) sF[i] = prm.F[i];
-    if (KIND == KIND_COLLFREE && !SINGLE) {
+    if (KIND == KIND_COLLFREE && SDFK == SDF_UNION) {
         const int words = prm.n_prims * (int)(sizeof(DevPrim<T>) / 4);
         const int32_t *src = reinterpret_cast<const int32_t *>(prm.prims);
         int32_t *dst = reinterpret_cast<int32_t *>(sP);
@@ -134,6 +168,7 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
 
     T *wbase = reinterpret_cast<T *>(smem + prm.off_warp) + (size_t)warp * prm.warp_elems;
     T *wq = wbase + prm.woff_q;
+    T *wsc = wbase + prm.woff_sc;
     T *wframes = wbase + prm.woff_frames;
     T *wtw = wbase + prm.woff_tw;
     T *wstage = wbase + prm.woff_stage;
@@ -145,13 +180,22 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
         const long long n0 = tile * G;
         const int g_live = (int)min((long long)G, prm.N - n0);
         __syncwarp();
-        for (int i = lane; i < g_live * D; i += 32) wq[i] = prm.q[n0 * D + i];
+        // q tile + one vectorised sin/cos pass over all G*D joint values (32 lanes busy), so the level walk below
+        // -- where only G x (nodes of the level) lanes are busy -- just picks (sin, cos) up from shared memory
+        for (int i = lane; i < g_live * D; i += 32) {
+            const T th = prm.q[n0 * D + i];
+            T sn, cs;
+            Rl::sincos(th, &sn, &cs);
+            wq[i] = th;
+            wsc[2 * i] = sn; wsc[2 * i + 1] = cs;
+        }
         __syncwarp();
 
         // ------------------------------------------------------------ phase 1: frames + twists
         {
             const int cfg = lane & (G - 1), slot = lane >> logG, slots = 32 >> logG;
             const T *myq = wq + min(cfg, g_live - 1) * D;
+            const T *mysc = wsc + 2 * min(cfg, g_live - 1) * D;
             V4 *fr = reinterpret_cast<V4 *>(wframes + cfg * fstride);
             T *tw = wtw + cfg * tstride;
             for (int lv = 0; lv < n_levels; ++lv) {
@@ -176,8 +220,7 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
                         }
                         T wx = T(0), wy = T(0), wz = T(0), vx = T(0), vy = T(0), vz = T(0);
                         if (type == NODE_REVOLUTE) {
-                            T s, c;
-                            Rl::sincos(myq[col], &s, &c);
+                            const T s = mysc[2 * col], c = mysc[2 * col + 1];
                             wx = y0.z; wy = y1.z; wz = y2.z;                 // joint axis = local +z
                             vx = y1.w * wz - y2.w * wy;                       // v = o x omega
                             vy = y2.w * wx - y0.w * wz;
@@ -210,20 +253,19 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
         }
 
         // ------------------------------------------------------------ phase 2: one lane per sphere
-        for (int c = 0; c < g_live; ++c) {
+        // per-configuration reduction state (validity / closest modes only)
+        T vmin = Rl::inf();
+        T best = Rl::inf();
+        int best_idx = 0x7fffffff;
+        T bgx = T(0), bgy = T(0), bgz = T(0), bmx = T(0), bmy = T(0), bmz = T(0);
+        unsigned long long bmask = 0;
+
+        // one (configuration c, round r) step; A / B are the round's per-lane sphere constants
+        auto step = [&](const int c, const int r, const int4 rd, const V4 &A, const int4 &B) {
             const long long n = n0 + c;
             const V4 *fr = reinterpret_cast<const V4 *>(wframes + c * fstride);
             const T *tw = wtw + c * tstride;
-            T vmin = Rl::inf();
-            T best = Rl::inf();
-            int best_idx = 0x7fffffff;
-            T bgx = T(0), bgy = T(0), bgz = T(0), bmx = T(0), bmy = T(0), bmz = T(0);
-            unsigned long long bmask = 0;
-
-            for (int r = 0; r < n_rounds; ++r) {
-                const int4 rd = roundI[r];                     // s0, cnt, -, -
-                const V4 A = tabA[r * 32 + lane];
-                const int4 B = tabB[r * 32 + lane];
+            {
                 const bool has = B.w != 0;
                 const V4 f0 = fr[3 * B.x], f1 = fr[3 * B.x + 1], f2 = fr[3 * B.x + 2];
                 const T px = f0.w + f0.x * A.x + f0.y * A.y + f0.z * A.z;
@@ -232,8 +274,9 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
                 T gx = T(0), gy = T(0), gz = T(0);
 
                 if (KIND == KIND_COLLFREE) {
-                    const T d = SINGLE ? sdf_prim_world<T>(prm.prim0, px, py, pz, gx, gy, gz)
-                                       : sdf_union<T>(sP, prm.n_prims, px, py, pz, gx, gy, gz);
+                    const T d = SDFK == SDF_GRID_FAST ? sdf_grid_fast(prm.prim0, px, py, pz, gx, gy, gz)
+                              : SDFK == SDF_SINGLE    ? sdf_prim_world<T>(prm.prim0, px, py, pz, gx, gy, gz)
+                                                      : sdf_union<T>(sP, prm.n_prims, px, py, pz, gx, gy, gz);
                     const T val = d - A.w - prm.margin;
                     if (has) vmin = val < vmin ? val : vmin;
                     if (CLOSEST) {
@@ -244,7 +287,7 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
                             bgx = gx; bgy = gy; bgz = gz;
                             bmx = py * gz - pz * gy; bmy = pz * gx - px * gz; bmz = px * gy - py * gx;
                         }
-                        continue;
+                        return;
                     }
                     if (prm.out_vals != nullptr && has) st_stream(prm.out_vals + n * S + rd.x + lane, val);
                 } else {
@@ -253,7 +296,7 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
                         st_stream(g, px); st_stream(g + 1, py); st_stream(g + 2, pz);
                     }
                 }
-                if (!WITH_JAC || CLOSEST) continue;
+                if (!WITH_JAC || CLOSEST) return;
 
                 // ---- Jacobian rows of this lane's sphere, all D columns, assembled VW at a time
                 const unsigned long long cm = prm.round_cm[r];               // warp-uniform (constant bank)
@@ -349,8 +392,13 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
                     }
                 }
                 stage_sel ^= 1;
-            }   // rounds
+            }
+        };   // step
 
+        // per-configuration epilogue of the reducing modes
+        auto finish = [&](const int c) {
+            const long long n = n0 + c;
+            const T *tw = wtw + c * tstride;
             if (KIND == KIND_COLLFREE) {
                 if (prm.out_valid != nullptr) {
                     T m = vmin;
@@ -384,7 +432,23 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
                     }
                 }
             }
-        }   // configurations of the tile
+            vmin = Rl::inf(); best = Rl::inf(); best_idx = 0x7fffffff;
+        };
+
+        if (!CLOSEST && prm.out_valid == nullptr) {
+            // no per-configuration reduction: rounds outermost, so each round's sphere table is read once per tile
+            for (int r = 0; r < n_rounds; ++r) {
+                const int4 rd = roundI[r];
+                const V4 A = tabA[r * 32 + lane];
+                const int4 B = tabB[r * 32 + lane];
+                for (int c = 0; c < g_live; ++c) step(c, r, rd, A, B);
+            }
+        } else {
+            for (int c = 0; c < g_live; ++c) {
+                for (int r = 0; r < n_rounds; ++r) step(c, r, roundI[r], tabA[r * 32 + lane], tabB[r * 32 + lane]);
+                finish(c);
+            }
+        }
     }       // tiles
     if (WITH_JAC && !CLOSEST) bulk_wait_read<0>();   // shared memory must outlive the last bulk reads
 }
@@ -438,7 +502,7 @@ static int sm_count_cached() {
     return sms;
 }
 
-template <typename T, int KIND, bool WITH_JAC, bool CLOSEST, bool SINGLE, int VW, typename MaskT>
+template <typename T, int KIND, bool WITH_JAC, bool CLOSEST, int SDFK, int VW, typename MaskT>
 static int launch_sphere_inst(const skb_plan *p, const skb_sphere_program *sp, const void *q, int64_t N, const void *dev_prims,
                               const void *host_prims, int n_prims, double margin, void *out_vals, void *out_jac,
                               uint8_t *out_valid, cudaStream_t stream) {
@@ -468,7 +532,7 @@ static int launch_sphere_inst(const skb_plan *p, const skb_sphere_program *sp, c
     const bool stage = WITH_JAC && !CLOSEST;
     prm.off_F = align_up(prm.i_total * 4, 16);
     prm.off_prims = align_up(prm.off_F + prm.f_total * (int)sizeof(T), 16);
-    prm.off_warp = align_up(prm.off_prims + ((KIND == KIND_COLLFREE && !SINGLE) ? n_prims : 0) * (int)sizeof(DevPrim<T>), 128);
+    prm.off_warp = align_up(prm.off_prims + ((KIND == KIND_COLLFREE && SDFK == SDF_UNION) ? n_prims : 0) * (int)sizeof(DevPrim<T>), 128);
     const int al = 16 / (int)sizeof(T);
     const int PER = al;
     // every round block [s0*ROWS*D, +cnt*ROWS*D) of every configuration must be 16-byte aligned for vector copy-out
@@ -488,6 +552,7 @@ static int launch_sphere_inst(const skb_plan *p, const skb_sphere_program *sp, c
     auto layout = [&](int g) {
         int e = 0;
         prm.woff_q = e;      e += align_up(g * D, al);
+        prm.woff_sc = e;     e += align_up(2 * g * D, al);
         prm.woff_frames = e; e += g * prm.fstride;
         prm.woff_tw = e;     e += WITH_JAC ? g * prm.tstride : 0;
         prm.stage_elems = align_up(32 * ROWS * D, al);
@@ -507,7 +572,7 @@ static int launch_sphere_inst(const skb_plan *p, const skb_sphere_program *sp, c
     prm.logG = 0;
     while ((1 << prm.logG) < G) ++prm.logG;
     prm.n_tiles = (N + G - 1) / G;
-    auto kern = sphere_kernel<T, KIND, WITH_JAC, CLOSEST, SINGLE, VW, MaskT>;
+    auto kern = sphere_kernel<T, KIND, WITH_JAC, CLOSEST, SDFK, VW, MaskT>;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
@@ -526,39 +591,46 @@ static int launch_sphere_inst(const skb_plan *p, const skb_sphere_program *sp, c
                 int n_prims, double margin, void *out_vals, void *out_jac, uint8_t *out_valid, cudaStream_t stream
 
 // all-spheres mode with Jacobian: pick the widest row store that keeps each lane's row start aligned, and the mask width
-template <typename T, int KIND, bool SINGLE>
+template <typename T, int KIND, int SDFK>
 static int launch_sphere_jac(SKB_SIG) {
     const int D = p->D;
     const int bytes = D * (int)sizeof(T);
     const bool wide = D > 32;
     if (bytes % 16 == 0 && sizeof(T) == 4)
-        return wide ? launch_sphere_inst<T, KIND, true, false, SINGLE, 4, unsigned long long>(SKB_ARGS)
-                    : launch_sphere_inst<T, KIND, true, false, SINGLE, 4, unsigned>(SKB_ARGS);
+        return wide ? launch_sphere_inst<T, KIND, true, false, SDFK, 4, unsigned long long>(SKB_ARGS)
+                    : launch_sphere_inst<T, KIND, true, false, SDFK, 4, unsigned>(SKB_ARGS);
     if ((bytes % 8 == 0 && sizeof(T) == 4) || (bytes % 16 == 0 && sizeof(T) == 8))
-        return wide ? launch_sphere_inst<T, KIND, true, false, SINGLE, 2, unsigned long long>(SKB_ARGS)
-                    : launch_sphere_inst<T, KIND, true, false, SINGLE, 2, unsigned>(SKB_ARGS);
-    return wide ? launch_sphere_inst<T, KIND, true, false, SINGLE, 1, unsigned long long>(SKB_ARGS)
-                : launch_sphere_inst<T, KIND, true, false, SINGLE, 1, unsigned>(SKB_ARGS);
+        return wide ? launch_sphere_inst<T, KIND, true, false, SDFK, 2, unsigned long long>(SKB_ARGS)
+                    : launch_sphere_inst<T, KIND, true, false, SDFK, 2, unsigned>(SKB_ARGS);
+    return wide ? launch_sphere_inst<T, KIND, true, false, SDFK, 1, unsigned long long>(SKB_ARGS)
+                : launch_sphere_inst<T, KIND, true, false, SDFK, 1, unsigned>(SKB_ARGS);
 }
 
-template <typename T, bool SINGLE>
+template <typename T, int SDFK>
 static int launch_sphere_collfree(SKB_SIG, int mode) {
     const bool wj = out_jac != nullptr;
     if (mode == SKB_MODE_CLOSEST)
-        return wj ? launch_sphere_inst<T, KIND_COLLFREE, true, true, SINGLE, 1, unsigned long long>(SKB_ARGS)
-                  : launch_sphere_inst<T, KIND_COLLFREE, false, true, SINGLE, 1, unsigned long long>(SKB_ARGS);
-    if (wj) return launch_sphere_jac<T, KIND_COLLFREE, SINGLE>(SKB_ARGS);
-    return launch_sphere_inst<T, KIND_COLLFREE, false, false, SINGLE, 1, unsigned>(SKB_ARGS);
+        return wj ? launch_sphere_inst<T, KIND_COLLFREE, true, true, SDFK, 1, unsigned long long>(SKB_ARGS)
+                  : launch_sphere_inst<T, KIND_COLLFREE, false, true, SDFK, 1, unsigned long long>(SKB_ARGS);
+    if (wj) return launch_sphere_jac<T, KIND_COLLFREE, SDFK>(SKB_ARGS);
+    return launch_sphere_inst<T, KIND_COLLFREE, false, false, SDFK, 1, unsigned>(SKB_ARGS);
 }
 
 template <typename T>
 static int launch_sphere_t(SKB_SIG, int kind, int mode) {
     if (kind == KIND_MAP) {
-        if (out_jac != nullptr) return launch_sphere_jac<T, KIND_MAP, true>(SKB_ARGS);
-        return launch_sphere_inst<T, KIND_MAP, false, false, true, 1, unsigned>(SKB_ARGS);
+        if (out_jac != nullptr) return launch_sphere_jac<T, KIND_MAP, SDF_SINGLE>(SKB_ARGS);
+        return launch_sphere_inst<T, KIND_MAP, false, false, SDF_SINGLE, 1, unsigned>(SKB_ARGS);
     }
-    if (n_prims == 1) return launch_sphere_collfree<T, true>(SKB_ARGS, mode);
-    return launch_sphere_collfree<T, false>(SKB_ARGS, mode);
+    if (n_prims == 1) {
+        const DevPrim<T> *pr = reinterpret_cast<const DevPrim<T> *>(host_prims);
+        const long long cells = (long long)(pr->dims[0] - 1) * (pr->dims[1] - 1) * (pr->dims[2] - 1);
+        if (sizeof(T) == 4 && pr->type == PRIM_GRID && (pr->flags & PF_GRID_CELLS) && (pr->flags & PF_IDENTITY) &&
+            !(pr->flags & PF_GRID_F64) && cells < (1ll << 31))
+            return launch_sphere_collfree<T, SDF_GRID_FAST>(SKB_ARGS, mode);
+        return launch_sphere_collfree<T, SDF_SINGLE>(SKB_ARGS, mode);
+    }
+    return launch_sphere_collfree<T, SDF_UNION>(SKB_ARGS, mode);
 }
 
 int launch_sphere(const skb_plan *p, const skb_sphere_program *sp, int kind, int dtype, const void *q, int64_t N,
