@@ -85,40 +85,61 @@ def joint_bounds(colkin):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML through
+    pynvml (~1 ms per sample) so that even a 30 ms timed region gets tens of samples; falls back to the
+    nvidia-smi query line of the recipe when pynvml is missing."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self._stop_evt = index, threading.Event()
+        self.sm, self.mx, self.reasons, self.how = [], [], set(), "nvml"
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nv, self.how = None, "nvidia-smi"
+
+    def _nvml_once(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _smi_once(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            r = [c.strip() for c in out.split(",")]
+            self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self._nvml_once() if self.nv is not None else self._smi_once()
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.002 if self.nv is not None else 0.1)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.how}
 
 
 def cpu_reference_rate(colkin, grid, lo, hi, seconds: float, threads: int):
@@ -285,7 +306,7 @@ def run_b200(args):
                        "valid_fraction": valid_frac},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_config": BYTES_PER_CONFIG,
-                         "kernel_ms": kernel_ms, "kernel": "tree_kernel<float,8,COLLFREE,jac>"},
+                         "kernel_ms": kernel_ms, "kernel": "skb::sphere_kernel<float, COLLFREE, jac, all, grid-fast, VW2, u32>"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "configs/s", "h2d_bytes_per_step": n * D * 4, "d2h_bytes_per_step": n * (S + S * D) * 4,
                     "steps": e2e_steps, "api": "CollFreeConst.evaluate(numpy (N,14) float32, with_jacobian=True) -> numpy", "check": chk},
