@@ -1,0 +1,186 @@
+"""Batched callers of the hot path (SURVEY.md 8f "next" rows 1 and 2).
+
+The reference feeds the constraint API one configuration at a time:
+  * edge validity  -- ``is_valid_motion_step`` evaluates every interpolated sample of an edge with
+    ``evaluate_single`` in a Python loop                       (skmp/solver/motion_step_box.py:8-57)
+  * SQP stacking   -- ``TrajectoryConstraint.evaluate`` calls ``evaluate_single`` per waypoint, fills a dense
+    (M_total x n_wp*D) matrix and converts it to CSC          (skmp/solver/nlp_solver/trajectory_constraint.py:128-195)
+Here both become ONE kernel launch per distinct constraint, with identical results:
+  * ``interpolate_fractions_batch`` / ``is_valid_motion_step_batch``: all samples of all edges in one
+    ``is_valid_batch`` call + a per-edge AND reduction (BASELINE config 5: RRT edge validity);
+  * ``TrajectoryConstraintStack``: per-waypoint blocks from one batched ``evaluate`` and the block-diagonal CSC
+    ``data`` array written directly (BASELINE config 4: 4096 trajectories x 100 waypoints).
+"""
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._array import _is_torch, torch
+
+
+# ------------------------------------------------------------------ edge discretisation
+def interpolate_fractions_batch(motion_step_box: np.ndarray, q1s: np.ndarray, q2s: np.ndarray,
+                                include_q1: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """Vectorised ``interpolate_fractions`` (motion_step_box.py:8-41) for E edges.
+
+    Returns (fractions (n_samples,), offsets (E+1,)): edge e owns ``fractions[offsets[e]:offsets[e+1]]``.
+    Per edge this reproduces the reference list exactly, including its quirks: an edge shorter than 1e-6 on
+    its active axis yields no sample; an edge shorter than one step yields only [1.0] (q1 is dropped even
+    when ``include_q1``); the running sum ``travel_rate += step_ratio`` is accumulated sequentially."""
+    box = np.asarray(motion_step_box, dtype=np.float64)
+    q1s, q2s = np.atleast_2d(np.asarray(q1s, dtype=np.float64)), np.atleast_2d(np.asarray(q2s, dtype=np.float64))
+    assert q1s.shape == q2s.shape and q1s.shape[1] == len(box)
+    E = len(q1s)
+    diff = q2s - q1s
+    active = np.argmax(np.abs(diff) / box, axis=1)
+    d_act = np.abs(diff[np.arange(E), active])
+    too_close = d_act < 1e-6
+    with np.errstate(divide="ignore"):
+        step = box[active] / d_act
+    single = (~too_close) & (step > 1.0)
+    multi = (~too_close) & ~single
+    counts = np.zeros(E, dtype=np.int64)
+    counts[single] = 1
+    frac_rows: Dict[int, np.ndarray] = {}
+    if multi.any():
+        idx = np.nonzero(multi)[0]
+        st = step[idx]
+        kmax = int(np.ceil(1.0 / st.min())) + 2
+        # travel[:, k] = value of travel_rate after k sequential additions (cumsum adds left to right)
+        travel = np.concatenate([np.zeros((len(idx), 1)), np.cumsum(np.repeat(st[:, None], kmax, axis=1), axis=1)], axis=1)
+        # the while loop appends travel[k+1] as long as travel[k] + step < 1.0
+        take = (travel[:, :-1] + st[:, None]) < 1.0
+        n_steps = np.where(take.all(axis=1), kmax, np.argmin(take, axis=1))      # first False = number of appended steps
+        for row, e in enumerate(idx):
+            fr = travel[row, 1: n_steps[row] + 1]
+            if include_q1:
+                fr = np.concatenate([[0.0], fr])
+            if len(fr) == 0 or abs(fr[-1] - 1.0) > 1e-6:
+                fr = np.concatenate([fr, [1.0]])
+            frac_rows[int(e)] = fr
+            counts[e] = len(fr)
+    offsets = np.concatenate([[0], np.cumsum(counts)])
+    fractions = np.empty(offsets[-1])
+    for e in np.nonzero(single)[0]:
+        fractions[offsets[e]] = 1.0
+    for e, fr in frac_rows.items():
+        fractions[offsets[e]: offsets[e + 1]] = fr
+    return fractions, offsets
+
+
+def edge_samples(motion_step_box, q1s, q2s, include_q1: bool = True):
+    """All interpolated configurations of all edges -> (samples (n_samples, D), offsets (E+1,))."""
+    q1s, q2s = np.atleast_2d(np.asarray(q1s, dtype=np.float64)), np.atleast_2d(np.asarray(q2s, dtype=np.float64))
+    fractions, offsets = interpolate_fractions_batch(motion_step_box, q1s, q2s, include_q1)
+    edge_of = np.repeat(np.arange(len(q1s)), np.diff(offsets))
+    samples = q1s[edge_of] + (q2s[edge_of] - q1s[edge_of]) * fractions[:, None]      # q1 + (q2 - q1) * frac, as the reference
+    return samples, offsets
+
+
+def is_valid_motion_step_batch(motion_step_box, q1s, q2s, ineq_const, dtype=np.float32, device=None) -> np.ndarray:
+    """``is_valid_motion_step`` (motion_step_box.py:44-57) for E edges at once -> (E,) bool.
+
+    An edge is valid iff every sample satisfies ``all(values > 0)``; an edge with no sample is valid.
+    One ``is_valid_batch`` launch over all samples; the per-edge AND is a segmented min on the device."""
+    samples, offsets = edge_samples(motion_step_box, q1s, q2s, include_q1=True)
+    E = len(offsets) - 1
+    if len(samples) == 0:
+        return np.ones(E, dtype=bool)
+    if torch is not None and torch.cuda.is_available():
+        dev = torch.device("cuda") if device is None else device
+        q = torch.as_tensor(samples.astype(dtype), device=dev)
+        ok = ineq_const.is_valid_batch(q).to(torch.uint8)
+        lengths = torch.as_tensor(np.diff(offsets), device=dev)
+        per_edge = torch.segment_reduce(ok.float(), "min", lengths=lengths, initial=1.0)
+        return (per_edge > 0.5).cpu().numpy()
+    ok = np.asarray(ineq_const.is_valid_batch(samples.astype(dtype)))      # host constraints (BoxConst ...) only
+    out = np.ones(E, dtype=bool)
+    nz = np.diff(offsets) > 0
+    out[nz] = np.minimum.reduceat(ok.astype(np.uint8), offsets[:-1][nz]).astype(bool)
+    return out
+
+
+# ------------------------------------------------------------------ trajectory-constraint stacking for SQP
+class TrajectoryConstraintStack:
+    """Batched ``TrajectoryConstraint.evaluate`` (trajectory_constraint.py:128-195) for the local-constraint table.
+
+    ``local_constraint_table`` maps waypoint index -> constraint (insertion order = row order, like the
+    reference's ``local_table.keys()`` loop).  Waypoints sharing one constraint object are evaluated in ONE
+    batched call.  The Jacobian is block diagonal; its CSC pattern is fixed by the table, so ``indices`` /
+    ``indptr`` are built once (the reference's ``determine_sparse_pattern``) and ``evaluate`` only writes ``data``.
+    """
+
+    def __init__(self, n_dof: int, n_wp: int, local_constraint_table: Dict[int, object]):
+        self.n_dof, self.n_wp = n_dof, n_wp
+        self.table = dict(local_constraint_table)
+        for i in self.table:
+            if not (0 <= i < n_wp):
+                raise ValueError("index {} exceeds the waypoint number {}".format(i, n_wp))
+        self._pattern = None
+
+    # groups: constraint object -> waypoint indices, in table order
+    def _groups(self):
+        groups: Dict[int, Tuple[object, List[int]]] = {}
+        for i, const in self.table.items():
+            groups.setdefault(id(const), (const, []))[1].append(i)
+        return list(groups.values())
+
+    def _blocks(self, traj: np.ndarray):
+        """waypoint index -> (values (M_i,), jac (M_i, n_dof)) as numpy fp64, one launch per distinct constraint."""
+        out = {}
+        for const, idxs in self._groups():
+            vals, jac = const.evaluate(traj[idxs], True)
+            if _is_torch(vals):
+                vals, jac = vals.cpu().numpy(), jac.cpu().numpy()
+            for k, i in enumerate(idxs):
+                out[i] = (np.asarray(vals[k], dtype=np.float64), np.asarray(jac[k], dtype=np.float64))
+        return out
+
+    def _build_pattern(self, dims: Dict[int, int]):
+        heads, head = {}, 0
+        for i in self.table:                       # row order = table order
+            heads[i] = head
+            head += dims[i]
+        indptr = np.zeros(self.n_dof * self.n_wp + 1, dtype=np.int64)
+        indices = []
+        for i in range(self.n_wp):                 # column order = waypoint order
+            m = dims.get(i, 0)
+            for d in range(self.n_dof):
+                indptr[i * self.n_dof + d + 1] = indptr[i * self.n_dof + d] + m
+                if m:
+                    indices.append(heads[i] + np.arange(m))
+        self._pattern = (heads, head, np.concatenate(indices) if indices else np.zeros(0, dtype=np.int64), indptr, dict(dims))
+
+    def evaluate(self, traj_vector: np.ndarray):
+        """-> (values (M_total,), scipy.sparse.csc_matrix (M_total, n_wp * n_dof)), equal to the reference's."""
+        from scipy.sparse import csc_matrix
+
+        traj = np.asarray(traj_vector).reshape(-1, self.n_dof)
+        assert len(traj) == self.n_wp
+        blocks = self._blocks(traj)
+        dims = {i: len(blocks[i][0]) for i in self.table}
+        if self._pattern is None or self._pattern[4] != dims:
+            self._build_pattern(dims)
+        heads, m_total, indices, indptr, _ = self._pattern
+        values = np.concatenate([blocks[i][0] for i in self.table]) if self.table else np.zeros(0)
+        # column (i, d) holds jac_i[:, d]: per waypoint the (n_dof, M_i) transpose, waypoints in ascending order
+        data = [blocks[i][1].T.reshape(-1) for i in sorted(self.table)]
+        data = np.concatenate(data) if data else np.zeros(0)
+        return values, csc_matrix((data, indices, indptr), shape=(m_total, self.n_dof * self.n_wp))
+
+    def evaluate_batch(self, traj_vectors):
+        """B trajectories at once (BASELINE config 4).  ``traj_vectors`` (B, n_wp * n_dof), numpy or CUDA torch.
+        -> dict waypoint index -> (values (B, M_i), jac (B, M_i, n_dof)): the diagonal blocks of every trajectory's
+        stacked Jacobian, produced by one launch per distinct constraint over all B x (its waypoints) rows.
+        Arrays stay on the device when the input is a CUDA tensor."""
+        B = traj_vectors.shape[0]
+        trajs = traj_vectors.reshape(B, self.n_wp, self.n_dof)
+        out = {}
+        for const, idxs in self._groups():
+            rows = trajs[:, idxs, :].reshape(B * len(idxs), self.n_dof)
+            vals, jac = const.evaluate(rows, True)
+            vals = vals.reshape(B, len(idxs), -1)
+            jac = jac.reshape(B, len(idxs), -1, self.n_dof)
+            for k, i in enumerate(idxs):
+                out[i] = (vals[:, k], jac[:, k])
+        return out
