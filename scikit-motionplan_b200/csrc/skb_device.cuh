@@ -17,7 +17,8 @@ template <> struct Real<float> {
     static __device__ __forceinline__ float floor(float x) { return floorf(x); }
     static __device__ __forceinline__ float atan2(float y, float x) { return atan2f(y, x); }
     static __device__ __forceinline__ float asin(float x) { return asinf(x); }
-    static __device__ __forceinline__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }   // never contracted
     static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
 };
 template <> struct Real<double> {
@@ -28,9 +29,32 @@ template <> struct Real<double> {
     static __device__ __forceinline__ double floor(double x) { return ::floor(x); }
     static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
     static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
-    static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 };
+
+// Fixed-association building blocks of the chain rule.  Every kernel instantiation (all-spheres, closest, packed
+// f32x2) must produce the same bits for the same sphere, so the contraction order is spelled out instead of being
+// left to the compiler's FMA contraction: cross = fma(a, b, -(c*d)), dot6 = mul, then five fma in w.xyz, v.xyz order
+// (exactly what the packed mul.rn.f32x2 / fma.rn.f32x2 chain computes per half).
+template <typename T>
+__device__ __forceinline__ void wrench_moment(T px, T py, T pz, T gx, T gy, T gz, T &mx, T &my, T &mz) {
+    using R = Real<T>;
+    mx = R::fma(py, gz, -R::mul(pz, gy));
+    my = R::fma(pz, gx, -R::mul(px, gz));
+    mz = R::fma(px, gy, -R::mul(py, gx));
+}
+template <typename T>
+__device__ __forceinline__ T dot6(T wx, T wy, T wz, T vx, T vy, T vz, T mx, T my, T mz, T gx, T gy, T gz) {
+    using R = Real<T>;
+    T a = R::mul(wx, mx);
+    a = R::fma(wy, my, a);
+    a = R::fma(wz, mz, a);
+    a = R::fma(vx, gx, a);
+    a = R::fma(vy, gy, a);
+    return R::fma(vz, gz, a);
+}
 
 // ------------------------------------------------------------------ SDF primitives (local frame)
 // Each returns the signed distance and writes the analytic gradient (local frame).

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
                             best = val; best_idx = rd.x + lane;
                             bmask = ((unsigned long long)(unsigned)B.z << 32) | (unsigned)B.y;
                             bgx = gx; bgy = gy; bgz = gz;
-                            bmx = py * gz - pz * gy; bmy = pz * gx - px * gz; bmz = px * gy - py * gx;
+                            wrench_moment<T>(px, py, pz, gx, gy, gz, bmx, bmy, bmz);
                         }
                         return;
                     }
@@ -301,7 +301,8 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
                 // ---- Jacobian rows of this lane's sphere, all D columns, assembled VW at a time
                 const unsigned long long cm = prm.round_cm[r];               // warp-uniform (constant bank)
                 const MaskT am = sizeof(MaskT) == 8 ? (MaskT)(((unsigned long long)(unsigned)B.z << 32) | (unsigned)B.y) : (MaskT)(unsigned)B.y;
-                const T mx = py * gz - pz * gy, my = pz * gx - px * gz, mz = px * gy - py * gx;   // wrench moment p x g
+                T mx, my, mz;                                                 // wrench moment p x g
+                wrench_moment<T>(px, py, pz, gx, gy, gz, mx, my, mz);
                 T *row0 = wstage + stage_sel * stage_elems;
                 T *row = row0 + lane * (ROWS * D);
                 // the bulk store issued from this buffer two rounds ago must have finished reading it
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
                                 const V4 v = *reinterpret_cast<const V4 *>(tw + col * 8 + 4);
                                 const bool mine = (am >> col) & 1;
                                 if (KIND == KIND_COLLFREE) {
-                                    const T jv = w.x * mx + w.y * my + w.z * mz + v.x * gx + v.y * gy + v.z * gz;
+                                    const T jv = dot6<T>(w.x, w.y, w.z, v.x, v.y, v.z, mx, my, mz, gx, gy, gz);
                                     v0[u] = mine ? jv : T(0);
                                 } else {                                // d p / d q_col = omega x p + v
                                     v0[u] = mine ? (w.y * pz - w.z * py + v.x) : T(0);
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
                             if ((am >> col) & 1ull) {
                                 const V4 w = *reinterpret_cast<const V4 *>(tw + col * 8);
                                 const V4 v = *reinterpret_cast<const V4 *>(tw + col * 8 + 4);
-                                jv = w.x * mx + w.y * my + w.z * mz + v.x * gx + v.y * gy + v.z * gz;
+                                jv = dot6<T>(w.x, w.y, w.z, v.x, v.y, v.z, mx, my, mz, gx, gy, gz);
                             }
                             prm.out_jac[n * D + col] = jv;
                         }
