@@ -213,6 +213,79 @@ __device__ __forceinline__ T sdf_union(const DevPrim<T> *prims, int np, T px, T 
     return best;
 }
 
+// ------------------------------------------------------------------ forward kinematics of one tile (warp-cooperative)
+template <typename T> struct alignas(16) Vec4 { T x, y, z, w; };
+
+// Level-by-level tree walk for the G configurations of a warp's tile, THREE lanes per (configuration, node): row r of a
+// node frame  Y = parent * pre * Rz(q)  depends only on row r of the parent frame, so each lane carries one row
+// [R_r0 R_r1 R_r2 t_r]; the joint twist (omega = third column, v = o x omega) needs the other two rows' (o, omega)
+// entries, fetched with four warp shuffles.  lane -> (row = lane % 3, cfg = (lane / 3) % G, slot = lane / 3 / G);
+// `slots3` = 32 / (3 G) nodes of a level are processed at once (G <= 8).  Frames go to `wframes` (rows of 4, 12 per node),
+// twists to `wtw` in the scalar layout [wx wy wz . | vx vy vz .] per column or, PAIR, component-interleaved per column
+// pair [wx_j wx_j1 wy_j wy_j1 | wz_j wz_j1 vx_j vx_j1 | vy_j vy_j1 vz_j vz_j1].
+template <typename T, bool WITH_JAC, bool PAIR>
+__device__ __forceinline__ void fk_phase(const int lane, const int G, const int logG, const int slots3, const int g_live,
+                                         const int D, const int n_levels, const int32_t *nodeI, const int32_t *levelI,
+                                         const int32_t *levelNodes, const Vec4<T> *nodeF, const T *wq, const T *wsc,
+                                         T *wframes, const int fstride, T *wtw, const int tstride) {
+    using V4 = Vec4<T>;
+    const int row = lane % 3, t = lane / 3;
+    const int cfg = t & (G - 1), slot = t >> logG;
+    const bool act = slot < slots3;
+    const int base = lane - row;
+    const int src1 = base + (row == 2 ? 0 : row + 1), src2 = base + (row == 0 ? 2 : row - 1);
+    const int ccfg = min(cfg, g_live - 1);          // dead configurations of a ragged last tile recompute a live one
+    const T *myq = wq + ccfg * D;
+    const T *mysc = wsc + 2 * ccfg * D;
+    V4 *fr = reinterpret_cast<V4 *>(wframes + cfg * fstride);
+    T *tw = wtw + cfg * tstride;
+    for (int lv = 0; lv < n_levels; ++lv) {
+        const int lbeg = levelI[2 * lv], lcnt = levelI[2 * lv + 1];
+        for (int k0 = 0; k0 < lcnt; k0 += slots3) {
+            const int k = k0 + slot;
+            const bool on = act && k < lcnt;
+            const int node = levelNodes[lbeg + (on ? k : 0)];
+            const int type = nodeI[4 * node], col = nodeI[4 * node + 1], par = nodeI[4 * node + 2];
+            V4 y;
+            if (par < 0) y = nodeF[3 * node + row];
+            else {
+                const V4 c0 = nodeF[3 * node], c1 = nodeF[3 * node + 1], c2 = nodeF[3 * node + 2];
+                const V4 P = fr[3 * par + row];
+                y.x = P.x * c0.x + P.y * c1.x + P.z * c2.x;
+                y.y = P.x * c0.y + P.y * c1.y + P.z * c2.y;
+                y.z = P.x * c0.z + P.y * c1.z + P.z * c2.z;
+                y.w = P.w + P.x * c0.w + P.y * c1.w + P.z * c2.w;
+            }
+            // (o, omega) entries of the two other rows: joint axis = local +z = third column, origin = fourth
+            const T o1 = __shfl_sync(0xffffffffu, y.w, src1), o2 = __shfl_sync(0xffffffffu, y.w, src2);
+            const T w1 = __shfl_sync(0xffffffffu, y.z, src1), w2 = __shfl_sync(0xffffffffu, y.z, src2);
+            T wr = T(0), vr = T(0);
+            if (type == NODE_REVOLUTE) {
+                const T s = mysc[2 * col], c = mysc[2 * col + 1];
+                wr = y.z;
+                vr = o1 * w2 - o2 * w1;                       // v = o x omega, component `row`
+                const T a = y.x, b = y.y;
+                y.x = c * a + s * b; y.y = c * b - s * a;
+            } else if (type == NODE_PRISMATIC) {
+                vr = y.z;
+                y.w += myq[col] * y.z;
+            }
+            if (on) {
+                fr[3 * node + row] = y;
+                if (WITH_JAC && col >= 0) {
+                    if (PAIR) {
+                        T *t2 = tw + (col >> 1) * 12 + (col & 1);
+                        t2[2 * row] = wr; t2[6 + 2 * row] = vr;
+                    } else {
+                        tw[col * 8 + row] = wr; tw[col * 8 + 4 + row] = vr;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------ bulk async store helpers (sm_90+/sm_100a)
 // cp.async.bulk shared::cta -> global (1-D TMA): SASS UBLKCP.  16-byte aligned src/dst/size.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -656,6 +656,156 @@ const skb_sphere_program *get_sphere_program(skb_plan *p) {
     return &sp;
 }
 
+
+// ------------------------------------------------------------------ step program (skb_sphere2.cu)
+// Rows (spheres or pairs) are cut into half-rounds of 32; adjacent half-rounds are fused into one two-rows-per-lane
+// step when that is cheaper under a simple issue-slot model (a fused step loads each twist pair once for both rows
+// but computes the union of the two halves' column sets).
+static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp) {
+    sp->built = true;
+    sp->supported = false;
+    const int n_nodes = (int)p->nodes.size(), nf = p->F, D = p->D;
+    const bool pairs = kind == KIND_PAIRWISE;
+    const int rows = pairs ? (int)p->pair_thr.size() : nf;
+    if (p->rot_type != SKB_ROT_IGNORE || D < 1 || D > (pairs ? 32 : 64) || n_nodes > 255 || rows < 1) return 0;
+    if (pairs && nf > 4096) return 0;
+    const char *force = getenv("SKB_KERNEL");
+    if (force && (std::string(force) == "tree" || std::string(force) == "sphere1")) return 0;
+    int n_levels = 0;
+    std::vector<int> level(n_nodes, 0);
+    for (int k = 0; k < n_nodes; ++k) {
+        level[k] = p->nodes[k].parent < 0 ? 0 : level[p->nodes[k].parent] + 1;
+        n_levels = std::max(n_levels, level[k] + 1);
+    }
+    std::vector<std::vector<int>> lv(n_levels);
+    for (int k = 0; k < n_nodes; ++k) lv[level[k]].push_back(k);
+    std::vector<uint64_t> nmask(n_nodes, 0);
+    for (int k = 1; k < n_nodes; ++k) {
+        nmask[k] = nmask[p->nodes[k].parent];
+        if (p->nodes[k].col >= 0) nmask[k] |= (uint64_t)1 << p->nodes[k].col;
+    }
+    // per-row column masks (pairs: plus = columns moving sphere i only, minus = sphere j only)
+    std::vector<uint64_t> plus(rows), minus(rows, 0);
+    for (int r = 0; r < rows; ++r) {
+        if (pairs) {
+            const int fi = p->pair_idx[2 * r], fj = p->pair_idx[2 * r + 1];
+            if (fi < 0 || fi >= nf || fj < 0 || fj >= nf) return set_error("pairs: feature index out of range");
+            const uint64_t mi = nmask[p->feat_node[fi]], mj = nmask[p->feat_node[fj]];
+            plus[r] = mi & ~mj; minus[r] = mj & ~mi;
+        } else plus[r] = nmask[p->feat_node[r]];
+    }
+    const int n_hr = (rows + 31) / 32;
+    std::vector<uint64_t> hcm(n_hr, 0);
+    for (int r = 0; r < rows; ++r) hcm[r / 32] |= plus[r] | minus[r];
+    auto npairs = [&](uint64_t m) { int c = 0; for (int j = 0; j < D; j += 2) if ((m >> j) & 3) ++c; return c; };
+    // dynamic programme over "single" / "fused with the next half-round"
+    std::vector<double> best(n_hr + 2, 0.0);
+    std::vector<char> fuse(n_hr + 1, 0);
+    for (int i = n_hr - 1; i >= 0; --i) {
+        const double single = 30.0 + 17.0 * npairs(hcm[i]) + best[i + 1];
+        best[i] = single; fuse[i] = 0;
+        if (i + 1 < n_hr) {
+            const double both = 40.0 + 29.0 * npairs(hcm[i] | hcm[i + 1]) + best[i + 2];
+            if (both < single) { best[i] = both; fuse[i] = 1; }
+        }
+    }
+    sp->steps.clear();
+    for (int i = 0; i < n_hr;) {
+        skb_s2_step st;
+        st.s0 = i * 32;
+        st.cntA = (int16_t)std::min(32, rows - i * 32);
+        if (fuse[i]) { st.cntB = (int16_t)std::min(32, rows - (i + 1) * 32); st.cm = hcm[i] | hcm[i + 1]; i += 2; }
+        else { st.cntB = 0; st.cm = hcm[i]; i += 1; }
+        sp->steps.push_back(st);
+    }
+    const int n_steps = (int)sp->steps.size();
+    if (n_steps > S2_MAX_STEPS) return 0;
+
+    std::vector<int32_t> &I = sp->I;
+    std::vector<double> &Fv = sp->F;
+    I.assign(QHDR_WORDS, 0);
+    I[Q_N_NODES] = n_nodes; I[Q_N_LEVELS] = n_levels; I[Q_N_STEPS] = n_steps; I[Q_D] = D; I[Q_ROWS] = rows;
+    I[Q_N_CEN] = pairs ? nf : 0;
+    I[Q_NODE_I] = (int)I.size();
+    for (int k = 0; k < n_nodes; ++k) { I.push_back(p->nodes[k].type); I.push_back(p->nodes[k].col); I.push_back(p->nodes[k].parent); I.push_back(0); }
+    I[Q_LEVEL_I] = (int)I.size();
+    int cursor = 0;
+    for (auto &l : lv) { I.push_back(cursor); I.push_back((int)l.size()); cursor += (int)l.size(); }
+    I[Q_LEVELNODE_I] = (int)I.size();
+    for (auto &l : lv) for (int k : l) I.push_back(k);
+    while (I.size() % 4) I.push_back(0);
+    I[Q_TABB_I] = (int)I.size();
+    for (int s = 0; s < n_steps; ++s)
+        for (int h = 0; h < (sp->steps[s].cntB > 0 ? 2 : 1); ++h)   // compact: an empty half B has no table slot
+            for (int l = 0; l < 32; ++l) {
+                const int r = sp->steps[s].s0 + 32 * h + l;
+                const int cnt = h == 0 ? sp->steps[s].cntA : sp->steps[s].cntB;
+                if (l >= cnt) { for (int j = 0; j < 4; ++j) I.push_back(0); continue; }
+                if (pairs) {
+                    float thr = (float)p->pair_thr[r];
+                    int32_t bits;
+                    memcpy(&bits, &thr, 4);
+                    I.push_back(p->pair_idx[2 * r] | (p->pair_idx[2 * r + 1] << 16));
+                    I.push_back((int32_t)(uint32_t)plus[r]); I.push_back((int32_t)(uint32_t)minus[r]); I.push_back(bits);
+                } else {
+                    I.push_back(p->feat_node[r]); I.push_back((int32_t)(uint32_t)(plus[r] & 0xffffffffu));
+                    I.push_back((int32_t)(uint32_t)(plus[r] >> 32)); I.push_back(0);
+                }
+            }
+    I[Q_CENNODE_I] = (int)I.size();
+    if (pairs) for (int f = 0; f < nf; ++f) I.push_back(p->feat_node[f]);
+    while (I.size() % 4) I.push_back(0);
+    I[Q_I_TOTAL] = (int)I.size();
+    Fv.clear();
+    I[Q_NODE_F] = 0;
+    for (int k = 0; k < n_nodes; ++k) {
+        double R[9];
+        quat_to_matrix(p->nodes[k].pre.q, R);
+        for (int r = 0; r < 3; ++r) { Fv.push_back(R[3 * r]); Fv.push_back(R[3 * r + 1]); Fv.push_back(R[3 * r + 2]); Fv.push_back(p->nodes[k].pre.t[r]); }
+    }
+    I[Q_TABA_F] = (int)Fv.size();
+    if (!pairs)
+        for (int s = 0; s < n_steps; ++s)
+            for (int h = 0; h < (sp->steps[s].cntB > 0 ? 2 : 1); ++h)
+                for (int l = 0; l < 32; ++l) {
+                    const int r = sp->steps[s].s0 + 32 * h + l;
+                    const int cnt = h == 0 ? sp->steps[s].cntA : sp->steps[s].cntB;
+                    if (l < cnt) { for (int j = 0; j < 3; ++j) Fv.push_back(p->feat_off[r].t[j]); Fv.push_back(p->radii[r]); }
+                    else for (int j = 0; j < 4; ++j) Fv.push_back(0.0);
+                }
+    I[Q_CENA_F] = (int)Fv.size();
+    if (pairs) for (int f = 0; f < nf; ++f) { for (int j = 0; j < 3; ++j) Fv.push_back(p->feat_off[f].t[j]); Fv.push_back(p->radii[f]); }
+    I[Q_F_TOTAL] = (int)Fv.size();
+    sp->n_nodes = n_nodes; sp->n_levels = n_levels; sp->rows = rows; sp->n_cen = pairs ? nf : 0;
+    sp->frame_stride = odd_quads(n_nodes * 12);
+    sp->supported = true;
+    return 0;
+}
+
+static void free_s2(skb_s2_program &sp) {
+    if (sp.dI) cudaFree(sp.dI);
+    if (sp.dF32) cudaFree(sp.dF32);
+    sp = skb_s2_program();
+}
+
+const skb_s2_program *get_s2_program(skb_plan *p, int kind) {
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (kind == KIND_PAIRWISE && !p->pairs_set) return nullptr;
+    skb_s2_program &sp = kind == KIND_PAIRWISE ? p->s2_pairs : p->s2_collfree;
+    if (!sp.built && build_s2_program(p, kind, &sp) != 0) return nullptr;
+    if (!sp.supported) return nullptr;
+    if (!sp.dI) {
+        if (cudaMalloc(&sp.dI, sp.I.size() * sizeof(int32_t)) != cudaSuccess ||
+            cudaMemcpy(sp.dI, sp.I.data(), sp.I.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("step program upload failed (no CUDA device?)");
+            sp.dI = nullptr;
+            return nullptr;
+        }
+        if (upload_reals<float>(sp.F, &sp.dF32) != 0) return nullptr;
+    }
+    return &sp;
+}
+
 template <typename T>
 static int upload_prims(skb_sdf *s, void **dst) {
     std::vector<DevPrim<T>> v(s->prims.size() ? s->prims.size() : 1);
@@ -901,8 +1051,11 @@ static void drop_schedules(skb_plan *p) {
     for (auto &kv : p->schedules) free_schedule(kv.second);
     p->schedules.clear();
     free_sphere(p->sphere);
+    free_s2(p->s2_collfree);
+    free_s2(p->s2_pairs);
 }
 static void drop_pairs(skb_plan *p) {
+    free_s2(p->s2_pairs);
     if (p->pairs.dI) cudaFree(p->pairs.dI);
     if (p->pairs.dF32) cudaFree(p->pairs.dF32);
     if (p->pairs.dF64) cudaFree(p->pairs.dF64);

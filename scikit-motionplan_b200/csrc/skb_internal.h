@@ -149,6 +149,36 @@ struct skb_sphere_program {
     bool built = false, supported = false;
 };
 
+// step program (skb_sphere2.cu): the two-rows-per-lane kernel for the full-output modes of CollFreeConst and
+// PairWiseSelfCollFreeConst.  A "step" covers up to 64 consecutive output rows (spheres or pairs) of one
+// configuration: lane l owns row s0 + l (half A) and row s0 + 32 + l (half B, only when half A is full).
+//   I: header (enum QHdr) | node records (4 ints) | level records (2) | level node lists |
+//      lane table B: int4 per (step, half, lane)
+//         collfree  {node, amask_lo, amask_hi, 0}
+//         pairwise  {centre_i | centre_j << 16, plus_mask, minus_mask, float bits of (r_i + r_j)^2}
+//      | pairwise only: node per centre
+//   F: node pre-transforms (12) | collfree: lane table A {off xyz, radius} per (step, half, lane)
+//      | pairwise: centre table {off xyz, radius} per sphere
+enum QHdr {
+    Q_N_NODES = 0, Q_N_LEVELS, Q_N_STEPS, Q_D, Q_ROWS, Q_N_CEN,
+    Q_NODE_I, Q_LEVEL_I, Q_LEVELNODE_I, Q_TABB_I, Q_CENNODE_I, Q_I_TOTAL,
+    Q_NODE_F, Q_TABA_F, Q_CENA_F, Q_F_TOTAL,
+    QHDR_WORDS = 16
+};
+enum { S2_MAX_STEPS = 96 };
+struct skb_s2_step { unsigned long long cm; int32_t s0; int16_t cntA, cntB; };   // cm: columns any row of the step touches
+
+struct skb_s2_program {
+    std::vector<int32_t> I;
+    std::vector<double> F;
+    std::vector<skb_s2_step> steps;
+    void *dI = nullptr;
+    void *dF32 = nullptr;
+    int n_nodes = 0, n_levels = 0, rows = 0, n_cen = 0;
+    int frame_stride = 0;            // floats per configuration
+    bool built = false, supported = false;
+};
+
 struct skb_stream_ctx;           // host-pipeline scratch (skb_hostpipe.cpp)
 
 struct skb_plan {
@@ -171,6 +201,7 @@ struct skb_plan {
     std::map<int, skb_schedule> schedules;   // keyed by rows-per-feature
     skb_pair_program pairs;
     skb_sphere_program sphere;
+    skb_s2_program s2_collfree, s2_pairs;
     bool pairs_set = false;
     std::vector<int32_t> pair_idx;
     std::vector<double> pair_thr;
@@ -184,6 +215,7 @@ int set_error(const std::string &msg);           // returns -1
 const skb_schedule *get_schedule(skb_plan *p, int rows);   // builds + uploads lazily; nullptr on error
 const skb_pair_program *get_pair_program(skb_plan *p);
 const skb_sphere_program *get_sphere_program(skb_plan *p);   // nullptr when the plan is not eligible (not an error)
+const skb_s2_program *get_s2_program(skb_plan *p, int kind);   // KIND_COLLFREE / KIND_PAIRWISE; nullptr when not eligible
 const void *get_dev_prims(skb_sdf *s, int dtype);
 const void *get_host_prims(const skb_sdf *s, int dtype);   // valid after get_dev_prims succeeded for that dtype
 
@@ -200,7 +232,11 @@ int launch_sphere(const skb_plan *p, const skb_sphere_program *sp, int kind, int
                   const void *dev_prims, const void *host_prims, int n_prims, double margin, int mode, void *out_vals,
                   void *out_jac, uint8_t *out_valid, void *stream);
 int launch_expand_cells(const void *grid, int is_f64, const int32_t dims[3], void *cells);
-enum { KIND_MAP = 0, KIND_COLLFREE = 1 };
+// skb_sphere2.cu (fp32, full-output modes)
+int launch_s2(const skb_plan *p, const skb_s2_program *sp, int kind, const void *q, int64_t N, const void *dev_prims,
+              const void *host_prims, int n_prims, double margin, int mode, void *out_vals, void *out_jac, uint8_t *out_valid,
+              void *stream);
+enum { KIND_MAP = 0, KIND_COLLFREE = 1, KIND_PAIRWISE = 2 };
 
 extern int64_t g_launch_count;
 

@@ -58,7 +58,7 @@ struct SphereParams {
     int off_F, off_prims, off_warp, warp_elems;   // bytes, bytes, bytes, elements of T per warp
     int woff_q, woff_sc, woff_frames, woff_tw, woff_stage; // element offsets inside a warp slab
     int fstride, tstride;                         // elements of T per configuration: frames, twists
-    int G, logG;                                  // configurations per tile (power of two)
+    int G, logG, slots3;                          // configurations per tile (power of two <= 8), nodes per FK pass
     int D, S, n_rounds, n_levels;                 // copies of the program header (uniform operands)
     int copy_vec;                                 // 1: every round block is 16-byte aligned in out_jac
     int stage_elems;                              // elements of T per staging buffer (two per warp)
@@ -68,8 +68,6 @@ struct SphereParams {
     unsigned long long round_cm[MAX_ROUNDS];      // per round: columns any of its spheres depends on
     DevPrim<T> prim0;                             // copy of primitive 0 (single-primitive fast path)
 };
-
-template <typename T> struct alignas(16) Vec4 { T x, y, z, w; };
 
 template <typename T>
 __device__ __forceinline__ void st_stream(T *p, T v) { __stcs(p, v); }
@@ -191,66 +189,9 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
         }
         __syncwarp();
 
-        // ------------------------------------------------------------ phase 1: frames + twists
-        {
-            const int cfg = lane & (G - 1), slot = lane >> logG, slots = 32 >> logG;
-            const T *myq = wq + min(cfg, g_live - 1) * D;
-            const T *mysc = wsc + 2 * min(cfg, g_live - 1) * D;
-            V4 *fr = reinterpret_cast<V4 *>(wframes + cfg * fstride);
-            T *tw = wtw + cfg * tstride;
-            for (int lv = 0; lv < n_levels; ++lv) {
-                const int lbeg = levelI[2 * lv], lcnt = levelI[2 * lv + 1];
-                for (int k0 = 0; k0 < lcnt; k0 += slots) {
-                    const int k = k0 + slot;
-                    if (k < lcnt) {
-                        const int node = levelNodes[lbeg + k];
-                        const int type = nodeI[4 * node], col = nodeI[4 * node + 1], par = nodeI[4 * node + 2];
-                        const V4 c0 = nodeF[3 * node], c1 = nodeF[3 * node + 1], c2 = nodeF[3 * node + 2];
-                        V4 y0, y1, y2;      // Y = parent * pre, rows [R_r0 R_r1 R_r2 t_r]
-                        if (par < 0) { y0 = c0; y1 = c1; y2 = c2; }
-                        else {
-                            const V4 p0 = fr[3 * par], p1 = fr[3 * par + 1], p2 = fr[3 * par + 2];
-#define SKB_ROW(P, Y)                                                   \
-    Y.x = P.x * c0.x + P.y * c1.x + P.z * c2.x;                         \
-    Y.y = P.x * c0.y + P.y * c1.y + P.z * c2.y;                         \
-    Y.z = P.x * c0.z + P.y * c1.z + P.z * c2.z;                         \
-    Y.w = P.w + P.x * c0.w + P.y * c1.w + P.z * c2.w;
-                            SKB_ROW(p0, y0) SKB_ROW(p1, y1) SKB_ROW(p2, y2)
-#undef SKB_ROW
-                        }
-                        T wx = T(0), wy = T(0), wz = T(0), vx = T(0), vy = T(0), vz = T(0);
-                        if (type == NODE_REVOLUTE) {
-                            const T s = mysc[2 * col], c = mysc[2 * col + 1];
-                            wx = y0.z; wy = y1.z; wz = y2.z;                 // joint axis = local +z
-                            vx = y1.w * wz - y2.w * wy;                       // v = o x omega
-                            vy = y2.w * wx - y0.w * wz;
-                            vz = y0.w * wy - y1.w * wx;
-                            T a, b;
-                            a = y0.x; b = y0.y; y0.x = c * a + s * b; y0.y = c * b - s * a;
-                            a = y1.x; b = y1.y; y1.x = c * a + s * b; y1.y = c * b - s * a;
-                            a = y2.x; b = y2.y; y2.x = c * a + s * b; y2.y = c * b - s * a;
-                        } else if (type == NODE_PRISMATIC) {
-                            const T th = myq[col];
-                            vx = y0.z; vy = y1.z; vz = y2.z;
-                            y0.w += th * vx; y1.w += th * vy; y2.w += th * vz;
-                        }
-                        fr[3 * node] = y0; fr[3 * node + 1] = y1; fr[3 * node + 2] = y2;
-                        if (WITH_JAC && col >= 0) {
-                            if (PAIR) {
-                                T *t2 = tw + (col >> 1) * 12 + (col & 1);
-                                t2[0] = wx; t2[2] = wy; t2[4] = wz; t2[6] = vx; t2[8] = vy; t2[10] = vz;
-                            } else {
-                                V4 *t2 = reinterpret_cast<V4 *>(tw + col * 8);
-                                V4 a; a.x = wx; a.y = wy; a.z = wz; a.w = T(0);
-                                V4 b; b.x = vx; b.y = vy; b.z = vz; b.w = T(0);
-                                t2[0] = a; t2[1] = b;
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-        }
+        // ------------------------------------------------------------ phase 1: frames + twists (three lanes per node)
+        fk_phase<T, WITH_JAC, PAIR>(lane, G, logG, prm.slots3, g_live, D, n_levels, nodeI, levelI, levelNodes, nodeF, wq, wsc,
+                                    wframes, fstride, wtw, tstride);
 
         // ------------------------------------------------------------ phase 2: one lane per sphere
         // per-configuration reduction state (validity / closest modes only)
@@ -549,7 +490,7 @@ static int launch_sphere_inst(const skb_plan *p, const skb_sphere_program *sp, c
     const size_t smem_limit = 227 * 1024;
     int warps = p->tune_warps > 0 ? std::min(p->tune_warps, SKB_LB_THREADS / 32) : SKB_LB_THREADS / 32;
     int ctas_target = p->tune_ctas > 0 ? p->tune_ctas : SKB_LB_BLOCKS;
-    int G = p->tune_chunk > 0 ? std::min(p->tune_chunk, 32) : 32;
+    int G = p->tune_chunk > 0 ? std::min(p->tune_chunk, 8) : 8;
     auto layout = [&](int g) {
         int e = 0;
         prm.woff_q = e;      e += align_up(g * D, al);
@@ -572,6 +513,7 @@ static int launch_sphere_inst(const skb_plan *p, const skb_sphere_program *sp, c
     prm.G = G;
     prm.logG = 0;
     while ((1 << prm.logG) < G) ++prm.logG;
+    prm.slots3 = 32 / (3 * G);
     prm.n_tiles = (N + G - 1) / G;
     auto kern = sphere_kernel<T, KIND, WITH_JAC, CLOSEST, SDFK, VW, MaskT>;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,0 +1,501 @@
+// skb_sphere2.cu -- the full-output kernel (fp32): every row of values and Jacobians, for
+//
+//     KIND_COLLFREE   CollFreeConst._evaluate_all               (skmp/constraint.py:335-374)
+//     KIND_PAIRWISE   PairWiseSelfCollFreeConst._evaluate       (skmp/constraint.py:749-778, all-pairs mode)
+//
+// One warp owns a tile of G configurations.
+//   phase 1   forward kinematics, level by level, three lanes per (configuration, node)  -> fk_phase (skb_device.cuh)
+//   phase 1b  (pairwise) sphere centres of the tile, one lane per sphere, into the warp's shared slab
+//   phase 2   "steps" of up to 64 consecutive output rows of ONE configuration: lane l owns row s0 + l and row
+//             s0 + 32 + l.  A row is reduced to a value, a wrench (m, g) and a column mask:
+//                 collfree   p = frame * offset,  (d, g) = SDF(p),  value = d - r - margin,  m = p x g
+//                 pairwise   delta = x_i - x_j,  value = |delta|^2 - (r_i + r_j)^2,  g = 2 delta,  m = x_i x g
+//                            (x_i x delta == x_j x delta, so one wrench serves both spheres; columns that move only
+//                             sphere j enter with a minus sign)
+//             and the Jacobian row is the twist/wrench pairing  J[d] = omega_d . m + v_d . g  over the masked columns,
+//             two columns per packed fma.rn.f32x2, the twist pair loaded once (warp-broadcast LDS.128 x3) for BOTH rows
+//             of the lane.  The dense [rows][D] block is assembled in shared memory -- it IS the output layout -- and
+//             leaves with one TMA bulk store per step (cp.async.bulk shared -> global, L2 evict-first).
+// Sphere centres, frames, twists and SDF gradients never touch HBM.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <type_traits>
+
+#include "skb_device.cuh"
+#include "skb_internal.h"
+
+namespace skb {
+
+#ifndef SKB_S2_THREADS
+#define SKB_S2_THREADS 256      // max threads per CTA
+#define SKB_S2_BLOCKS 3         // min CTAs per SM (register cap = 65536 / product)
+#endif
+
+struct S2Params {
+    const int32_t *I;
+    const float *F;
+    const float *q;
+    long long N;
+    long long n_tiles;
+    const DevPrim<float> *prims;
+    int n_prims;
+    float margin;
+    float *out_vals;
+    float *out_jac;
+    uint8_t *out_valid;
+    int i_total, f_total;
+    int off_F, off_prims, off_warp, warp_elems;                       // bytes, bytes, bytes, floats per warp
+    int woff_q, woff_sc, woff_frames, woff_tw, woff_cen, woff_stage;  // float offsets inside a warp slab
+    int fstride, tstride, cstride;                                    // floats per configuration: frames, twists, centres
+    int G, logG, slots3;
+    int D, NP, R, n_steps, n_levels, n_cen;                           // R = output rows per configuration
+    int copy_vec;                                                     // 1: every step block is 16-byte aligned in out_jac
+    // warp-uniform data of the hot loop lives in the kernel parameters (constant bank -> uniform datapath)
+    skb_s2_step steps[S2_MAX_STEPS];
+    DevPrim<float> prim0;
+};
+
+__device__ __forceinline__ void st_stream(float *p, float v) { __stcs(p, v); }
+
+// packed fp32x2 FMA (sm_100: SASS FFMA2 / FMUL2): both halves in one issue slot
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
+enum { SDF_UNION = 0, SDF_SINGLE = 1, SDF_GRID_FAST = 2 };
+
+// fp32 corner-packed grid, identity rotation: same arithmetic (and rounding) as sdf_prim_world -> sdf_grid_local
+__device__ __forceinline__ float s2_grid_fast(const DevPrim<float> &pr, float px, float py, float pz, float &gx, float &gy, float &gz) {
+    const float ux = ((px - pr.pos[0]) - pr.par[0]) * pr.par[3], uy = ((py - pr.pos[1]) - pr.par[1]) * pr.par[4],
+                uz = ((pz - pr.pos[2]) - pr.par[2]) * pr.par[5];
+    const float tx = float(pr.dims[0] - 1), ty = float(pr.dims[1] - 1), tz = float(pr.dims[2] - 1);
+    gx = gy = gz = 0.f;
+    if (!(ux >= 0.f && ux <= tx && uy >= 0.f && uy <= ty && uz >= 0.f && uz <= tz)) return pr.par[6];
+    const int ix = min((int)floorf(ux), pr.dims[0] - 2), iy = min((int)floorf(uy), pr.dims[1] - 2), iz = min((int)floorf(uz), pr.dims[2] - 2);
+    const float fx = ux - float(ix), fy = uy - float(iy), fz = uz - float(iz);
+    const unsigned cell = ((unsigned)ix * (unsigned)(pr.dims[1] - 1) + (unsigned)iy) * (unsigned)(pr.dims[2] - 1) + (unsigned)iz;
+    float c[8];
+    ldg_cell(reinterpret_cast<const float *>(pr.cells) + (size_t)cell * 8, c);
+    const float d00 = c[4] - c[0], d01 = c[5] - c[1], d10 = c[6] - c[2], d11 = c[7] - c[3];
+    const float c00 = c[0] + fx * d00, c01 = c[1] + fx * d01, c10 = c[2] + fx * d10, c11 = c[3] + fx * d11;
+    const float e0 = c10 - c00, e1 = c11 - c01;
+    const float c0 = c00 + fy * e0, c1 = c01 + fy * e1;
+    const float h = c1 - c0;
+    const float dx0 = d00 + fy * (d10 - d00), dx1 = d01 + fy * (d11 - d01);
+    gx = (dx0 + fz * (dx1 - dx0)) * pr.par[3];
+    gy = (e0 + fz * (e1 - e0)) * pr.par[4];
+    gz = h * pr.par[5];
+    return c0 + fz * h;
+}
+
+template <typename MaskT> struct RowState {   // what phase 2 keeps of one output row
+    float gx, gy, gz, mx, my, mz;
+    MaskT pm, mm;
+};
+
+// RED = false: every row is written (values, and with JAC the dense Jacobian block)
+// RED = true : per-configuration reduction -- closest row (np.argmin: first index wins ties) and / or validity byte
+template <int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC>
+__global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const __grid_constant__ S2Params prm) {
+    using V4 = Vec4<float>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    int32_t *sI = reinterpret_cast<int32_t *>(smem);
+    float *sF = reinterpret_cast<float *>(smem + prm.off_F);
+    DevPrim<float> *sP = reinterpret_cast<DevPrim<float> *>(smem + prm.off_prims);
+
+    // the warp index goes through a shuffle so the compiler treats it (and everything derived from it) as warp-uniform
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), n_warps = blockDim.x >> 5;
+    for (int i = tid; i < prm.i_total; i += blockDim.x) sI[i] = prm.I[i];
+    for (int i = tid; i < prm.f_total; i += blockDim.x) sF[i] = prm.F[i];
+    if (KIND == KIND_COLLFREE && SDFK == SDF_UNION) {
+        const int words = prm.n_prims * (int)(sizeof(DevPrim<float>) / 4);
+        const int32_t *src = reinterpret_cast<const int32_t *>(prm.prims);
+        int32_t *dst = reinterpret_cast<int32_t *>(sP);
+        for (int i = tid; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    const int n_levels = prm.n_levels, n_steps = prm.n_steps, D = prm.D, NP = prm.NP, R = prm.R;
+    const int fstride = prm.fstride, tstride = prm.tstride, cstride = prm.cstride;
+    const int32_t *nodeI = sI + sI[Q_NODE_I];
+    const int32_t *levelI = sI + sI[Q_LEVEL_I];
+    const int32_t *levelNodes = sI + sI[Q_LEVELNODE_I];
+    const int4 *tabB = reinterpret_cast<const int4 *>(sI + sI[Q_TABB_I]);
+    const int32_t *cenNode = sI + sI[Q_CENNODE_I];
+    const V4 *nodeF = reinterpret_cast<const V4 *>(sF + sI[Q_NODE_F]);
+    const V4 *tabA = reinterpret_cast<const V4 *>(sF + sI[Q_TABA_F]);
+    const V4 *cenA = reinterpret_cast<const V4 *>(sF + sI[Q_CENA_F]);
+    const int G = prm.G, logG = prm.logG;
+
+    float *wbase = reinterpret_cast<float *>(smem + prm.off_warp) + (size_t)warp * prm.warp_elems;
+    float *wq = wbase + prm.woff_q;
+    float *wsc = wbase + prm.woff_sc;
+    float *wframes = wbase + prm.woff_frames;
+    float *wtw = wbase + prm.woff_tw;
+    float *wcen = wbase + prm.woff_cen;
+    float *wstage = wbase + prm.woff_stage;
+    const uint64_t l2_policy = l2_evict_first_policy();
+
+    for (long long tile = (long long)blockIdx.x * n_warps + warp; tile < prm.n_tiles; tile += (long long)gridDim.x * n_warps) {
+        const long long n0 = tile * G;
+        const int g_live = (int)min((long long)G, prm.N - n0);
+        __syncwarp();
+        // q tile + one fully populated sin/cos pass over all G*D joint values
+        for (int i = lane; i < g_live * D; i += 32) {
+            const float th = prm.q[n0 * D + i];
+            float sn, cs;
+            sincosf(th, &sn, &cs);
+            wq[i] = th;
+            wsc[2 * i] = sn; wsc[2 * i + 1] = cs;
+        }
+        __syncwarp();
+
+        // ------------------------------------------------------------ phase 1: frames + twists
+        fk_phase<float, JAC, true>(lane, G, logG, prm.slots3, g_live, D, n_levels, nodeI, levelI, levelNodes, nodeF, wq, wsc,
+                                    wframes, fstride, wtw, tstride);
+
+        // ------------------------------------------------------------ phase 1b: sphere centres (pairwise)
+        if (KIND == KIND_PAIRWISE) {
+            for (int s = lane; s < prm.n_cen; s += 32) {
+                const int node = cenNode[s];
+                const V4 A = cenA[s];
+                for (int c = 0; c < g_live; ++c) {
+                    const V4 *fr = reinterpret_cast<const V4 *>(wframes + c * fstride);
+                    const V4 f0 = fr[3 * node], f1 = fr[3 * node + 1], f2 = fr[3 * node + 2];
+                    V4 x;
+                    x.x = f0.w + f0.x * A.x + f0.y * A.y + f0.z * A.z;
+                    x.y = f1.w + f1.x * A.x + f1.y * A.y + f1.z * A.z;
+                    x.z = f2.w + f2.x * A.x + f2.y * A.y + f2.z * A.z;
+                    x.w = 0.f;
+                    reinterpret_cast<V4 *>(wcen + c * cstride)[s] = x;
+                }
+            }
+            __syncwarp();
+        }
+
+        // ------------------------------------------------------------ phase 2: steps of up to 64 rows
+        // value + wrench + masks of one row of configuration c
+        auto front = [&](const int c, const V4 &A, const int4 &B, RowState<MaskT> &rs) -> float {
+            float val;
+            if (KIND == KIND_COLLFREE) {
+                const V4 *fr = reinterpret_cast<const V4 *>(wframes + c * fstride);
+                const V4 f0 = fr[3 * B.x], f1 = fr[3 * B.x + 1], f2 = fr[3 * B.x + 2];
+                const float px = f0.w + f0.x * A.x + f0.y * A.y + f0.z * A.z;
+                const float py = f1.w + f1.x * A.x + f1.y * A.y + f1.z * A.z;
+                const float pz = f2.w + f2.x * A.x + f2.y * A.y + f2.z * A.z;
+                const float d = SDFK == SDF_GRID_FAST ? s2_grid_fast(prm.prim0, px, py, pz, rs.gx, rs.gy, rs.gz)
+                              : SDFK == SDF_SINGLE    ? sdf_prim_world<float>(prm.prim0, px, py, pz, rs.gx, rs.gy, rs.gz)
+                                                      : sdf_union<float>(sP, prm.n_prims, px, py, pz, rs.gx, rs.gy, rs.gz);
+                val = d - A.w - prm.margin;
+                if (JAC) wrench_moment<float>(px, py, pz, rs.gx, rs.gy, rs.gz, rs.mx, rs.my, rs.mz);
+                rs.pm = sizeof(MaskT) == 8 ? (MaskT)(((unsigned long long)(unsigned)B.z << 32) | (unsigned)B.y) : (MaskT)(unsigned)B.y;
+                rs.mm = 0;
+            } else {
+                const V4 *cen = reinterpret_cast<const V4 *>(wcen + c * cstride);
+                const V4 xi = cen[B.x & 0xffff], xj = cen[(unsigned)B.x >> 16];
+                const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                val = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))) - __int_as_float(B.w);
+                rs.gx = 2.f * dx; rs.gy = 2.f * dy; rs.gz = 2.f * dz;
+                if (JAC) wrench_moment<float>(xi.x, xi.y, xi.z, rs.gx, rs.gy, rs.gz, rs.mx, rs.my, rs.mz);
+                rs.pm = (MaskT)(unsigned)B.y;
+                rs.mm = (MaskT)(unsigned)B.z;
+            }
+            return val;
+        };
+
+        if (!RED) {
+            int slot = 0;                                   // running index into the per-(half, lane) tables
+            for (int st = 0; st < n_steps; ++st) {
+                const unsigned long long cm = prm.steps[st].cm;
+                const int s0 = prm.steps[st].s0, cntA = prm.steps[st].cntA, cntB = prm.steps[st].cntB;
+                const int4 B0 = tabB[slot * 32 + lane];
+                const int4 B1 = tabB[(slot + (cntB > 0 ? 1 : 0)) * 32 + lane];
+                V4 A0, A1;
+                if (KIND == KIND_COLLFREE) { A0 = tabA[slot * 32 + lane]; A1 = tabA[(slot + (cntB > 0 ? 1 : 0)) * 32 + lane]; }
+                slot += cntB > 0 ? 2 : 1;
+
+                // twist pair x wrench for the columns (col, col + 1), masked / signed
+                auto contract = [&](const float4 &t0, const float4 &t1, const float4 &t2, const RowState<MaskT> &rs, const int col) -> float2 {
+                    float2 a = mul2(make_float2(t0.x, t0.y), make_float2(rs.mx, rs.mx));
+                    a = fma2(make_float2(t0.z, t0.w), make_float2(rs.my, rs.my), a);
+                    a = fma2(make_float2(t1.x, t1.y), make_float2(rs.mz, rs.mz), a);
+                    a = fma2(make_float2(t1.z, t1.w), make_float2(rs.gx, rs.gx), a);
+                    a = fma2(make_float2(t2.x, t2.y), make_float2(rs.gy, rs.gy), a);
+                    a = fma2(make_float2(t2.z, t2.w), make_float2(rs.gz, rs.gz), a);
+                    const MaskT sp = rs.pm >> col;
+                    if (KIND == KIND_PAIRWISE) {
+                        const MaskT sm = rs.mm >> col;
+                        a.x = (sp & 1) ? a.x : ((sm & 1) ? -a.x : 0.f);
+                        a.y = (sp & 2) ? a.y : ((sm & 2) ? -a.y : 0.f);
+                    } else {
+                        a.x = (sp & 1) ? a.x : 0.f;
+                        a.y = (sp & 2) ? a.y : 0.f;
+                    }
+                    return a;
+                };
+
+                auto body = [&](auto has_b, const int c) {
+                    constexpr bool HAS_B = decltype(has_b)::value;
+                    const long long n = n0 + c;
+                    const float *tw = wtw + c * tstride;
+                    RowState<MaskT> ra, rb;
+                    const float va = front(c, A0, B0, ra);
+                    float vb = 0.f;
+                    if (HAS_B) vb = front(c, A1, B1, rb);
+                    if (prm.out_vals != nullptr) {
+                        float *gv = prm.out_vals + n * R + s0 + lane;
+                        if (lane < cntA) st_stream(gv, va);
+                        if (HAS_B && lane < cntB) st_stream(gv + 32, vb);
+                    }
+                    if (!JAC) return;
+                    float *rowA = wstage + lane * D;
+                    float *rowB = rowA + 32 * D;
+                    // the bulk store of the previous step must have finished reading the staging block
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                    for (int jp = 0; jp < NP; ++jp) {
+                        const int col = 2 * jp;
+                        float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+                        if ((cm >> col) & 3ull) {                     // uniform: some row of this step needs col or col + 1
+                            const float4 *t4 = reinterpret_cast<const float4 *>(tw + jp * 12);
+                            const float4 t0 = t4[0], t1 = t4[1], t2 = t4[2];
+                            a = contract(t0, t1, t2, ra, col);
+                            if (HAS_B) b = contract(t0, t1, t2, rb, col);
+                        }
+                        if (VW == 2) {
+                            *reinterpret_cast<float2 *>(rowA + col) = a;
+                            if (HAS_B) *reinterpret_cast<float2 *>(rowB + col) = b;
+                        } else {
+                            rowA[col] = a.x;
+                            if (HAS_B) rowB[col] = b.x;
+                            if (col + 1 < D) {
+                                rowA[col + 1] = a.y;
+                                if (HAS_B) rowB[col + 1] = b.y;
+                            }
+                        }
+                    }
+                    // ship: the dense [rows][D] block is contiguous in HBM
+                    const int len = (cntA + (HAS_B ? cntB : 0)) * D;
+                    float *g = prm.out_jac + (n * R + s0) * (long long)D;
+                    if (prm.copy_vec) {
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            bulk_store_hint(g, wstage, (uint32_t)(len * sizeof(float)), l2_policy);
+                            bulk_commit();
+                        }
+                    } else {
+                        __syncwarp();
+#pragma unroll 4
+                        for (int i = lane; i < len; i += 32) st_stream(g + i, wstage[i]);
+                        __syncwarp();
+                    }
+                };
+
+                if (cntB > 0) for (int c = 0; c < g_live; ++c) body(std::true_type{}, c);
+                else          for (int c = 0; c < g_live; ++c) body(std::false_type{}, c);
+            }
+        } else {
+            // ---- per-configuration reduction: closest row (value, Jacobian row) and / or validity byte
+            for (int c = 0; c < g_live; ++c) {
+                const long long n = n0 + c;
+                float best = __int_as_float(0x7f800000);
+                int bidx = 0x7fffffff;
+                RowState<MaskT> brs;
+                brs.gx = brs.gy = brs.gz = brs.mx = brs.my = brs.mz = 0.f; brs.pm = 0; brs.mm = 0;
+                int slot = 0;
+                for (int st = 0; st < n_steps; ++st) {
+                    const int s0 = prm.steps[st].s0, cntA = prm.steps[st].cntA, cntB = prm.steps[st].cntB;
+                    RowState<MaskT> rs;
+                    V4 A;
+                    if (KIND == KIND_COLLFREE) A = tabA[slot * 32 + lane];
+                    const float va = front(c, A, tabB[slot * 32 + lane], rs);
+                    if (lane < cntA && va < best) { best = va; bidx = s0 + lane; brs = rs; }
+                    ++slot;
+                    if (cntB > 0) {
+                        if (KIND == KIND_COLLFREE) A = tabA[slot * 32 + lane];
+                        const float vb = front(c, A, tabB[slot * 32 + lane], rs);
+                        if (lane < cntB && vb < best) { best = vb; bidx = s0 + 32 + lane; brs = rs; }
+                        ++slot;
+                    }
+                }
+                float m = best; int mi = bidx;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float x = __shfl_xor_sync(0xffffffffu, m, o);
+                    const int xi = __shfl_xor_sync(0xffffffffu, mi, o);
+                    if (x < m || (x == m && xi < mi)) { m = x; mi = xi; }
+                }
+                if (lane == 0) {
+                    if (prm.out_vals != nullptr) prm.out_vals[n] = m;
+                    if (prm.out_valid != nullptr) prm.out_valid[n] = m > 0.f ? 1 : 0;
+                }
+                if (JAC) {
+                    const int src = max(0, __ffs(__ballot_sync(0xffffffffu, bidx == mi && best == m)) - 1);
+                    const float gx = __shfl_sync(0xffffffffu, brs.gx, src), gy = __shfl_sync(0xffffffffu, brs.gy, src), gz = __shfl_sync(0xffffffffu, brs.gz, src);
+                    const float mx = __shfl_sync(0xffffffffu, brs.mx, src), my = __shfl_sync(0xffffffffu, brs.my, src), mz = __shfl_sync(0xffffffffu, brs.mz, src);
+                    const unsigned long long pm = __shfl_sync(0xffffffffu, (unsigned long long)brs.pm, src);
+                    const unsigned long long mm = __shfl_sync(0xffffffffu, (unsigned long long)brs.mm, src);
+                    const float *tw = wtw + c * tstride;
+                    for (int col = lane; col < D; col += 32) {     // one lane per column of the single row
+                        const float *t2 = tw + (col >> 1) * 12 + (col & 1);
+                        float jv = dot6<float>(t2[0], t2[2], t2[4], t2[6], t2[8], t2[10], mx, my, mz, gx, gy, gz);
+                        jv = ((pm >> col) & 1ull) ? jv : (((mm >> col) & 1ull) ? -jv : 0.f);
+                        prm.out_jac[n * D + col] = jv;
+                    }
+                }
+            }
+        }
+    }       // tiles
+    if (JAC && !RED) bulk_wait_read<0>();   // shared memory must outlive the last bulk reads
+}
+
+// ------------------------------------------------------------------ launcher
+#define CUDA_OK(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+    } while (0)
+
+static int align_up(int x, int a) { return (x + a - 1) / a * a; }
+static int odd_quads(int words) { int q = (words + 3) / 4; if (q % 2 == 0) q += 1; return q * 4; }
+
+static int sm_count_cached() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+template <int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC>
+static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const void *q, int64_t N, const void *dev_prims,
+                          const void *host_prims, int n_prims, double margin, void *out_vals, void *out_jac, uint8_t *out_valid,
+                          cudaStream_t stream) {
+    S2Params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.I = reinterpret_cast<const int32_t *>(sp->dI);
+    prm.F = reinterpret_cast<const float *>(sp->dF32);
+    prm.q = reinterpret_cast<const float *>(q);
+    prm.N = N;
+    prm.prims = reinterpret_cast<const DevPrim<float> *>(dev_prims);
+    prm.n_prims = n_prims;
+    prm.margin = (float)margin;
+    prm.out_vals = reinterpret_cast<float *>(out_vals);
+    prm.out_jac = reinterpret_cast<float *>(out_jac);
+    prm.out_valid = out_valid;
+    prm.i_total = (int)sp->I.size();
+    prm.f_total = (int)sp->F.size();
+    if (KIND == KIND_COLLFREE && host_prims) prm.prim0 = *reinterpret_cast<const DevPrim<float> *>(host_prims);
+    const int D = p->D, R = sp->rows, NP = (D + 1) / 2;
+    prm.D = D; prm.NP = NP; prm.R = R; prm.n_steps = (int)sp->steps.size(); prm.n_levels = sp->n_levels; prm.n_cen = sp->n_cen;
+    prm.copy_vec = (((long long)R * D) % 4 == 0 && reinterpret_cast<uintptr_t>(out_jac) % 16 == 0) ? 1 : 0;
+    for (int s = 0; s < prm.n_steps; ++s) {
+        prm.steps[s] = sp->steps[s];
+        const int len = (sp->steps[s].cntA + sp->steps[s].cntB) * D;
+        if ((sp->steps[s].s0 * D) % 4 != 0 || len % 4 != 0) prm.copy_vec = 0;
+    }
+    prm.off_F = align_up(prm.i_total * 4, 16);
+    prm.off_prims = align_up(prm.off_F + prm.f_total * 4, 16);
+    prm.off_warp = align_up(prm.off_prims + ((KIND == KIND_COLLFREE && SDFK == SDF_UNION) ? n_prims : 0) * (int)sizeof(DevPrim<float>), 128);
+    prm.fstride = sp->frame_stride;
+    prm.tstride = odd_quads(NP * 12);
+    prm.cstride = KIND == KIND_PAIRWISE ? odd_quads(4 * sp->n_cen) : 0;
+    const size_t smem_limit = 227 * 1024;
+    auto layout = [&](int g, int warps) {
+        int e = 0;
+        prm.woff_q = e;      e += align_up(g * D, 4);
+        prm.woff_sc = e;     e += align_up(2 * g * D, 4);
+        prm.woff_frames = e; e += g * prm.fstride;
+        prm.woff_tw = e;     e += JAC ? g * prm.tstride : 0;
+        prm.woff_cen = e;    e += g * prm.cstride;
+        prm.woff_stage = e;  e += (JAC && !RED) ? align_up(64 * D, 4) : 0;
+        prm.warp_elems = align_up(e, 4);
+        return (size_t)prm.off_warp + (size_t)warps * prm.warp_elems * sizeof(float);
+    };
+    // configurations per tile G (more lanes busy in the tree walk) against warps per CTA, at SKB_S2_BLOCKS CTAs per SM
+    static const int cand[][2] = {{8, 8}, {4, 8}, {4, 7}, {4, 6}, {2, 8}, {2, 6}, {1, 8}, {1, 6}, {1, 4}, {1, 2}, {1, 1}};
+    int G = 0, warps = 0;
+    for (int ctas = p->tune_ctas > 0 ? p->tune_ctas : SKB_S2_BLOCKS; ctas >= 1 && G == 0; --ctas)
+        for (auto &c : cand) {
+            if (p->tune_chunk > 0 && c[0] != p->tune_chunk) continue;
+            if (p->tune_warps > 0 && c[1] != p->tune_warps) continue;
+            if ((layout(c[0], c[1]) + 1024) * ctas <= smem_limit) { G = c[0]; warps = c[1]; break; }
+        }
+    if (G == 0) return set_error("step kernel: shared-memory footprint exceeds 227 KB");
+    const size_t smem = layout(G, warps);
+    prm.G = G;
+    prm.logG = 0;
+    while ((1 << prm.logG) < G) ++prm.logG;
+    prm.slots3 = 32 / (3 * G);
+    prm.n_tiles = (N + G - 1) / G;
+    auto kern = s2_kernel<KIND, SDFK, VW, MaskT, RED, JAC>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) return set_error("step kernel: zero occupancy");
+    if (p->tune_ctas > 0) per_sm = std::min(per_sm, p->tune_ctas);
+    const long long want = (prm.n_tiles + warps - 1) / warps;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count_cached() * per_sm));
+    kern<<<grid, warps * 32, smem, stream>>>(prm);
+    CUDA_OK(cudaGetLastError());
+    ++g_launch_count;
+    return 0;
+}
+
+#define S2_ARGS p, sp, q, N, dev_prims, host_prims, n_prims, margin, out_vals, out_jac, out_valid, stream
+#define S2_SIG const skb_plan *p, const skb_s2_program *sp, const void *q, int64_t N, const void *dev_prims, const void *host_prims, \
+               int n_prims, double margin, void *out_vals, void *out_jac, uint8_t *out_valid, cudaStream_t stream
+
+template <int KIND, int SDFK>
+static int launch_s2_mode(S2_SIG, int mode) {
+    const bool even = p->D % 2 == 0, wide = p->D > 32, jac = out_jac != nullptr;
+    if (mode == SKB_MODE_CLOSEST || out_valid != nullptr) {
+        if (mode != SKB_MODE_CLOSEST && (out_vals != nullptr || jac))
+            return set_error("step kernel: validity bytes come with the closest mode or alone");
+        return jac ? launch_s2_inst<KIND, SDFK, 1, unsigned long long, true, true>(S2_ARGS)
+                   : launch_s2_inst<KIND, SDFK, 1, unsigned long long, true, false>(S2_ARGS);
+    }
+    if (!jac) return launch_s2_inst<KIND, SDFK, 1, unsigned, false, false>(S2_ARGS);
+    if (KIND == KIND_PAIRWISE)
+        return even ? launch_s2_inst<KIND, SDFK, 2, unsigned, false, true>(S2_ARGS) : launch_s2_inst<KIND, SDFK, 1, unsigned, false, true>(S2_ARGS);
+    if (even) return wide ? launch_s2_inst<KIND, SDFK, 2, unsigned long long, false, true>(S2_ARGS)
+                          : launch_s2_inst<KIND, SDFK, 2, unsigned, false, true>(S2_ARGS);
+    return wide ? launch_s2_inst<KIND, SDFK, 1, unsigned long long, false, true>(S2_ARGS)
+                : launch_s2_inst<KIND, SDFK, 1, unsigned, false, true>(S2_ARGS);
+}
+
+int launch_s2(const skb_plan *p, const skb_s2_program *sp, int kind, const void *q, int64_t N, const void *dev_prims,
+              const void *host_prims, int n_prims, double margin, int mode, void *out_vals, void *out_jac, uint8_t *out_valid,
+              void *stream_) {
+    if (N <= 0) return 0;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (kind == KIND_PAIRWISE) return launch_s2_mode<KIND_PAIRWISE, SDF_SINGLE>(S2_ARGS, mode);
+    if (n_prims == 1) {
+        const DevPrim<float> *pr = reinterpret_cast<const DevPrim<float> *>(host_prims);
+        const long long cells = (long long)(pr->dims[0] - 1) * (pr->dims[1] - 1) * (pr->dims[2] - 1);
+        if (pr->type == PRIM_GRID && (pr->flags & PF_GRID_CELLS) && (pr->flags & PF_IDENTITY) && !(pr->flags & PF_GRID_F64) &&
+            cells < (1ll << 31))
+            return launch_s2_mode<KIND_COLLFREE, SDF_GRID_FAST>(S2_ARGS, mode);
+        return launch_s2_mode<KIND_COLLFREE, SDF_SINGLE>(S2_ARGS, mode);
+    }
+    return launch_s2_mode<KIND_COLLFREE, SDF_UNION>(S2_ARGS, mode);
+}
+
+}  // namespace skb
