@@ -76,14 +76,17 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
 
 enum { SDF_UNION = 0, SDF_SINGLE = 1, SDF_GRID_FAST = 2 };
 
-// fp32 corner-packed grid, identity rotation: same arithmetic (and rounding) as sdf_prim_world -> sdf_grid_local
+// fp32 corner-packed grid, identity rotation: same arithmetic (and rounding) as sdf_prim_world -> sdf_grid_local for
+// points inside the sample box.  Branch-free: the cell index is clamped and the gather always issued, the fill value /
+// zero gradient are selected afterwards -- so the two gathers of a lane's two rows are in flight together instead of
+// being serialised by a divergent branch.
 __device__ __forceinline__ float s2_grid_fast(const DevPrim<float> &pr, float px, float py, float pz, float &gx, float &gy, float &gz) {
     const float ux = ((px - pr.pos[0]) - pr.par[0]) * pr.par[3], uy = ((py - pr.pos[1]) - pr.par[1]) * pr.par[4],
                 uz = ((pz - pr.pos[2]) - pr.par[2]) * pr.par[5];
     const float tx = float(pr.dims[0] - 1), ty = float(pr.dims[1] - 1), tz = float(pr.dims[2] - 1);
-    gx = gy = gz = 0.f;
-    if (!(ux >= 0.f && ux <= tx && uy >= 0.f && uy <= ty && uz >= 0.f && uz <= tz)) return pr.par[6];
-    const int ix = min((int)floorf(ux), pr.dims[0] - 2), iy = min((int)floorf(uy), pr.dims[1] - 2), iz = min((int)floorf(uz), pr.dims[2] - 2);
+    const bool inside = ux >= 0.f && ux <= tx && uy >= 0.f && uy <= ty && uz >= 0.f && uz <= tz;
+    const int ix = max(0, min((int)floorf(ux), pr.dims[0] - 2)), iy = max(0, min((int)floorf(uy), pr.dims[1] - 2)),
+              iz = max(0, min((int)floorf(uz), pr.dims[2] - 2));
     const float fx = ux - float(ix), fy = uy - float(iy), fz = uz - float(iz);
     const unsigned cell = ((unsigned)ix * (unsigned)(pr.dims[1] - 1) + (unsigned)iy) * (unsigned)(pr.dims[2] - 1) + (unsigned)iz;
     float c[8];
@@ -94,10 +97,10 @@ __device__ __forceinline__ float s2_grid_fast(const DevPrim<float> &pr, float px
     const float c0 = c00 + fy * e0, c1 = c01 + fy * e1;
     const float h = c1 - c0;
     const float dx0 = d00 + fy * (d10 - d00), dx1 = d01 + fy * (d11 - d01);
-    gx = (dx0 + fz * (dx1 - dx0)) * pr.par[3];
-    gy = (e0 + fz * (e1 - e0)) * pr.par[4];
-    gz = h * pr.par[5];
-    return c0 + fz * h;
+    gx = inside ? (dx0 + fz * (dx1 - dx0)) * pr.par[3] : 0.f;
+    gy = inside ? (e0 + fz * (e1 - e0)) * pr.par[4] : 0.f;
+    gz = inside ? h * pr.par[5] : 0.f;
+    return inside ? c0 + fz * h : pr.par[6];
 }
 
 template <typename MaskT> struct RowState {   // what phase 2 keeps of one output row
@@ -216,6 +219,9 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
         };
 
         if (!RED) {
+            // 64-bit output bases once per tile; (configuration, step) offsets stay 32-bit (G * R * D < 2^31)
+            float *tile_vals = prm.out_vals + n0 * R;
+            float *tile_jac = JAC ? prm.out_jac + n0 * R * (long long)D : nullptr;
             int slot = 0;                                   // running index into the per-(half, lane) tables
             for (int st = 0; st < n_steps; ++st) {
                 const unsigned long long cm = prm.steps[st].cm;
@@ -234,28 +240,27 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                     a = fma2(make_float2(t1.z, t1.w), make_float2(rs.gx, rs.gx), a);
                     a = fma2(make_float2(t2.x, t2.y), make_float2(rs.gy, rs.gy), a);
                     a = fma2(make_float2(t2.z, t2.w), make_float2(rs.gz, rs.gz), a);
-                    const MaskT sp = rs.pm >> col;
+                    // column bits are warp-uniform operands: one LOP3 (predicate) + one FSEL per element
+                    const MaskT b0 = (MaskT)1 << col, b1 = (MaskT)2 << col;
                     if (KIND == KIND_PAIRWISE) {
-                        const MaskT sm = rs.mm >> col;
-                        a.x = (sp & 1) ? a.x : ((sm & 1) ? -a.x : 0.f);
-                        a.y = (sp & 2) ? a.y : ((sm & 2) ? -a.y : 0.f);
+                        a.x = (rs.pm & b0) ? a.x : ((rs.mm & b0) ? -a.x : 0.f);
+                        a.y = (rs.pm & b1) ? a.y : ((rs.mm & b1) ? -a.y : 0.f);
                     } else {
-                        a.x = (sp & 1) ? a.x : 0.f;
-                        a.y = (sp & 2) ? a.y : 0.f;
+                        a.x = (rs.pm & b0) ? a.x : 0.f;
+                        a.y = (rs.pm & b1) ? a.y : 0.f;
                     }
                     return a;
                 };
 
                 auto body = [&](auto has_b, const int c) {
                     constexpr bool HAS_B = decltype(has_b)::value;
-                    const long long n = n0 + c;
                     const float *tw = wtw + c * tstride;
                     RowState<MaskT> ra, rb;
                     const float va = front(c, A0, B0, ra);
                     float vb = 0.f;
                     if (HAS_B) vb = front(c, A1, B1, rb);
                     if (prm.out_vals != nullptr) {
-                        float *gv = prm.out_vals + n * R + s0 + lane;
+                        float *gv = tile_vals + (unsigned)(c * R + s0 + lane);
                         if (lane < cntA) st_stream(gv, va);
                         if (HAS_B && lane < cntB) st_stream(gv + 32, vb);
                     }
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                     }
                     // ship: the dense [rows][D] block is contiguous in HBM
                     const int len = (cntA + (HAS_B ? cntB : 0)) * D;
-                    float *g = prm.out_jac + (n * R + s0) * (long long)D;
+                    float *g = tile_jac + (unsigned)((c * R + s0) * D);
                     if (prm.copy_vec) {
                         fence_async_smem();
                         __syncwarp();
