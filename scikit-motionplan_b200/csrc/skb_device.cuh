@@ -240,12 +240,14 @@ __device__ __forceinline__ void fk_phase(const int lane, const int G, const int 
     V4 *fr = reinterpret_cast<V4 *>(wframes + cfg * fstride);
     T *tw = wtw + cfg * tstride;
     for (int lv = 0; lv < n_levels; ++lv) {
-        const int lbeg = levelI[2 * lv], lcnt = levelI[2 * lv + 1];
+        const int2 lrec = reinterpret_cast<const int2 *>(levelI)[lv];       // {first index into levelNodes, count}
+        const int lbeg = lrec.x, lcnt = lrec.y;
         for (int k0 = 0; k0 < lcnt; k0 += slots3) {
             const int k = k0 + slot;
             const bool on = act && k < lcnt;
             const int node = levelNodes[lbeg + (on ? k : 0)];
-            const int type = nodeI[4 * node], col = nodeI[4 * node + 1], par = nodeI[4 * node + 2];
+            const int4 nrec = reinterpret_cast<const int4 *>(nodeI)[node];  // {type, column, parent, -}
+            const int type = nrec.x, col = nrec.y, par = nrec.z;
             V4 y;
             if (par < 0) y = nodeF[3 * node + row];
             else {
@@ -261,7 +263,9 @@ __device__ __forceinline__ void fk_phase(const int lane, const int G, const int 
             const T w1 = __shfl_sync(0xffffffffu, y.z, src1), w2 = __shfl_sync(0xffffffffu, y.z, src2);
             T wr = T(0), vr = T(0);
             if (type == NODE_REVOLUTE) {
-                const T s = mysc[2 * col], c = mysc[2 * col + 1];
+                struct alignas(2 * sizeof(T)) SC { T s, c; };
+                const SC sc = reinterpret_cast<const SC *>(mysc)[col];
+                const T s = sc.s, c = sc.c;
                 wr = y.z;
                 vr = o1 * w2 - o2 * w1;                       // v = o x omega, component `row`
                 const T a = y.x, b = y.y;

@@ -110,7 +110,9 @@ template <typename MaskT> struct RowState {   // what phase 2 keeps of one outpu
 
 // RED = false: every row is written (values, and with JAC the dense Jacobian block)
 // RED = true : per-configuration reduction -- closest row (np.argmin: first index wins ties) and / or validity byte
-template <int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC>
+// NPMAX: compile-time bound on the number of column pairs (the Jacobian loop is fully unrolled against it, so twist
+// addresses and column bits become immediates)
+template <int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX>
 __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const __grid_constant__ S2Params prm) {
     using V4 = Vec4<float>;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -220,11 +222,16 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
 
         if (!RED) {
             // 64-bit output bases once per tile; (configuration, step) offsets stay 32-bit (G * R * D < 2^31)
+            int row_off = lane * D;                         // opaque: computed once, not rematerialised per column pair
+            asm volatile("" : "+r"(row_off));
             float *tile_vals = prm.out_vals + n0 * R;
             float *tile_jac = JAC ? prm.out_jac + n0 * R * (long long)D : nullptr;
             int slot = 0;                                   // running index into the per-(half, lane) tables
             for (int st = 0; st < n_steps; ++st) {
-                const unsigned long long cm = prm.steps[st].cm;
+                // pair-activity bits of the step (bit jp: some row needs column 2 jp or 2 jp + 1); made opaque so it stays in one
+                // register instead of being re-read from the constant bank inside the unrolled loop
+                unsigned pact = (unsigned)prm.steps[st].cm;
+                asm volatile("" : "+r"(pact));
                 const int s0 = prm.steps[st].s0, cntA = prm.steps[st].cntA, cntB = prm.steps[st].cntB;
                 const int4 B0 = tabB[slot * 32 + lane];
                 const int4 B1 = tabB[(slot + (cntB > 0 ? 1 : 0)) * 32 + lane];
@@ -254,7 +261,9 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
 
                 auto body = [&](auto has_b, const int c) {
                     constexpr bool HAS_B = decltype(has_b)::value;
-                    const float *tw = wtw + c * tstride;
+                    int tw_off = c * tstride;                      // opaque: one address register for the whole unrolled loop
+                    asm volatile("" : "+r"(tw_off));
+                    const float *tw = wtw + tw_off;
                     RowState<MaskT> ra, rb;
                     const float va = front(c, A0, B0, ra);
                     float vb = 0.f;
@@ -265,29 +274,32 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                         if (HAS_B && lane < cntB) st_stream(gv + 32, vb);
                     }
                     if (!JAC) return;
-                    float *rowA = wstage + lane * D;
+                    float *rowA = wstage + row_off;
                     float *rowB = rowA + 32 * D;
                     // the bulk store of the previous step must have finished reading the staging block
                     if (lane == 0) bulk_wait_read<0>();
                     __syncwarp();
-                    for (int jp = 0; jp < NP; ++jp) {
-                        const int col = 2 * jp;
-                        float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
-                        if ((cm >> col) & 3ull) {                     // uniform: some row of this step needs col or col + 1
-                            const float4 *t4 = reinterpret_cast<const float4 *>(tw + jp * 12);
-                            const float4 t0 = t4[0], t1 = t4[1], t2 = t4[2];
-                            a = contract(t0, t1, t2, ra, col);
-                            if (HAS_B) b = contract(t0, t1, t2, rb, col);
-                        }
-                        if (VW == 2) {
-                            *reinterpret_cast<float2 *>(rowA + col) = a;
-                            if (HAS_B) *reinterpret_cast<float2 *>(rowB + col) = b;
-                        } else {
-                            rowA[col] = a.x;
-                            if (HAS_B) rowB[col] = b.x;
-                            if (col + 1 < D) {
-                                rowA[col + 1] = a.y;
-                                if (HAS_B) rowB[col + 1] = b.y;
+                    const float4 *t4 = reinterpret_cast<const float4 *>(tw);
+#pragma unroll
+                    for (int jp = 0; jp < NPMAX; ++jp) {
+                        if (jp < NP) {                                    // uniform
+                            const int col = 2 * jp;
+                            float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+                            if (pact & (1u << jp)) {                      // uniform: some row of this step needs col or col + 1
+                                const float4 t0 = t4[3 * jp], t1 = t4[3 * jp + 1], t2 = t4[3 * jp + 2];
+                                a = contract(t0, t1, t2, ra, col);
+                                if (HAS_B) b = contract(t0, t1, t2, rb, col);
+                            }
+                            if (VW == 2) {
+                                *reinterpret_cast<float2 *>(rowA + col) = a;
+                                if (HAS_B) *reinterpret_cast<float2 *>(rowB + col) = b;
+                            } else {
+                                rowA[col] = a.x;
+                                if (HAS_B) rowB[col] = b.x;
+                                if (col + 1 < D) {
+                                    rowA[col + 1] = a.y;
+                                    if (HAS_B) rowB[col + 1] = b.y;
+                                }
                             }
                         }
                     }
@@ -389,7 +401,7 @@ static int sm_count_cached() {
     return sms;
 }
 
-template <int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC>
+template <int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX = 1>
 static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const void *q, int64_t N, const void *dev_prims,
                           const void *host_prims, int n_prims, double margin, void *out_vals, void *out_jac, uint8_t *out_valid,
                           cudaStream_t stream) {
@@ -413,6 +425,9 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
     prm.copy_vec = (((long long)R * D) % 4 == 0 && reinterpret_cast<uintptr_t>(out_jac) % 16 == 0) ? 1 : 0;
     for (int s = 0; s < prm.n_steps; ++s) {
         prm.steps[s] = sp->steps[s];
+        unsigned long long pact = 0;            // the kernel wants pair-activity bits, not column bits
+        for (int jp = 0; jp < NP; ++jp) if ((sp->steps[s].cm >> (2 * jp)) & 3ull) pact |= 1ull << jp;
+        prm.steps[s].cm = pact;
         const int len = (sp->steps[s].cntA + sp->steps[s].cntB) * D;
         if ((sp->steps[s].s0 * D) % 4 != 0 || len % 4 != 0) prm.copy_vec = 0;
     }
@@ -450,7 +465,7 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
     while ((1 << prm.logG) < G) ++prm.logG;
     prm.slots3 = 32 / (3 * G);
     prm.n_tiles = (N + G - 1) / G;
-    auto kern = s2_kernel<KIND, SDFK, VW, MaskT, RED, JAC>;
+    auto kern = s2_kernel<KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
@@ -478,12 +493,15 @@ static int launch_s2_mode(S2_SIG, int mode) {
                    : launch_s2_inst<KIND, SDFK, 1, unsigned long long, true, false>(S2_ARGS);
     }
     if (!jac) return launch_s2_inst<KIND, SDFK, 1, unsigned, false, false>(S2_ARGS);
-    if (KIND == KIND_PAIRWISE)
-        return even ? launch_s2_inst<KIND, SDFK, 2, unsigned, false, true>(S2_ARGS) : launch_s2_inst<KIND, SDFK, 1, unsigned, false, true>(S2_ARGS);
-    if (even) return wide ? launch_s2_inst<KIND, SDFK, 2, unsigned long long, false, true>(S2_ARGS)
-                          : launch_s2_inst<KIND, SDFK, 2, unsigned, false, true>(S2_ARGS);
-    return wide ? launch_s2_inst<KIND, SDFK, 1, unsigned long long, false, true>(S2_ARGS)
-                : launch_s2_inst<KIND, SDFK, 1, unsigned, false, true>(S2_ARGS);
+    const int NP = (p->D + 1) / 2;
+#define S2_FULL(VWv, MT, NPM) launch_s2_inst<KIND, SDFK, VWv, MT, false, true, NPM>(S2_ARGS)
+    if (NP <= 4) return even ? S2_FULL(2, unsigned, 4) : S2_FULL(1, unsigned, 4);
+    if (NP <= 8) return even ? S2_FULL(2, unsigned, 8) : S2_FULL(1, unsigned, 8);
+    if (NP <= 16) return even ? S2_FULL(2, unsigned, 16) : S2_FULL(1, unsigned, 16);
+    if (KIND == KIND_PAIRWISE) return set_error("step kernel: pairwise needs D <= 32");
+    (void)wide;
+    return even ? S2_FULL(2, unsigned long long, 32) : S2_FULL(1, unsigned long long, 32);
+#undef S2_FULL
 }
 
 int launch_s2(const skb_plan *p, const skb_s2_program *sp, int kind, const void *q, int64_t N, const void *dev_prims,
