@@ -306,7 +306,7 @@ def run_b200(args):
                        "valid_fraction": valid_frac},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_config": BYTES_PER_CONFIG,
-                         "kernel_ms": kernel_ms, "kernel": "skb::sphere_kernel<float, COLLFREE, jac, all, grid-fast, VW2, u32>"},
+                         "kernel_ms": kernel_ms, "kernel": "skb::s2_kernel<COLLFREE, grid-fast, VW2, u32, all, jac, NP<=8> (skb_sphere2.cu)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "configs/s", "h2d_bytes_per_step": n * D * 4, "d2h_bytes_per_step": n * (S + S * D) * 4,
                     "steps": e2e_steps, "api": "CollFreeConst.evaluate(numpy (N,14) float32, with_jacobian=True) -> numpy", "check": chk},

@@ -667,7 +667,7 @@ static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp) {
     const int n_nodes = (int)p->nodes.size(), nf = p->F, D = p->D;
     const bool pairs = kind == KIND_PAIRWISE;
     const int rows = pairs ? (int)p->pair_thr.size() : nf;
-    if (p->rot_type != SKB_ROT_IGNORE || D < 1 || D > (pairs ? 32 : 64) || n_nodes > 255 || rows < 1) return 0;
+    if (p->rot_type != SKB_ROT_IGNORE || D < 1 || D > 64 || n_nodes > 255 || rows < 1) return 0;
     if (pairs && nf > 4096) return 0;
     const char *force = getenv("SKB_KERNEL");
     if (force && (std::string(force) == "tree" || std::string(force) == "sphere1")) return 0;
@@ -755,6 +755,17 @@ static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp) {
     I[Q_CENNODE_I] = (int)I.size();
     if (pairs) for (int f = 0; f < nf; ++f) I.push_back(p->feat_node[f]);
     while (I.size() % 4) I.push_back(0);
+    I[Q_TABC_I] = (int)I.size();
+    if (pairs && D > 32)
+        for (int s = 0; s < n_steps; ++s)
+            for (int h = 0; h < (sp->steps[s].cntB > 0 ? 2 : 1); ++h)
+                for (int l = 0; l < 32; ++l) {
+                    const int r = sp->steps[s].s0 + 32 * h + l;
+                    const int cnt = h == 0 ? sp->steps[s].cntA : sp->steps[s].cntB;
+                    if (l < cnt) { I.push_back((int32_t)(uint32_t)(plus[r] >> 32)); I.push_back((int32_t)(uint32_t)(minus[r] >> 32)); }
+                    else { I.push_back(0); I.push_back(0); }
+                    I.push_back(0); I.push_back(0);
+                }
     I[Q_I_TOTAL] = (int)I.size();
     Fv.clear();
     I[Q_NODE_F] = 0;

@@ -163,7 +163,8 @@ enum QHdr {
     Q_N_NODES = 0, Q_N_LEVELS, Q_N_STEPS, Q_D, Q_ROWS, Q_N_CEN,
     Q_NODE_I, Q_LEVEL_I, Q_LEVELNODE_I, Q_TABB_I, Q_CENNODE_I, Q_I_TOTAL,
     Q_NODE_F, Q_TABA_F, Q_CENA_F, Q_F_TOTAL,
-    QHDR_WORDS = 16
+    Q_TABC_I,      // pairwise with D > 32: int4 per (step, half, lane) {plus_mask_hi, minus_mask_hi, 0, 0}
+    QHDR_WORDS = 20
 };
 enum { S2_MAX_STEPS = 96 };
 struct skb_s2_step { unsigned long long cm; int32_t s0; int16_t cntA, cntB; };   // cm: columns any row of the step touches

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
     const int32_t *levelI = sI + sI[Q_LEVEL_I];
     const int32_t *levelNodes = sI + sI[Q_LEVELNODE_I];
     const int4 *tabB = reinterpret_cast<const int4 *>(sI + sI[Q_TABB_I]);
+    const int4 *tabC = reinterpret_cast<const int4 *>(sI + sI[Q_TABC_I]);
     const int32_t *cenNode = sI + sI[Q_CENNODE_I];
     const V4 *nodeF = reinterpret_cast<const V4 *>(sF + sI[Q_NODE_F]);
     const V4 *tabA = reinterpret_cast<const V4 *>(sF + sI[Q_TABA_F]);
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
 
         // ------------------------------------------------------------ phase 2: steps of up to 64 rows
         // value + wrench + masks of one row of configuration c
-        auto front = [&](const int c, const V4 &A, const int4 &B, RowState<MaskT> &rs) -> float {
+        auto front = [&](const int c, const V4 &A, const int4 &B, const int tslot, RowState<MaskT> &rs) -> float {
             float val;
             if (KIND == KIND_COLLFREE) {
                 const V4 *fr = reinterpret_cast<const V4 *>(wframes + c * fstride);
@@ -216,6 +217,11 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                 if (JAC) wrench_moment<float>(xi.x, xi.y, xi.z, rs.gx, rs.gy, rs.gz, rs.mx, rs.my, rs.mz);
                 rs.pm = (MaskT)(unsigned)B.y;
                 rs.mm = (MaskT)(unsigned)B.z;
+                if (sizeof(MaskT) == 8) {                     // D > 32: the high mask words live in a second table
+                    const int4 C = tabC[tslot * 32 + lane];
+                    rs.pm |= (MaskT)((unsigned long long)(unsigned)C.x << 32);
+                    rs.mm |= (MaskT)((unsigned long long)(unsigned)C.y << 32);
+                }
             }
             return val;
         };
@@ -235,6 +241,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                 const int s0 = prm.steps[st].s0, cntA = prm.steps[st].cntA, cntB = prm.steps[st].cntB;
                 const int4 B0 = tabB[slot * 32 + lane];
                 const int4 B1 = tabB[(slot + (cntB > 0 ? 1 : 0)) * 32 + lane];
+                const int slotA = slot, slotB = slot + (cntB > 0 ? 1 : 0);
                 V4 A0, A1;
                 if (KIND == KIND_COLLFREE) { A0 = tabA[slot * 32 + lane]; A1 = tabA[(slot + (cntB > 0 ? 1 : 0)) * 32 + lane]; }
                 slot += cntB > 0 ? 2 : 1;
@@ -265,9 +272,9 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                     asm volatile("" : "+r"(tw_off));
                     const float *tw = wtw + tw_off;
                     RowState<MaskT> ra, rb;
-                    const float va = front(c, A0, B0, ra);
+                    const float va = front(c, A0, B0, slotA, ra);
                     float vb = 0.f;
-                    if (HAS_B) vb = front(c, A1, B1, rb);
+                    if (HAS_B) vb = front(c, A1, B1, slotB, rb);
                     if (prm.out_vals != nullptr) {
                         float *gv = tile_vals + (unsigned)(c * R + s0 + lane);
                         if (lane < cntA) st_stream(gv, va);
@@ -338,12 +345,12 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                     RowState<MaskT> rs;
                     V4 A;
                     if (KIND == KIND_COLLFREE) A = tabA[slot * 32 + lane];
-                    const float va = front(c, A, tabB[slot * 32 + lane], rs);
+                    const float va = front(c, A, tabB[slot * 32 + lane], slot, rs);
                     if (lane < cntA && va < best) { best = va; bidx = s0 + lane; brs = rs; }
                     ++slot;
                     if (cntB > 0) {
                         if (KIND == KIND_COLLFREE) A = tabA[slot * 32 + lane];
-                        const float vb = front(c, A, tabB[slot * 32 + lane], rs);
+                        const float vb = front(c, A, tabB[slot * 32 + lane], slot, rs);
                         if (lane < cntB && vb < best) { best = vb; bidx = s0 + 32 + lane; brs = rs; }
                         ++slot;
                     }
@@ -363,13 +370,13 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                     const int src = max(0, __ffs(__ballot_sync(0xffffffffu, bidx == mi && best == m)) - 1);
                     const float gx = __shfl_sync(0xffffffffu, brs.gx, src), gy = __shfl_sync(0xffffffffu, brs.gy, src), gz = __shfl_sync(0xffffffffu, brs.gz, src);
                     const float mx = __shfl_sync(0xffffffffu, brs.mx, src), my = __shfl_sync(0xffffffffu, brs.my, src), mz = __shfl_sync(0xffffffffu, brs.mz, src);
-                    const unsigned long long pm = __shfl_sync(0xffffffffu, (unsigned long long)brs.pm, src);
-                    const unsigned long long mm = __shfl_sync(0xffffffffu, (unsigned long long)brs.mm, src);
+                    const MaskT pm = __shfl_sync(0xffffffffu, brs.pm, src);
+                    const MaskT mm = __shfl_sync(0xffffffffu, brs.mm, src);
                     const float *tw = wtw + c * tstride;
                     for (int col = lane; col < D; col += 32) {     // one lane per column of the single row
                         const float *t2 = tw + (col >> 1) * 12 + (col & 1);
                         float jv = dot6<float>(t2[0], t2[2], t2[4], t2[6], t2[8], t2[10], mx, my, mz, gx, gy, gz);
-                        jv = ((pm >> col) & 1ull) ? jv : (((mm >> col) & 1ull) ? -jv : 0.f);
+                        jv = ((pm >> col) & 1) ? jv : (((mm >> col) & 1) ? -jv : 0.f);
                         prm.out_jac[n * D + col] = jv;
                     }
                 }
@@ -489,8 +496,10 @@ static int launch_s2_mode(S2_SIG, int mode) {
     if (mode == SKB_MODE_CLOSEST || out_valid != nullptr) {
         if (mode != SKB_MODE_CLOSEST && (out_vals != nullptr || jac))
             return set_error("step kernel: validity bytes come with the closest mode or alone");
-        return jac ? launch_s2_inst<KIND, SDFK, 1, unsigned long long, true, true>(S2_ARGS)
-                   : launch_s2_inst<KIND, SDFK, 1, unsigned long long, true, false>(S2_ARGS);
+        if (wide) return jac ? launch_s2_inst<KIND, SDFK, 1, unsigned long long, true, true>(S2_ARGS)
+                             : launch_s2_inst<KIND, SDFK, 1, unsigned long long, true, false>(S2_ARGS);
+        return jac ? launch_s2_inst<KIND, SDFK, 1, unsigned, true, true>(S2_ARGS)
+                   : launch_s2_inst<KIND, SDFK, 1, unsigned, true, false>(S2_ARGS);
     }
     if (!jac) return launch_s2_inst<KIND, SDFK, 1, unsigned, false, false>(S2_ARGS);
     const int NP = (p->D + 1) / 2;
@@ -498,7 +507,6 @@ static int launch_s2_mode(S2_SIG, int mode) {
     if (NP <= 4) return even ? S2_FULL(2, unsigned, 4) : S2_FULL(1, unsigned, 4);
     if (NP <= 8) return even ? S2_FULL(2, unsigned, 8) : S2_FULL(1, unsigned, 8);
     if (NP <= 16) return even ? S2_FULL(2, unsigned, 16) : S2_FULL(1, unsigned, 16);
-    if (KIND == KIND_PAIRWISE) return set_error("step kernel: pairwise needs D <= 32");
     (void)wide;
     return even ? S2_FULL(2, unsigned long long, 32) : S2_FULL(1, unsigned long long, 32);
 #undef S2_FULL

@@ -236,3 +236,35 @@ def test_min_all_equals_closest(pr2):
     va, _ = a.evaluate(q, False)
     vc, _ = c.evaluate(q, False)
     assert torch.equal(va.min(dim=1).values, vc[:, 0])
+
+
+def test_pairwise_jaxon_floating_base_wide_masks():
+    """JAXON 37-DoF floating base self collision (D > 32: 64-bit plus / minus column masks, > 2000 pairs):
+    all-pairs values + Jacobians and the closest row against the oracle, validity == min > 0."""
+    from skmp_b200.constraint import PairWiseSelfCollFreeConst
+    from skmp_b200.robot.jaxon import JaxonConfig
+    from skmp_b200.robot_model import Jaxon
+
+    torch = _torch()
+    jaxon = Jaxon(); jaxon.reset_manip_pose()
+    colkin = JaxonConfig().get_collision_kin()
+    full = PairWiseSelfCollFreeConst(colkin, jaxon)
+    closest = PairWiseSelfCollFreeConst(colkin, jaxon, only_closest_feature=True)
+    assert closest.check_sphere_id_pairs == full.check_sphere_id_pairs and len(full.check_sphere_id_pairs) > 1000
+    rng = np.random.default_rng(12)
+    qs = sample_q(colkin, 300, rng).astype(np.float32).astype(np.float64)
+    q_dev = torch.as_tensor(qs.astype(np.float32), device="cuda")
+    v, j = full.evaluate(q_dev, True)
+    tree, _, jl, base = oracle_args(colkin)
+    sq, gr = oracle.inter_link_sqdists(tree, qs, np.array(full.check_sphere_id_pairs), jl, base)
+    rv = sq - full.check_sphere_pair_sqdists
+    tol = TOL[np.float32]
+    assert close(v.cpu().numpy(), rv, tol) < tol
+    assert close(j.cpu().numpy(), gr, tol) < tol * 4
+    vc, jc = closest.evaluate(q_dev, True)
+    assert torch.equal(vc[:, 0], v.min(dim=1).values)                      # same arithmetic in both modes
+    idx = v.argmin(dim=1)
+    assert torch.equal(jc[:, 0], j[torch.arange(len(qs), device="cuda"), idx])
+    assert torch.equal(closest.is_valid_batch(q_dev), vc[:, 0] > 0)
+    v2, _ = full.evaluate(q_dev, False)
+    assert torch.equal(v2, v)
