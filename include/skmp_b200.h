@@ -47,6 +47,7 @@ enum { SKB_BASE_FIXED = 0, SKB_BASE_PLANER = 1, SKB_BASE_FLOATING = 2 }; /* tiny
 enum { SKB_ROT_IGNORE = 0, SKB_ROT_RPY = 1, SKB_ROT_XYZW = 2 };          /* tinyfk.RotationType */
 enum { SKB_F32 = 0, SKB_F64 = 1 };
 enum { SKB_MODE_ALL = 0, SKB_MODE_CLOSEST = 1 }; /* only_closest_feature (skmp/constraint.py:277,692) */
+enum { SKB_COM_POINT = 0, SKB_COM_STABILITY = 1 }; /* solve_com_fk / COMStabilityConst (skmp/constraint.py:899-928) */
 
 SKB_API int skb_version(void);
 SKB_API const char *skb_last_error(void);
@@ -114,6 +115,9 @@ SKB_API int skb_plan_set_radii(skb_plan *p, const double *radii /* n_features */
  * pairs index into the plan's feature list (0..n_features-1), thresholds = (r1+r2)^2 */
 SKB_API int skb_plan_set_pairs(skb_plan *p, const int32_t *pairs /* 2*P */, int32_t n_pairs,
                                const double *rsum_sq /* P */);
+/* weights of the plan's features for the centre of mass: link masses at the inertial origins, force / g for
+ * "action" links (COMStabilityConst.__init__, skmp/constraint.py:857-897) */
+SKB_API int skb_plan_set_weights(skb_plan *p, const double *weights /* n_features */);
 /* tuning knobs (0 = auto): spheres per staged chunk, staging buffers per warp, warps per CTA */
 SKB_API int skb_plan_set_tuning(skb_plan *p, int32_t chunk_features, int32_t n_buffers, int32_t warps_per_cta,
                                 int32_t ctas_per_sm);
@@ -139,6 +143,13 @@ SKB_API int skb_collfree(const skb_plan *p, const skb_sdf *s, int32_t dtype, con
 SKB_API int skb_pairwise(const skb_plan *p, int32_t dtype, const void *q_dev, int64_t N, int32_t mode,
                          void *out_vals_dev, void *out_jac_dev, uint8_t *out_valid_dev, void *stream);
 
+/* tinyfk.solve_com_fk + COMStabilityConst._evaluate           skmp/constraint.py:899-928
+ *        com = sum_f w_f x_f / sum_f w_f over the plan's features (skb_plan_set_weights).
+ *        SKB_COM_POINT:     out_vals (N,3) = com,          out_jac (N,3,D) (nullable)      [solve_com_fk]
+ *        SKB_COM_STABILITY: out_vals (N,1) = -sdf(com),    out_jac (N,1,D) (nullable)      [the constraint; `s` required] */
+SKB_API int skb_com(const skb_plan *p, const skb_sdf *s /* nullable for SKB_COM_POINT */, int32_t dtype, const void *q_dev,
+                    int64_t N, int32_t what, void *out_vals_dev, void *out_jac_dev, void *stream);
+
 /* ---------------------------------------------------------------- hot path (host pointers)
  * Same semantics with host buffers: what a numpy caller of the reference sees.  Chunked
  * H2D -> kernel -> D2H over internal streams; synchronous on return. */
@@ -149,6 +160,8 @@ SKB_API int skb_collfree_host(const skb_plan *p, const skb_sdf *s, int32_t dtype
                               uint8_t *out_valid_host);
 SKB_API int skb_pairwise_host(const skb_plan *p, int32_t dtype, const void *q_host, int64_t N, int32_t mode,
                               void *out_vals_host, void *out_jac_host, uint8_t *out_valid_host);
+SKB_API int skb_com_host(const skb_plan *p, const skb_sdf *s, int32_t dtype, const void *q_host, int64_t N, int32_t what,
+                         void *out_vals_host, void *out_jac_host);
 
 /* number of kernel launches issued by this process through the library (bench.py's gpu_launches) */
 SKB_API int64_t skb_launch_count(void);

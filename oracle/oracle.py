@@ -209,3 +209,34 @@ def collfree_threaded(n_threads: int, tree: Tree, qs, *args, keep: bool = True, 
     if not keep:
         return int(sum(parts))
     return tuple(np.concatenate([p[i] for p in parts], axis=0) for i in range(len(parts[0])))
+
+
+def com_fk(tree: Tree, qs, point_links, weights, joint_links, base_type=BASE_FIXED, with_jacobian=True):
+    """tinyfk.solve_com_fk restated (call site skmp/constraint.py:901-909): the weighted mean of the point features'
+    positions -- link masses at the inertial origins, action links weighted by force / g -- and of their geometric
+    Jacobians.  [UNVERIFIED-UPSTREAM] for the action-force weighting."""
+    w = np.asarray(weights, dtype=np.float64)
+    pts, jac = solve_fk(tree, qs, point_links, joint_links, base_type, ROT_IGNORE, with_jacobian)
+    com = np.einsum("f,nfk->nk", w, pts) / w.sum()
+    jc = np.einsum("f,nfkd->nkd", w, jac) / w.sum() if with_jacobian else np.empty(0)
+    return com, jc
+
+
+def com_stability(tree: Tree, qs, point_links, weights, joint_links, box: Sdf, base_type=BASE_FIXED, with_jacobian=True,
+                  grad_mode=GRAD_ANALYTIC, with_kink=False):
+    """COMStabilityConst._evaluate restated (skmp/constraint.py:899-928): value = -sdf(com); Jacobian = -grad . J_com
+    with the analytic gradient or the reference's forward difference (eps = 1e-7)."""
+    com, jc = com_fk(tree, qs, point_links, weights, joint_links, base_type, with_jacobian)
+    d, g, kink = box(com, with_grad=True, with_kink=True)
+    vals = -d.reshape(-1, 1)
+    if not with_jacobian:
+        return vals, np.empty(0)
+    if grad_mode == GRAD_FD:
+        eps = 1e-7
+        g = np.zeros_like(com)
+        for i in range(3):
+            xp = com.copy()
+            xp[:, i] += eps
+            g[:, i] = (box(xp) - d) / eps
+    jac = -np.einsum("nk,nkd->nd", g, jc)[:, None, :]
+    return (vals, jac, kink) if with_kink else (vals, jac)

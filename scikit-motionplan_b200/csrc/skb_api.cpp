@@ -162,6 +162,35 @@ int skb_pairwise(const skb_plan *p, int32_t dtype, const void *q_dev, int64_t N,
     return launch_pairwise(p, pp, dtype, q_dev, N, mode, out_vals_dev, out_jac_dev, out_valid_dev, stream);
 }
 
+int skb_com(const skb_plan *p, const skb_sdf *s, int32_t dtype, const void *q_dev, int64_t N, int32_t what, void *out_vals_dev,
+            void *out_jac_dev, void *stream) {
+    if (!p || N < 0 || (N > 0 && (!q_dev || !out_vals_dev))) return set_error("com: bad arguments");
+    if (what != SKB_COM_POINT && what != SKB_COM_STABILITY) return set_error("com: bad `what`");
+    const void *dp = nullptr;
+    int n_prims = 0;
+    if (what == SKB_COM_STABILITY) {
+        if (!s || s->prims.empty()) return set_error("com: the stability constraint needs an SDF");
+        if (s->prims.size() > 64) return set_error("com: more than 64 SDF primitives");
+        dp = get_dev_prims(const_cast<skb_sdf *>(s), dtype);
+        if (!dp) return -1;
+        n_prims = (int)s->prims.size();
+    }
+    const skb_com_program *cp = get_com_program(const_cast<skb_plan *>(p));
+    if (!cp) return -1;
+    return launch_com(p, cp, dtype, q_dev, N, dp, n_prims, what, out_vals_dev, out_jac_dev, stream);
+}
+
+int skb_com_host(const skb_plan *p_, const skb_sdf *s, int32_t dtype, const void *q_host, int64_t N, int32_t what,
+                 void *out_vals_host, void *out_jac_host) {
+    skb_plan *p = const_cast<skb_plan *>(p_);
+    if (!p || N < 0 || (N > 0 && (!q_host || !out_vals_host))) return set_error("com_host: bad arguments");
+    const size_t M = what == SKB_COM_POINT ? 3 : 1;
+    return host_pipeline(p, dtype, q_host, N, M, M * p->D, out_vals_host, out_jac_host, nullptr,
+                         [&](void *dq, int64_t n, void *dv, void *dj, uint8_t *, cudaStream_t st) {
+                             return skb_com(p, s, dtype, dq, n, what, dv, dj, st);
+                         });
+}
+
 int skb_fk_host(const skb_plan *p_, int32_t dtype, const void *q_host, int64_t N, int32_t with_jacobian, void *out_pts_host,
                 void *out_jac_host) {
     skb_plan *p = const_cast<skb_plan *>(p_);

@@ -817,6 +817,102 @@ const skb_s2_program *get_s2_program(skb_plan *p, int kind) {
     return &sp;
 }
 
+
+// ------------------------------------------------------------------ centre-of-mass program (skb_com.cu)
+static int build_com_program(skb_plan *p, skb_com_program *cp) {
+    const int n_nodes = (int)p->nodes.size(), nf = p->F, D = p->D;
+    if (p->rot_type != SKB_ROT_IGNORE) return set_error("com: the plan must be built with rot_type IGNORE");
+    if ((int)p->weights.size() != nf) return set_error("com: skb_plan_set_weights was not called");
+    double W = 0;
+    for (double w : p->weights) { if (!(w >= 0)) return set_error("com: weights must be non-negative"); W += w; }
+    if (!(W > 0)) return set_error("com: the total weight must be positive");
+    if (n_nodes > 255) return set_error("com: too many nodes");
+    // DFS preorder position of every node and the end of its subtree
+    std::vector<int> pos(n_nodes), end(n_nodes);
+    for (int i = 0; i < n_nodes; ++i) pos[p->order[i]] = i;
+    for (int i = n_nodes - 1; i >= 0; --i) {
+        const int k = p->order[i];
+        end[k] = i + 1;
+        for (int c : p->nodes[k].children) end[k] = std::max(end[k], end[c]);
+    }
+    std::vector<int> pts(nf);
+    for (int f = 0; f < nf; ++f) pts[f] = f;
+    std::stable_sort(pts.begin(), pts.end(), [&](int a, int b) { return pos[p->feat_node[a]] < pos[p->feat_node[b]]; });
+    std::vector<int> ppos(nf);
+    for (int i = 0; i < nf; ++i) ppos[i] = pos[p->feat_node[pts[i]]];
+    int n_levels = 0;
+    std::vector<int> level(n_nodes, 0);
+    for (int k = 0; k < n_nodes; ++k) {
+        level[k] = p->nodes[k].parent < 0 ? 0 : level[p->nodes[k].parent] + 1;
+        n_levels = std::max(n_levels, level[k] + 1);
+    }
+    std::vector<std::vector<int>> lv(n_levels);
+    for (int k = 0; k < n_nodes; ++k) lv[level[k]].push_back(k);
+    std::vector<int32_t> &I = cp->I;
+    std::vector<double> &Fv = cp->F;
+    I.assign(CHDR_WORDS, 0);
+    I[C_N_NODES] = n_nodes; I[C_N_LEVELS] = n_levels; I[C_N_POINTS] = nf; I[C_D] = D;
+    I[C_NODE_I] = (int)I.size();
+    for (int k = 0; k < n_nodes; ++k) { I.push_back(p->nodes[k].type); I.push_back(p->nodes[k].col); I.push_back(p->nodes[k].parent); I.push_back(0); }
+    I[C_LEVEL_I] = (int)I.size();
+    int cursor = 0;
+    for (auto &l : lv) { I.push_back(cursor); I.push_back((int)l.size()); cursor += (int)l.size(); }
+    I[C_LEVELNODE_I] = (int)I.size();
+    for (auto &l : lv) for (int k : l) I.push_back(k);
+    I[C_PTNODE_I] = (int)I.size();
+    for (int i = 0; i < nf; ++i) I.push_back(p->feat_node[pts[i]]);
+    while (I.size() % 2) I.push_back(0);
+    I[C_COLRANGE_I] = (int)I.size();
+    std::vector<int> col_node(D, -1);
+    for (int k = 0; k < n_nodes; ++k) if (p->nodes[k].col >= 0) col_node[p->nodes[k].col] = k;
+    for (int d = 0; d < D; ++d) {
+        int a = 0, b = 0;
+        if (col_node[d] >= 0) {
+            const int k = col_node[d];
+            a = (int)(std::lower_bound(ppos.begin(), ppos.end(), pos[k]) - ppos.begin());
+            b = (int)(std::lower_bound(ppos.begin(), ppos.end(), end[k]) - ppos.begin());
+        }
+        I.push_back(a); I.push_back(b);
+    }
+    I[C_I_TOTAL] = (int)I.size();
+    Fv.clear();
+    I[C_NODE_F] = 0;
+    for (int k = 0; k < n_nodes; ++k) {
+        double R[9];
+        quat_to_matrix(p->nodes[k].pre.q, R);
+        for (int r = 0; r < 3; ++r) { Fv.push_back(R[3 * r]); Fv.push_back(R[3 * r + 1]); Fv.push_back(R[3 * r + 2]); Fv.push_back(p->nodes[k].pre.t[r]); }
+    }
+    I[C_PT_F] = (int)Fv.size();
+    for (int i = 0; i < nf; ++i) { for (int j = 0; j < 3; ++j) Fv.push_back(p->feat_off[pts[i]].t[j]); Fv.push_back(p->weights[pts[i]]); }
+    I[C_F_TOTAL] = (int)Fv.size();
+    cp->n_nodes = n_nodes; cp->n_levels = n_levels; cp->n_points = nf;
+    cp->built = true;
+    return 0;
+}
+
+static void free_com(skb_com_program &cp) {
+    if (cp.dI) cudaFree(cp.dI);
+    if (cp.dF32) cudaFree(cp.dF32);
+    if (cp.dF64) cudaFree(cp.dF64);
+    cp = skb_com_program();
+}
+
+const skb_com_program *get_com_program(skb_plan *p) {
+    std::lock_guard<std::mutex> lk(p->mu);
+    skb_com_program &cp = p->com;
+    if (!cp.built && build_com_program(p, &cp) != 0) return nullptr;
+    if (!cp.dI) {
+        if (cudaMalloc(&cp.dI, cp.I.size() * sizeof(int32_t)) != cudaSuccess ||
+            cudaMemcpy(cp.dI, cp.I.data(), cp.I.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("com program upload failed (no CUDA device?)");
+            cp.dI = nullptr;
+            return nullptr;
+        }
+        if (upload_reals<float>(cp.F, &cp.dF32) != 0 || upload_reals<double>(cp.F, &cp.dF64) != 0) return nullptr;
+    }
+    return &cp;
+}
+
 template <typename T>
 static int upload_prims(skb_sdf *s, void **dst) {
     std::vector<DevPrim<T>> v(s->prims.size() ? s->prims.size() : 1);
@@ -1064,6 +1160,7 @@ static void drop_schedules(skb_plan *p) {
     free_sphere(p->sphere);
     free_s2(p->s2_collfree);
     free_s2(p->s2_pairs);
+    free_com(p->com);
 }
 static void drop_pairs(skb_plan *p) {
     free_s2(p->s2_pairs);
@@ -1079,6 +1176,14 @@ int skb_plan_set_radii(skb_plan *p, const double *radii) {
     p->radii.assign(radii, radii + p->F);
     drop_schedules(p);
     drop_pairs(p);
+    return 0;
+}
+
+int skb_plan_set_weights(skb_plan *p, const double *weights) {
+    if (!p || !weights) return set_error("set_weights: bad arguments");
+    std::lock_guard<std::mutex> lk(p->mu);
+    p->weights.assign(weights, weights + p->F);
+    free_com(p->com);
     return 0;
 }
 

@@ -180,6 +180,26 @@ struct skb_s2_program {
     bool built = false, supported = false;
 };
 
+// centre-of-mass program (skb_com.cu): features = weighted points sorted by the DFS preorder of their node
+//   I: header (enum CHdr) | node records (4) | level records (2) | level node lists | node per point |
+//      per column {first point, one past the last point} of the joint's subtree
+//   F: node pre-transforms (12) | point table {off xyz, weight}
+enum CHdr {
+    C_N_NODES = 0, C_N_LEVELS, C_N_POINTS, C_D,
+    C_NODE_I, C_LEVEL_I, C_LEVELNODE_I, C_PTNODE_I, C_COLRANGE_I, C_I_TOTAL,
+    C_NODE_F, C_PT_F, C_F_TOTAL,
+    CHDR_WORDS = 16
+};
+struct skb_com_program {
+    std::vector<int32_t> I;
+    std::vector<double> F;
+    void *dI = nullptr;
+    void *dF32 = nullptr;
+    void *dF64 = nullptr;
+    int n_nodes = 0, n_levels = 0, n_points = 0;
+    bool built = false;
+};
+
 struct skb_stream_ctx;           // host-pipeline scratch (skb_hostpipe.cpp)
 
 struct skb_plan {
@@ -203,6 +223,8 @@ struct skb_plan {
     skb_pair_program pairs;
     skb_sphere_program sphere;
     skb_s2_program s2_collfree, s2_pairs;
+    skb_com_program com;
+    std::vector<double> weights;     // per feature (COM plans), empty otherwise
     bool pairs_set = false;
     std::vector<int32_t> pair_idx;
     std::vector<double> pair_thr;
@@ -233,6 +255,10 @@ int launch_sphere(const skb_plan *p, const skb_sphere_program *sp, int kind, int
                   const void *dev_prims, const void *host_prims, int n_prims, double margin, int mode, void *out_vals,
                   void *out_jac, uint8_t *out_valid, void *stream);
 int launch_expand_cells(const void *grid, int is_f64, const int32_t dims[3], void *cells);
+// skb_com.cu
+const skb_com_program *get_com_program(skb_plan *p);
+int launch_com(const skb_plan *p, const skb_com_program *cp, int dtype, const void *q, int64_t N, const void *dev_prims,
+               int n_prims, int what, void *out_vals, void *out_jac, void *stream);
 // skb_sphere2.cu (fp32, full-output modes)
 int launch_s2(const skb_plan *p, const skb_s2_program *sp, int kind, const void *q, int64_t N, const void *dev_prims,
               const void *host_prims, int n_prims, double margin, int mode, void *out_vals, void *out_jac, uint8_t *out_valid,

@@ -13,6 +13,7 @@ LIB_PATH = _HERE / "libskmp_b200.so"
 
 F32, F64 = 0, 1
 MODE_ALL, MODE_CLOSEST = 0, 1
+COM_POINT, COM_STABILITY = 0, 1
 
 _lib = None
 
@@ -48,11 +49,14 @@ def _declare(lib):
         "skb_plan_dims": ([vp, pi32, pi32, pi32], C.c_int),
         "skb_plan_set_radii": ([vp, pdbl], C.c_int),
         "skb_plan_set_pairs": ([vp, pi32, i32, pdbl], C.c_int),
+        "skb_plan_set_weights": ([vp, pdbl], C.c_int),
         "skb_plan_set_tuning": ([vp, i32, i32, i32, i32], C.c_int),
         "skb_plan_destroy": ([vp], None),
         "skb_fk": ([vp, i32, vp, i64, i32, vp, vp, vp], C.c_int),
         "skb_collfree": ([vp, vp, i32, vp, i64, dbl, i32, vp, vp, vp, vp], C.c_int),
         "skb_pairwise": ([vp, i32, vp, i64, i32, vp, vp, vp, vp], C.c_int),
+        "skb_com": ([vp, vp, i32, vp, i64, i32, vp, vp, vp], C.c_int),
+        "skb_com_host": ([vp, vp, i32, vp, i64, i32, vp, vp], C.c_int),
         "skb_fk_host": ([vp, i32, vp, i64, i32, vp, vp], C.c_int),
         "skb_collfree_host": ([vp, vp, i32, vp, i64, dbl, i32, vp, vp, vp], C.c_int),
         "skb_pairwise_host": ([vp, i32, vp, i64, i32, vp, vp, vp], C.c_int),

@@ -32,7 +32,7 @@ from ._array import Batch, _is_torch, torch
 from .kinematics import CollSpheresKinematicsMapBase, EndEffectorKinematicsMap
 from .rotmath import matrix2quaternion, rpy_angle, wxyz2xyzw
 from .sdf import SignedDistanceFunction, as_descriptor
-from .tinyfk import RotationType
+from .tinyfk import BaseType, RotationType
 from .urdf import parse_urdf
 
 
@@ -485,3 +485,49 @@ class PairWiseSelfCollFreeConst(AbstractIneqConst):
     def _reflect_skrobot_model(self, robot_model) -> None:
         assert robot_model is not None
         self.colkin.reflect_skrobot_model(robot_model)
+
+
+class COMStabilityConst(AbstractIneqConst):
+    """value = -com_box.sdf(com(q)) (positive while the centre of mass projects inside the box), one row.
+
+    Reference: skmp/constraint.py:845-931.  The centre of mass is the weighted mean of the links' inertial origins
+    (URDF masses) and, optionally, of "action" links weighted by force / g -- one fused CUDA launch (FK, weighted
+    prefix sums, box SDF with analytic gradient, chain rule).  The reference differentiates the box by forward
+    differences (eps 1e-7, :912-920); see DESIGN.md "Gradient semantics".
+    """
+
+    def __init__(self, urdfpath, joint_names: List[str], base_type: BaseType, robot_model, com_box,
+                 action_link_names: Optional[List[str]] = None, action_forces: Optional[List[float]] = None,
+                 fksolver_init_hook=None):
+        from .kinematics import _make_solver
+
+        self.dim_cspace = len(joint_names) + (base_type == BaseType.PLANER) * 3 + (base_type == BaseType.FLOATING) * 6
+        self.fksolver = _make_solver(urdfpath, fksolver_init_hook)
+        self.tinyfk_joint_ids = self.fksolver.get_joint_ids(joint_names)
+        self.control_joint_names = list(joint_names)
+        if action_link_names is None:
+            assert action_forces is None
+            self.action_link_ids, self.action_forces = [], []
+        else:
+            assert action_forces is not None and len(action_forces) == len(action_link_names)
+            self.action_link_ids = self.fksolver.get_link_ids(action_link_names)
+            self.action_forces = list(action_forces)
+        self.base_type = base_type
+        self.model = robot_model
+        self.com_box = as_descriptor(com_box)
+        self.reflect_skrobot_model(robot_model)
+        self.assign_id_value()
+
+    def _evaluate(self, qs, with_jacobian: bool = False):
+        b, vals, jac = self.fksolver._com_call(qs, self.tinyfk_joint_ids, self.action_link_ids, self.action_forces,
+                                               self.base_type, with_jacobian, _lib.COM_STABILITY, self.com_box)
+        return b.out(vals), (b.out(jac) if with_jacobian else self.dummy_jacobian())
+
+    def com(self, qs, with_jacobian: bool = False):
+        """Centre of mass (N,3) [+ Jacobian (N,3,D)] of the same weighted point set."""
+        b, vals, jac = self.fksolver._com_call(qs, self.tinyfk_joint_ids, self.action_link_ids, self.action_forces,
+                                               self.base_type, with_jacobian, _lib.COM_POINT, None)
+        return b.out(vals), (b.out(jac) if with_jacobian else None)
+
+    def _reflect_skrobot_model(self, robot_model) -> None:
+        pass   # as the reference (:930-931): the solver keeps its own sticky state

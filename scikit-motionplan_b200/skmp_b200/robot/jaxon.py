@@ -8,7 +8,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from ..collision import SphereCollection
-from ..constraint import BoxConst
+from ..constraint import BoxConst, COMStabilityConst
 from ..kinematics import AttachedObstacleCollPointsKinematicsMap, CollSphereKinematicsMap, EndEffectorKinematicsMap
 from ..robot_model import bundled_urdf
 from ..rotmath import rotation_matrix, rpy_angle
@@ -104,3 +104,9 @@ class JaxonConfig:
             for i in range(3):
                 width[f"{limb}_JOINT{i}"] = 0.1
         return np.hstack([np.array(list(width.values())), np.ones(6) * 0.1])
+
+    def get_com_stability_const(self, robot_model, com_box: Box, action_link_names: Optional[List[str]] = None,
+                                action_forces: Optional[List[float]] = None) -> COMStabilityConst:
+        """skmp/robot/jaxon.py:407-426"""
+        return COMStabilityConst(self.urdf_path(), self._get_control_joint_names(), BaseType.FLOATING, robot_model, com_box,
+                                 action_link_names, action_forces)

@@ -190,10 +190,12 @@ class KinematicModel:
 
     def get_plan(self, feature_ids: Sequence[int], joint_ids: Sequence[int], base_type: BaseType,
                  rot_type: RotationType, radii: Optional[Sequence[float]] = None,
-                 pairs: Optional[np.ndarray] = None, pair_sqdists: Optional[np.ndarray] = None) -> Plan:
+                 pairs: Optional[np.ndarray] = None, pair_sqdists: Optional[np.ndarray] = None,
+                 weights: Optional[Sequence[float]] = None) -> Plan:
         key = (tuple(feature_ids), tuple(joint_ids), base_type, rot_type,
                None if radii is None else tuple(float(r) for r in radii),
-               None if pairs is None else (np.asarray(pairs).tobytes(), np.asarray(pair_sqdists).tobytes()))
+               None if pairs is None else (np.asarray(pairs).tobytes(), np.asarray(pair_sqdists).tobytes()),
+               None if weights is None else tuple(float(w) for w in weights))
         plan = self._plans.get(key)
         if plan is None:
             L = _lib.lib()
@@ -211,6 +213,10 @@ class KinematicModel:
                 pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
                 sq = np.ascontiguousarray(pair_sqdists, dtype=np.float64)
                 _lib.check(L.skb_plan_set_pairs(plan.handle, _lib.dptr(pr, C.c_int32), len(pr), _lib.dptr(sq)))
+            if weights is not None:
+                w = np.ascontiguousarray(weights, dtype=np.float64)
+                assert len(w) == len(feats)
+                _lib.check(L.skb_plan_set_weights(plan.handle, _lib.dptr(w)))
             self._plans[key] = plan
         return plan
 
@@ -250,3 +256,50 @@ class KinematicModel:
                 _lib.check(L.skb_pairwise_host(plan.handle, b.dtype_code, b.q_ptr, b.n, _lib.MODE_ALL, b.ptr(vals), b.ptr(jac), None))
         vals_o = b.out(vals).reshape(-1)
         return vals_o, (b.out(jac).reshape(b.n * P, plan.dim_cspace) if with_jacobian else b.empty0())
+
+    # ------------------------------------------------------------------ centre of mass
+    GRAVITY = 9.8      # action forces (newton) enter the weighted mean as force / GRAVITY (kg)
+
+    def com_points(self, action_link_ids: Sequence[int] = (), action_forces: Sequence[float] = ()):
+        """(feature link ids, weights) of the centre-of-mass plan: one fixed child link at the inertial origin of
+        every link with mass > 0 (created on first use, named ``<link>_com``), plus the action links themselves
+        weighted by force / g."""
+        feats, weights = [], []
+        for i, m in enumerate(list(self.mass)):
+            if m <= 0:
+                continue
+            name = self.link_names[i] + "_com"
+            if name not in self._link_index:
+                self.add_new_link(name, i, self.com[i])
+            feats.append(self._link_index[name])
+            weights.append(float(m))
+        for lid, f in zip(action_link_ids, action_forces):
+            feats.append(int(lid))
+            weights.append(float(f) / self.GRAVITY)
+        if not feats:
+            raise ValueError("the model has no link with a positive mass")
+        return feats, weights
+
+    def _com_call(self, qs, joint_ids, action_link_ids, action_forces, base_type, with_jacobian, what, sdf):
+        feats, weights = self.com_points(action_link_ids, action_forces)
+        plan = self.get_plan(feats, joint_ids, base_type, RotationType.IGNORE, weights=weights)
+        b = Batch(qs, plan.dim_cspace)
+        m = 3 if what == _lib.COM_POINT else 1
+        vals = b.empty((b.n, m))
+        jac = b.empty((b.n, m, plan.dim_cspace)) if with_jacobian else None
+        L = _lib.lib()
+        sdf_h = sdf.native() if sdf is not None else None
+        with b.device_ctx():
+            if b.on_device:
+                _lib.check(L.skb_com(plan.handle, sdf_h, b.dtype_code, b.q_ptr, b.n, what, b.ptr(vals), b.ptr(jac), b.stream))
+            else:
+                _lib.check(L.skb_com_host(plan.handle, sdf_h, b.dtype_code, b.q_ptr, b.n, what, b.ptr(vals), b.ptr(jac)))
+        return b, vals, jac
+
+    def solve_com_fk(self, qs, joint_ids, action_link_ids=(), action_forces=(), base_type: BaseType = BaseType.FIXED,
+                     with_jacobian: bool = False):
+        """-> com (N, 3), jacobian (N*3, D) (call site skmp/constraint.py:901-909, which reshapes it to (N,1,3,D)).
+        com = (sum_l m_l x_l + sum_a (f_a / g) x_a) / (sum_l m_l + sum_a f_a / g)."""
+        b, vals, jac = self._com_call(qs, joint_ids, list(action_link_ids or ()), list(action_forces or ()), base_type,
+                                      with_jacobian, _lib.COM_POINT, None)
+        return b.out(vals), (b.out(jac).reshape(b.n * 3, -1) if with_jacobian else b.empty0())

@@ -268,3 +268,47 @@ def test_pairwise_jaxon_floating_base_wide_masks():
     assert torch.equal(closest.is_valid_batch(q_dev), vc[:, 0] > 0)
     v2, _ = full.evaluate(q_dev, False)
     assert torch.equal(v2, v)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("with_forces", [False, True])
+def test_com_stability_jaxon(dtype, with_forces):
+    """COMStabilityConst (skmp/constraint.py:845-931) and solve_com_fk against the oracle: JAXON 37-DoF floating base,
+    38 massive links (+ 2 action links with 5 N each), box 0.2 x 0.6 x 5."""
+    from skmp_b200.robot.jaxon import JaxonConfig
+    from skmp_b200.robot_model import Jaxon
+    from skmp_b200.sdf import Box
+    from skmp_b200.tinyfk import BaseType
+
+    torch = _torch()
+    jaxon = Jaxon(); jaxon.reset_manip_pose()
+    conf = JaxonConfig()
+    box = Box([0.2, 0.6, 5.0])
+    const = conf.get_com_stability_const(jaxon, box, *( (["RARM_LINK7", "LARM_LINK7"], [5.0, 5.0]) if with_forces else ()))
+    assert isinstance(const.id_value, str)
+    s = const.fksolver
+    feats, w = s.com_points(const.action_link_ids, const.action_forces)
+    tree = oracle.Tree.from_solver(s)
+    jl = s.joint_child_links(const.tinyfk_joint_ids)
+    rng = np.random.default_rng(21)
+    qs = (rng.normal(size=(1000, 37)) * 0.3).astype(dtype).astype(np.float64)
+    q_dev = torch.as_tensor(qs.astype(dtype), device="cuda")
+    tol = TOL[dtype]
+    com, jc = const.com(q_dev, True)
+    rcom, rjc = oracle.com_fk(tree, qs, feats, np.array(w), jl, oracle.BASE_FLOATING)
+    assert com.shape == (1000, 3) and jc.shape == (1000, 3, 37)
+    assert close(com.cpu().numpy(), rcom, tol) < tol and close(jc.cpu().numpy(), rjc, tol) < tol * 2
+    xs, jt = s.solve_com_fk(qs.astype(dtype), const.tinyfk_joint_ids, const.action_link_ids, const.action_forces,
+                            BaseType.FLOATING, True)                  # numpy in -> numpy out, the reference's call shape
+    assert isinstance(xs, np.ndarray) and xs.shape == (1000, 3) and jt.shape == (3000, 37)
+    assert close(xs, rcom, tol) < tol and close(jt.reshape(1000, 3, 37), rjc, tol) < tol * 2
+    v, j = const.evaluate(q_dev, True)
+    rv, rj, kink = oracle.com_stability(tree, qs, feats, np.array(w), jl, oracle.Sdf(box.primitives()), oracle.BASE_FLOATING,
+                                        with_kink=True)
+    assert v.shape == (1000, 1) and j.shape == (1000, 1, 37)
+    assert close(v.cpu().numpy(), rv, tol) < tol
+    ok = kink > (2e-5 if dtype == np.float32 else 1e-9)
+    assert ok.mean() > 0.95 and close(j.cpu().numpy()[ok], rj[ok], tol) < tol * 4
+    v2, j2 = const.evaluate(q_dev, False)
+    assert torch.equal(v2, v) and np.isnan(np.asarray(j2)).all()
+    assert const.is_valid(qs[0].astype(dtype)) == bool(rv[0, 0] > 0)
