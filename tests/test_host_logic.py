@@ -140,3 +140,21 @@ def test_fetch_reachability_box_and_body_obstacles():
     assert (ub > lb).all()
     assert len(conf.get_self_body_obstacles()) >= 2
     f = Fetch(); f.reset_pose()
+
+
+def test_satisfy_shortcuts_and_no_cpu_fallback():
+    """skmp/satisfy.py:55-56: a ConfigPointConst equality is answered without optimisation; anything else needs the GPU."""
+    import torch
+
+    from skmp_b200.constraint import BoxConst, ConfigPointConst
+    from skmp_b200.satisfy import SatisfactionConfig, satisfy_by_optimization, satisfy_by_optimization_batch
+
+    box = BoxConst(-np.ones(3), np.ones(3))
+    eq = ConfigPointConst(np.array([0.1, 0.2, 0.3]))
+    res = satisfy_by_optimization(eq, box, None, None)
+    assert res.success and np.allclose(res.q, [0.1, 0.2, 0.3])
+    cfg = SatisfactionConfig()
+    assert (cfg.ftol, cfg.n_max_eval, cfg.acceptable_error) == (1e-6, 200, 1e-6)      # the reference's defaults (:29-34)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            satisfy_by_optimization_batch(None, box, None, np.zeros((2, 3)))
