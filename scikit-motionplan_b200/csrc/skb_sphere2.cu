@@ -154,18 +154,41 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
     float *wstage = wbase + prm.woff_stage;
     const uint64_t l2_policy = l2_evict_first_policy();
 
-    for (long long tile = (long long)blockIdx.x * n_warps + warp; tile < prm.n_tiles; tile += (long long)gridDim.x * n_warps) {
+    // the next tile's joint values are fetched while the current tile is being processed (first 128 of the G * D values
+    // of a tile; longer tiles read the rest directly), so the DRAM latency of q never sits on the critical path
+    const long long tile_step = (long long)gridDim.x * n_warps;
+    float qn[4];
+    auto fetch_q = [&](const long long t) {
+        const long long b = t * G * D;
+        const int cnt = t < prm.n_tiles ? (int)min((long long)G, prm.N - t * G) * D : 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) qn[k] = (lane + 32 * k < cnt) ? __ldg(prm.q + b + lane + 32 * k) : 0.f;
+    };
+    fetch_q((long long)blockIdx.x * n_warps + warp);
+
+    for (long long tile = (long long)blockIdx.x * n_warps + warp; tile < prm.n_tiles; tile += tile_step) {
         const long long n0 = tile * G;
         const int g_live = (int)min((long long)G, prm.N - n0);
         __syncwarp();
         // q tile + one fully populated sin/cos pass over all G*D joint values
-        for (int i = lane; i < g_live * D; i += 32) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = lane + 32 * k;
+            if (i < g_live * D) {
+                float sn, cs;
+                sincosf(qn[k], &sn, &cs);
+                wq[i] = qn[k];
+                wsc[2 * i] = sn; wsc[2 * i + 1] = cs;
+            }
+        }
+        for (int i = lane + 128; i < g_live * D; i += 32) {
             const float th = prm.q[n0 * D + i];
             float sn, cs;
             sincosf(th, &sn, &cs);
             wq[i] = th;
             wsc[2 * i] = sn; wsc[2 * i + 1] = cs;
         }
+        fetch_q(tile + tile_step);
         __syncwarp();
 
         // ------------------------------------------------------------ phase 1: frames + twists
