@@ -112,7 +112,7 @@ int skb_sdf_eval(const skb_sdf *s, int32_t dtype, const void *pts_dev, int64_t M
 int skb_fk(const skb_plan *p, int32_t dtype, const void *q_dev, int64_t N, int32_t with_jacobian, void *out_pts_dev,
            void *out_jac_dev, void *stream) {
     if (!p || N < 0 || (N > 0 && (!q_dev || !out_pts_dev))) return set_error("fk: bad arguments");
-    if (with_jacobian && !out_jac_dev) return set_error("fk: with_jacobian set but out_jac is NULL");
+    if (N > 0 && with_jacobian && !out_jac_dev) return set_error("fk: with_jacobian set but out_jac is NULL");
     if (p->rot_type == SKB_ROT_IGNORE) {   // point features: lane-per-feature kernel (skb_sphere.cu)
         const skb_sphere_program *sp = get_sphere_program(const_cast<skb_plan *>(p));
         if (sp) return launch_sphere(p, sp, KIND_MAP, dtype, q_dev, N, nullptr, nullptr, 0, 0.0, SKB_MODE_ALL, out_pts_dev,
@@ -195,7 +195,7 @@ int skb_fk_host(const skb_plan *p_, int32_t dtype, const void *q_host, int64_t N
                 void *out_jac_host) {
     skb_plan *p = const_cast<skb_plan *>(p_);
     if (!p || N < 0 || (N > 0 && (!q_host || !out_pts_host))) return set_error("fk_host: bad arguments");
-    if (with_jacobian && !out_jac_host) return set_error("fk_host: with_jacobian set but out_jac is NULL");
+    if (N > 0 && with_jacobian && !out_jac_host) return set_error("fk_host: with_jacobian set but out_jac is NULL");
     const size_t vpc = (size_t)p->F * p->T, jpc = vpc * p->D;
     return host_pipeline(p, dtype, q_host, N, vpc, jpc, out_pts_host, with_jacobian ? out_jac_host : nullptr, nullptr,
                          [&](void *dq, int64_t n, void *dv, void *dj, uint8_t *, cudaStream_t st) {

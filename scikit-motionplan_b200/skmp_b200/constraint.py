@@ -316,8 +316,9 @@ class PoseConstraint(AbstractEqConst):
     def _evaluate(self, qs, with_jacobian: bool = False):
         n_point, n_dim = qs.shape
         xs, jacs = self.efkin.map(qs)       # always with jacobian, like the reference (:455)
-        values = xs.reshape(n_point, -1) - _to_kind(xs, np.hstack(self.desired_poses))
-        jacs = jacs.reshape(n_point, -1, n_dim)
+        m = xs.shape[1] * xs.shape[2]       # explicit: reshape(.., -1) is ambiguous for an empty batch
+        values = xs.reshape(n_point, m) - _to_kind(xs, np.hstack(self.desired_poses))
+        jacs = jacs.reshape(n_point, m, n_dim)
         if self.debug_rank_deficiency:
             jn = jacs.cpu().numpy() if _is_torch(jacs) else jacs
             for jac in jn:

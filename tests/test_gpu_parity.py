@@ -312,3 +312,41 @@ def test_com_stability_jaxon(dtype, with_forces):
     v2, j2 = const.evaluate(q_dev, False)
     assert torch.equal(v2, v) and np.isnan(np.asarray(j2)).all()
     assert const.is_valid(qs[0].astype(dtype)) == bool(rv[0, 0] > 0)
+
+
+def test_ragged_and_empty_batches_bit_exact(pr2):
+    """Tile tails: batches of 0, 1, 3, 5, 33 rows give exactly the rows of a large batch (every mode of both
+    collision constraints, pose map, centre of mass), and N = 0 returns empty arrays of the right shape."""
+    from skmp_b200.constraint import CollFreeConst, PoseConstraint
+    from skmp_b200.robot.fetch import FetchConfig
+    from skmp_b200.robot.jaxon import JaxonConfig
+    from skmp_b200.robot.pr2 import PR2Config
+    from skmp_b200.robot_model import Fetch, Jaxon
+    from skmp_b200.sdf import Box
+
+    torch = _torch()
+    conf = PR2Config()
+    colkin = conf.get_collision_kin()
+    box = box_scene()
+    fetch = Fetch(); fetch.reset_pose()
+    jaxon = Jaxon(); jaxon.reset_manip_pose()
+    cases = [
+        (CollFreeConst(colkin, box.sdf, pr2), 7),
+        (CollFreeConst(colkin, box.sdf, pr2, only_closest_feature=True), 7),
+        (FetchConfig().get_pairwise_selcol_consts(fetch), 8),
+        (FetchConfig().get_pairwise_selcol_consts(fetch, only_closest_feature=True), 8),
+        (PoseConstraint([np.zeros(6)], conf.get_endeffector_kin(), pr2), 7),
+        (JaxonConfig().get_com_stability_const(jaxon, Box([0.2, 0.6, 5.0])), 37),
+    ]
+    g = torch.Generator("cuda").manual_seed(3)
+    for const, d in cases:
+        qs = (torch.rand((133, d), generator=g, device="cuda") - 0.5) * 1.5
+        v, j = const.evaluate(qs, True)
+        for n in (1, 3, 5, 33):
+            v1, j1 = const.evaluate(qs[40:40 + n].contiguous(), True)
+            assert torch.equal(v1, v[40:40 + n]) and torch.equal(j1, j[40:40 + n]), (type(const).__name__, n)
+        v0, j0 = const.evaluate(qs[:0], True)
+        assert v0.shape == (0,) + v.shape[1:] and j0.shape == (0,) + j.shape[1:]
+        if hasattr(const, "is_valid_batch"):
+            assert torch.equal(const.is_valid_batch(qs), (v > 0).all(dim=1))
+            assert const.is_valid_batch(qs[:0]).shape == (0,)
