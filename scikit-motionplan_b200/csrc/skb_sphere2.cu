@@ -365,18 +365,20 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                 int slot = 0;
                 for (int st = 0; st < n_steps; ++st) {
                     const int s0 = prm.steps[st].s0, cntA = prm.steps[st].cntA, cntB = prm.steps[st].cntB;
-                    RowState<MaskT> rs;
-                    V4 A;
-                    if (KIND == KIND_COLLFREE) A = tabA[slot * 32 + lane];
-                    const float va = front(c, A, tabB[slot * 32 + lane], slot, rs);
-                    if (lane < cntA && va < best) { best = va; bidx = s0 + lane; brs = rs; }
-                    ++slot;
-                    if (cntB > 0) {
-                        if (KIND == KIND_COLLFREE) A = tabA[slot * 32 + lane];
-                        const float vb = front(c, A, tabB[slot * 32 + lane], slot, rs);
-                        if (lane < cntB && vb < best) { best = vb; bidx = s0 + 32 + lane; brs = rs; }
-                        ++slot;
-                    }
+                    // both rows of the lane are evaluated before either is compared, so their gathers overlap
+                    RowState<MaskT> rsa, rsb;
+                    V4 Aa, Ab;
+                    const int slot_b = slot + (cntB > 0 ? 1 : 0);
+                    if (KIND == KIND_COLLFREE) { Aa = tabA[slot * 32 + lane]; Ab = tabA[slot_b * 32 + lane]; }
+                    const float va = front(c, Aa, tabB[slot * 32 + lane], slot, rsa);
+                    float vb = __int_as_float(0x7f800000);
+                    if (cntB > 0) vb = front(c, Ab, tabB[slot_b * 32 + lane], slot_b, rsb);
+                    if (lane < cntA && va < best) { best = va; bidx = s0 + lane; brs = rsa; }
+                    if (lane < cntB && vb < best) { best = vb; bidx = s0 + 32 + lane; brs = rsb; }
+                    slot = slot_b + 1;
+                    // validity only: one row at or below zero decides the configuration (the reference's composite
+                    // short-circuits the same way, skmp/constraint.py:167-176)
+                    if (!JAC && prm.out_vals == nullptr && __any_sync(0xffffffffu, best <= 0.f)) break;
                 }
                 float m = best; int mi = bidx;
 #pragma unroll

@@ -109,6 +109,10 @@ def workloads():
         qs = device_samples(colkin, n, 11, scale=0.5); qs[:, 33] += 1.0
         if mode == "all":
             return (lambda: env.evaluate(qs, True)), n, 4 * (D + S + S * D), f"JAXON env CollFreeConst S={S} all + Jacobian, N={n}"
+        if mode == "self_valid":
+            selfc = PairWiseSelfCollFreeConst(colkin, jaxon, only_closest_feature=True)
+            P = len(selfc.check_sphere_id_pairs)
+            return (lambda: selfc.is_valid_batch(qs)), n, 4 * D + 1, f"JAXON self collision P={P} validity bytes, N={n}"
         if mode == "self":
             selfc = PairWiseSelfCollFreeConst(colkin, jaxon, only_closest_feature=True)
             P = len(selfc.check_sphere_id_pairs)
@@ -119,6 +123,7 @@ def workloads():
     W["cfg5_valid"] = lambda: cfg5("valid")
     W["cfg5_env_all"] = lambda: cfg5("all")
     W["cfg5_self_closest"] = lambda: cfg5("self")
+    W["cfg5_self_valid"] = lambda: cfg5("self_valid")
     W["cfg5_pose"] = lambda: cfg5("pose")
     return W
 
