@@ -35,6 +35,19 @@ namespace skb {
 #define SKB_S2_BLOCKS 3         // min CTAs per SM (register cap = 65536 / product)
 #endif
 
+// Launch-time constants of the fp32 corner-packed grid with identity rotation (the cfg3 hot path), folded on the host:
+// origin = world position + lower bound (added in fp64, rounded once), float upper bounds, integer index caps and cell
+// strides -- the lookup then needs no int<->float conversion or address arithmetic on descriptor fields.
+struct GridFast {
+    float ox, oy, oz;          // sample-box origin in world coordinates
+    float ix_, iy_, iz_;       // 1 / spacing
+    float tx, ty, tz;          // dims - 1 (last sample index, as float)
+    int mx, my, mz;            // dims - 2 (last cell index)
+    unsigned sy, sz;           // cells per x step = (ny - 1)(nz - 1) is sy * sz; sy = ny - 1, sz = nz - 1
+    float fill;
+    const float *cells;
+};
+
 struct S2Params {
     const int32_t *I;
     const float *F;
@@ -57,6 +70,7 @@ struct S2Params {
     // warp-uniform data of the hot loop lives in the kernel parameters (constant bank -> uniform datapath)
     skb_s2_step steps[S2_MAX_STEPS];
     DevPrim<float> prim0;
+    GridFast grid;
 };
 
 __device__ __forceinline__ void st_stream(float *p, float v) { __stcs(p, v); }
@@ -76,31 +90,27 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
 
 enum { SDF_UNION = 0, SDF_SINGLE = 1, SDF_GRID_FAST = 2 };
 
-// fp32 corner-packed grid, identity rotation: same arithmetic (and rounding) as sdf_prim_world -> sdf_grid_local for
-// points inside the sample box.  Branch-free: the cell index is clamped and the gather always issued, the fill value /
-// zero gradient are selected afterwards -- so the two gathers of a lane's two rows are in flight together instead of
-// being serialised by a divergent branch.
-__device__ __forceinline__ float s2_grid_fast(const DevPrim<float> &pr, float px, float py, float pz, float &gx, float &gy, float &gz) {
-    const float ux = ((px - pr.pos[0]) - pr.par[0]) * pr.par[3], uy = ((py - pr.pos[1]) - pr.par[1]) * pr.par[4],
-                uz = ((pz - pr.pos[2]) - pr.par[2]) * pr.par[5];
-    const float tx = float(pr.dims[0] - 1), ty = float(pr.dims[1] - 1), tz = float(pr.dims[2] - 1);
-    const bool inside = ux >= 0.f && ux <= tx && uy >= 0.f && uy <= ty && uz >= 0.f && uz <= tz;
-    const int ix = max(0, min((int)floorf(ux), pr.dims[0] - 2)), iy = max(0, min((int)floorf(uy), pr.dims[1] - 2)),
-              iz = max(0, min((int)floorf(uz), pr.dims[2] - 2));
+// Branch-free: the cell index is clamped and the gather always issued, the fill value / zero gradient are selected
+// afterwards -- so the two gathers of a lane's two rows are in flight together instead of being serialised by a
+// divergent branch.  Trilinear value and gradient in the oracle's association order.
+__device__ __forceinline__ float s2_grid_fast(const GridFast &gr, float px, float py, float pz, float &gx, float &gy, float &gz) {
+    const float ux = (px - gr.ox) * gr.ix_, uy = (py - gr.oy) * gr.iy_, uz = (pz - gr.oz) * gr.iz_;
+    const bool inside = ux >= 0.f && ux <= gr.tx && uy >= 0.f && uy <= gr.ty && uz >= 0.f && uz <= gr.tz;
+    const int ix = max(0, min((int)floorf(ux), gr.mx)), iy = max(0, min((int)floorf(uy), gr.my)), iz = max(0, min((int)floorf(uz), gr.mz));
     const float fx = ux - float(ix), fy = uy - float(iy), fz = uz - float(iz);
-    const unsigned cell = ((unsigned)ix * (unsigned)(pr.dims[1] - 1) + (unsigned)iy) * (unsigned)(pr.dims[2] - 1) + (unsigned)iz;
+    const unsigned cell = ((unsigned)ix * gr.sy + (unsigned)iy) * gr.sz + (unsigned)iz;
     float c[8];
-    ldg_cell(reinterpret_cast<const float *>(pr.cells) + (size_t)cell * 8, c);
+    ldg_cell(gr.cells + (size_t)cell * 8, c);
     const float d00 = c[4] - c[0], d01 = c[5] - c[1], d10 = c[6] - c[2], d11 = c[7] - c[3];
     const float c00 = c[0] + fx * d00, c01 = c[1] + fx * d01, c10 = c[2] + fx * d10, c11 = c[3] + fx * d11;
     const float e0 = c10 - c00, e1 = c11 - c01;
     const float c0 = c00 + fy * e0, c1 = c01 + fy * e1;
     const float h = c1 - c0;
     const float dx0 = d00 + fy * (d10 - d00), dx1 = d01 + fy * (d11 - d01);
-    gx = inside ? (dx0 + fz * (dx1 - dx0)) * pr.par[3] : 0.f;
-    gy = inside ? (e0 + fz * (e1 - e0)) * pr.par[4] : 0.f;
-    gz = inside ? h * pr.par[5] : 0.f;
-    return inside ? c0 + fz * h : pr.par[6];
+    gx = inside ? (dx0 + fz * (dx1 - dx0)) * gr.ix_ : 0.f;
+    gy = inside ? (e0 + fz * (e1 - e0)) * gr.iy_ : 0.f;
+    gz = inside ? h * gr.iz_ : 0.f;
+    return inside ? c0 + fz * h : gr.fill;
 }
 
 template <typename MaskT> struct RowState {   // what phase 2 keeps of one output row
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                 const float px = f0.w + f0.x * A.x + f0.y * A.y + f0.z * A.z;
                 const float py = f1.w + f1.x * A.x + f1.y * A.y + f1.z * A.z;
                 const float pz = f2.w + f2.x * A.x + f2.y * A.y + f2.z * A.z;
-                const float d = SDFK == SDF_GRID_FAST ? s2_grid_fast(prm.prim0, px, py, pz, rs.gx, rs.gy, rs.gz)
+                const float d = SDFK == SDF_GRID_FAST ? s2_grid_fast(prm.grid, px, py, pz, rs.gx, rs.gy, rs.gz)
                               : SDFK == SDF_SINGLE    ? sdf_prim_world<float>(prm.prim0, px, py, pz, rs.gx, rs.gy, rs.gz)
                                                       : sdf_union<float>(sP, prm.n_prims, px, py, pz, rs.gx, rs.gy, rs.gz);
                 val = d - A.w - prm.margin;
@@ -452,6 +462,18 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
     prm.i_total = (int)sp->I.size();
     prm.f_total = (int)sp->F.size();
     if (KIND == KIND_COLLFREE && host_prims) prm.prim0 = *reinterpret_cast<const DevPrim<float> *>(host_prims);
+    if (KIND == KIND_COLLFREE && SDFK == SDF_GRID_FAST) {
+        const DevPrim<float> &pr = prm.prim0;
+        GridFast &g = prm.grid;
+        g.ox = (float)((double)pr.pos[0] + (double)pr.par[0]); g.oy = (float)((double)pr.pos[1] + (double)pr.par[1]);
+        g.oz = (float)((double)pr.pos[2] + (double)pr.par[2]);
+        g.ix_ = pr.par[3]; g.iy_ = pr.par[4]; g.iz_ = pr.par[5];
+        g.tx = (float)(pr.dims[0] - 1); g.ty = (float)(pr.dims[1] - 1); g.tz = (float)(pr.dims[2] - 1);
+        g.mx = pr.dims[0] - 2; g.my = pr.dims[1] - 2; g.mz = pr.dims[2] - 2;
+        g.sy = (unsigned)(pr.dims[1] - 1); g.sz = (unsigned)(pr.dims[2] - 1);
+        g.fill = pr.par[6];
+        g.cells = reinterpret_cast<const float *>(pr.cells);
+    }
     const int D = p->D, R = sp->rows, NP = (D + 1) / 2;
     prm.D = D; prm.NP = NP; prm.R = R; prm.n_steps = (int)sp->steps.size(); prm.n_levels = sp->n_levels; prm.n_cen = sp->n_cen;
     prm.copy_vec = (((long long)R * D) % 4 == 0 && reinterpret_cast<uintptr_t>(out_jac) % 16 == 0) ? 1 : 0;
