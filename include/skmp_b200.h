@@ -150,6 +150,14 @@ SKB_API int skb_pairwise(const skb_plan *p, int32_t dtype, const void *q_dev, in
 SKB_API int skb_com(const skb_plan *p, const skb_sdf *s /* nullable for SKB_COM_POINT */, int32_t dtype, const void *q_dev,
                     int64_t N, int32_t what, void *out_vals_dev, void *out_jac_dev, void *stream);
 
+/* One damped Gauss-Newton step for B seeds at once -- the linear-algebra half of the batched replacement of the
+ * sequential SLSQP restarts in satisfy_by_optimization (skmp/satisfy.py:45-143):
+ *   q_new[b] = clamp(q[b] + dq, lb, ub),  (J^T J + lam_b (I + diag J^T J)) dq = -J^T r
+ * J (B,M,D), r (B,M), lam (B), q / q_new (B,D), lb / ub (D); all device pointers of `dtype`; 1 <= D <= 64. */
+SKB_API int skb_lm_step(int32_t dtype, const void *J_dev, const void *r_dev, const void *lam_dev, const void *q_dev,
+                        const void *lb_dev, const void *ub_dev, void *q_new_dev, int64_t B, int32_t M, int32_t D,
+                        void *stream);
+
 /* ---------------------------------------------------------------- hot path (host pointers)
  * Same semantics with host buffers: what a numpy caller of the reference sees.  Chunked
  * H2D -> kernel -> D2H over internal streams; synchronous on return. */

@@ -57,6 +57,7 @@ def _declare(lib):
         "skb_pairwise": ([vp, i32, vp, i64, i32, vp, vp, vp, vp], C.c_int),
         "skb_com": ([vp, vp, i32, vp, i64, i32, vp, vp, vp], C.c_int),
         "skb_com_host": ([vp, vp, i32, vp, i64, i32, vp, vp], C.c_int),
+        "skb_lm_step": ([i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp], C.c_int),
         "skb_fk_host": ([vp, i32, vp, i64, i32, vp, vp], C.c_int),
         "skb_collfree_host": ([vp, vp, i32, vp, i64, dbl, i32, vp, vp, vp], C.c_int),
         "skb_pairwise_host": ([vp, i32, vp, i64, i32, vp, vp, vp], C.c_int),

@@ -10,7 +10,8 @@ the GPU (values + Jacobians from the CUDA kernels) followed by a batched project
 with a per-seed damping factor; violated inequality rows enter as hinge residuals, box bounds by projection.
 The success test is the reference's (:108-112): |e|^2 < acceptable_error, inequality rows valid, inside the box.
 Same public names: SatisfactionConfig, SatisfactionResult, satisfy_by_optimization(_with_budget); the batch entry
-point is satisfy_by_optimization_batch.  The D x D normal-equation solves are torch.linalg (cuSOLVER) calls.
+point is satisfy_by_optimization_batch.  The step itself (normal equations, Cholesky, bound projection) is the CUDA
+kernel ``skb_lm_step`` (csrc/skb_lm.cu), one warp per seed.
 """
 import time
 from dataclasses import dataclass
@@ -62,6 +63,22 @@ def _device():
     if torch is None or not torch.cuda.is_available():
         raise RuntimeError("skmp_b200.satisfy needs a CUDA device (no CPU fallback)")
     return torch.device("cuda", torch.cuda.current_device())
+
+
+def _lm_step(J, r, lam, Q, lb, ub):
+    """skb_lm_step: q_new = clamp(q + dq), (J^T J + lam (I + diag J^T J)) dq = -J^T r  for every seed."""
+    import ctypes as C
+
+    from . import _lib
+
+    J, r = J.contiguous(), r.contiguous()
+    B, M, D = J.shape
+    out = torch.empty_like(Q)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    with torch.cuda.device(Q.device):
+        _lib.check(_lib.lib().skb_lm_step(_lib.F64, p(J), p(r), p(lam), p(Q), p(lb), p(ub), p(out), B, M, D,
+                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out
 
 
 def satisfy_by_optimization_batch(eq_const: Optional[AbstractEqConst], box_const: BoxConst,
@@ -120,12 +137,7 @@ def satisfy_by_optimization_batch(eq_const: Optional[AbstractEqConst], box_const
         done = finished()
         if bool(done.all()):
             break
-        Jt = J.transpose(1, 2)
-        A = Jt @ J
-        b = -(Jt @ r[:, :, None])[:, :, 0]
-        A = A + lam[:, None, None] * (eye + torch.diag_embed(torch.diagonal(A, dim1=1, dim2=2)))
-        dq = torch.linalg.solve(A, b)
-        Qn = torch.minimum(torch.maximum(Q + dq, lb), ub)
+        Qn = _lm_step(J, r, lam, Q, lb, ub)      # CUDA: normal equations + Cholesky + bound projection, warp per seed
         Qn = torch.where(done[:, None], Q, Qn)
         rn, Jn, eq_n, gmin_n = residuals(Qn)
         n_eval += 1

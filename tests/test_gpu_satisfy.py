@@ -87,3 +87,29 @@ def test_relative_pose_dual_arm():
     assert res.success
     v, _ = rel.evaluate_single(res.q, False)
     assert float(np.dot(v, v)) < 1e-6
+
+
+@pytest.mark.parametrize("D,M", [(7, 6), (7, 82), (37, 29), (64, 10)])
+def test_lm_step_kernel_matches_numpy(D, M):
+    """skb_lm_step against numpy.linalg.solve on random systems (rank-deficient J included: M < D relies on the damping)."""
+    import torch
+
+    from skmp_b200.satisfy import _lm_step
+
+    rng = np.random.default_rng(D * 100 + M)
+    B = 33
+    J = rng.normal(size=(B, M, D))
+    J[:, M // 2] = 0.0                                   # an inactive hinge row
+    r = rng.normal(size=(B, M))
+    r[:, M // 2] = 0.0
+    lam = 10.0 ** rng.uniform(-6, 1, size=B)
+    q = rng.normal(size=(B, D))
+    lb, ub = -np.ones(D) * 1.5, np.ones(D) * 1.5
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device="cuda")
+    got = _lm_step(t(J), t(r), t(lam), t(q), t(lb), t(ub)).cpu().numpy()
+    for b in range(B):
+        A = J[b].T @ J[b]
+        A = A + lam[b] * (np.eye(D) + np.diag(np.diag(A)))
+        dq = np.linalg.solve(A, -J[b].T @ r[b])
+        ref = np.clip(q[b] + dq, lb, ub)
+        assert np.abs(got[b] - ref).max() < 1e-7 * max(1.0, np.abs(dq).max())
