@@ -158,6 +158,19 @@ SKB_API int skb_lm_step(int32_t dtype, const void *J_dev, const void *r_dev, con
                         const void *lb_dev, const void *ub_dev, void *q_new_dev, int64_t B, int32_t M, int32_t D,
                         void *stream);
 
+/* Batched edge discretisation for is_valid_motion_step (skmp/solver/motion_step_box.py:8-57), fp64 and sequential like
+ * the reference so the sample lists are bit-identical:
+ *   skb_edge_counts   counts[e] = len(interpolate_fractions(box, q1[e], q2[e], include_q1))
+ *   skb_edge_samples  rows offsets[e] .. offsets[e+1] of `samples` = q1[e] + (q2[e] - q1[e]) * frac   (out_dtype rows)
+ *   skb_segment_all   out[e] = AND of valid[offsets[e] .. offsets[e+1])   (an edge without samples is valid)
+ * q1 / q2 (E,D) fp64, box (D) fp64, offsets (E+1) int64 = exclusive prefix sum of counts. */
+SKB_API int skb_edge_counts(const double *q1_dev, const double *q2_dev, const double *box_dev, int64_t E, int32_t D,
+                            int32_t include_q1, int64_t *counts_dev, void *stream);
+SKB_API int skb_edge_samples(const double *q1_dev, const double *q2_dev, const double *box_dev, int64_t E, int32_t D,
+                             int32_t include_q1, const int64_t *offsets_dev, int32_t out_dtype, void *samples_dev,
+                             void *stream);
+SKB_API int skb_segment_all(const uint8_t *valid_dev, const int64_t *offsets_dev, int64_t E, uint8_t *out_dev, void *stream);
+
 /* ---------------------------------------------------------------- hot path (host pointers)
  * Same semantics with host buffers: what a numpy caller of the reference sees.  Chunked
  * H2D -> kernel -> D2H over internal streams; synchronous on return. */

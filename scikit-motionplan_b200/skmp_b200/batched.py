@@ -77,22 +77,65 @@ def edge_samples(motion_step_box, q1s, q2s, include_q1: bool = True):
     return samples, offsets
 
 
-def is_valid_motion_step_batch(motion_step_box, q1s, q2s, ineq_const, dtype=np.float32, device=None) -> np.ndarray:
+def edge_samples_device(motion_step_box, q1s, q2s, include_q1: bool = True, dtype=np.float32, device=None):
+    """``edge_samples`` on the GPU (csrc/skb_edges.cu): -> (samples (n_samples, D) CUDA tensor of ``dtype``, offsets
+    (E+1,) int64 CUDA tensor).  fp64 sequential fraction arithmetic, bit-identical to the host version; q1s / q2s may
+    be numpy arrays or CUDA tensors (fp64 is used for the interpolation either way)."""
+    import ctypes as C
+
+    from . import _lib
+
+    if torch is None or not torch.cuda.is_available():
+        raise RuntimeError("edge_samples_device needs a CUDA device (no CPU fallback)")
+    dev = (q1s.device if _is_torch(q1s) and q1s.is_cuda else torch.device("cuda", torch.cuda.current_device())) if device is None else device
+    q1 = torch.as_tensor(q1s, device=dev).to(torch.float64).reshape(-1, len(motion_step_box)).contiguous()
+    q2 = torch.as_tensor(q2s, device=dev).to(torch.float64).reshape(-1, len(motion_step_box)).contiguous()
+    assert q1.shape == q2.shape
+    box = torch.as_tensor(np.asarray(motion_step_box, dtype=np.float64), device=dev)
+    E, D = q1.shape
+    L = _lib.lib()
+    p = lambda t: C.c_void_p(t.data_ptr())
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        counts = torch.zeros(E, dtype=torch.int64, device=dev)
+        _lib.check(L.skb_edge_counts(p(q1), p(q2), p(box), E, D, int(include_q1), p(counts), st))
+        offsets = torch.zeros(E + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, dim=0, out=offsets[1:])
+        n = int(offsets[-1].item()) if E else 0                      # the one scalar read-back: output allocation
+        tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+        samples = torch.empty((n, D), dtype=tdt, device=dev)
+        if n:
+            _lib.check(L.skb_edge_samples(p(q1), p(q2), p(box), E, D, int(include_q1), p(offsets),
+                                          _lib.F64 if tdt == torch.float64 else _lib.F32, p(samples), st))
+    return samples, offsets
+
+
+def is_valid_motion_step_batch(motion_step_box, q1s, q2s, ineq_const, dtype=np.float32, device=None):
     """``is_valid_motion_step`` (motion_step_box.py:44-57) for E edges at once -> (E,) bool.
 
-    An edge is valid iff every sample satisfies ``all(values > 0)``; an edge with no sample is valid.
-    One ``is_valid_batch`` launch over all samples; the per-edge AND is a segmented min on the device."""
+    An edge is valid iff every sample satisfies ``all(values > 0)``; an edge with no sample is valid.  With a CUDA
+    device everything stays on the GPU: edge discretisation (``skb_edge_counts`` / ``skb_edge_samples``), ONE
+    ``is_valid_batch`` launch per constraint over all samples, per-edge AND (``skb_segment_all``); the result is a
+    numpy array for numpy inputs and a CUDA bool tensor for CUDA tensor inputs."""
+    if torch is not None and torch.cuda.is_available():
+        import ctypes as C
+
+        from . import _lib
+
+        samples, offsets = edge_samples_device(motion_step_box, q1s, q2s, True, dtype, device)
+        E = offsets.numel() - 1
+        out = torch.ones(E, dtype=torch.uint8, device=samples.device)
+        if samples.shape[0]:
+            ok = ineq_const.is_valid_batch(samples).to(torch.uint8).contiguous()
+            with torch.cuda.device(samples.device):
+                _lib.check(_lib.lib().skb_segment_all(C.c_void_p(ok.data_ptr()), C.c_void_p(offsets.data_ptr()), E,
+                                                      C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        res = out.bool()
+        return res if (_is_torch(q1s) and q1s.is_cuda) else res.cpu().numpy()
     samples, offsets = edge_samples(motion_step_box, q1s, q2s, include_q1=True)
     E = len(offsets) - 1
     if len(samples) == 0:
         return np.ones(E, dtype=bool)
-    if torch is not None and torch.cuda.is_available():
-        dev = torch.device("cuda") if device is None else device
-        q = torch.as_tensor(samples.astype(dtype), device=dev)
-        ok = ineq_const.is_valid_batch(q).to(torch.uint8)
-        lengths = torch.as_tensor(np.diff(offsets), device=dev)
-        per_edge = torch.segment_reduce(ok.float(), "min", lengths=lengths, initial=1.0)
-        return (per_edge > 0.5).cpu().numpy()
     ok = np.asarray(ineq_const.is_valid_batch(samples.astype(dtype)))      # host constraints (BoxConst ...) only
     out = np.ones(E, dtype=bool)
     nz = np.diff(offsets) > 0

@@ -117,6 +117,22 @@ def workloads():
             selfc = PairWiseSelfCollFreeConst(colkin, jaxon, only_closest_feature=True)
             P = len(selfc.check_sphere_id_pairs)
             return (lambda: selfc.evaluate(qs, True)), n, 4 * (D + 1 + D), f"JAXON self collision P={P} closest + Jacobian, N={n}"
+        if mode == "edges":
+            # RRT edge validity (BASELINE config 5): env + self collision over every interpolated sample of every edge
+            from skmp_b200.batched import edge_samples_device, is_valid_motion_step_batch
+            from skmp_b200.constraint import IneqCompositeConst
+
+            selfc = PairWiseSelfCollFreeConst(colkin, jaxon, only_closest_feature=True)
+            comp = IneqCompositeConst([env, selfc])
+            step_box = conf.get_motion_step_box()
+            E = 200_000
+            q1 = qs[:E].double()
+            g = torch.Generator(device="cuda").manual_seed(5)
+            q2 = q1 + torch.randn((E, D), generator=g, device="cuda", dtype=torch.float64) * 0.25
+            _, off = edge_samples_device(step_box, q1, q2)
+            ns = int(off[-1])
+            return (lambda: is_valid_motion_step_batch(step_box, q1, q2, comp)), ns, 4 * D + 1, \
+                f"JAXON RRT edge validity: {E} edges -> {ns} samples, env + self collision, discretisation + validity + per-edge AND on the GPU"
         efkin = conf.get_endeffector_kin(rot_type=RotationType.XYZW)
         pose = PoseConstraint([np.zeros(7)] * 4, efkin, jaxon)
         return (lambda: pose.evaluate(qs, True)), n, 4 * (D + 28 + 28 * D), f"JAXON PoseConstraint 4 x XYZW + Jacobian, N={n}"
@@ -125,6 +141,7 @@ def workloads():
     W["cfg5_self_closest"] = lambda: cfg5("self")
     W["cfg5_self_valid"] = lambda: cfg5("self_valid")
     W["cfg5_pose"] = lambda: cfg5("pose")
+    W["cfg5_edges"] = lambda: cfg5("edges")
     return W
 
 

@@ -3,7 +3,9 @@
 algorithm restated on the CPU -- scipy SLSQP with the objective |e|^2 and the inequality g - 1e-6 >= 0 exactly as
 skmp/satisfy.py:66-106, constraints evaluated by the CPU oracle (fp64, forward-difference SDF gradient).
 
-  python scikit-motionplan_b200/tools/bench_ik.py [--seeds 4096] [--cpu-seeds 24]
+Lives under tests/ because it executes the oracle (test infrastructure) as the CPU side of the comparison.
+
+  python tests/bench_ik.py [--seeds 4096] [--cpu-seeds 24]
 """
 import argparse
 import json
@@ -13,7 +15,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parents[2]
+ROOT = Path(__file__).resolve().parents[1]
 for p in (ROOT, ROOT / "scikit-motionplan_b200", ROOT / "tests"):
     if str(p) not in sys.path:
         sys.path.insert(0, str(p))

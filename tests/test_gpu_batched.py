@@ -86,3 +86,46 @@ def test_sharded_entry_points_single_rank():
     assert (s, e) == (0, 1000) and vals.is_cuda and vals.shape == (1000, 76) and jac.shape == (1000, 76, 7)
     valid = sharded_is_valid(const, qs)
     assert valid.shape == (1000,) and (valid.cpu() == (vals > 0).all(dim=1).cpu()).all()
+
+
+@pytest.mark.parametrize("include_q1", [True, False])
+def test_device_edge_discretisation_is_bit_identical_to_the_reference_loop(include_q1):
+    """csrc/skb_edges.cu against the host restatement of motion_step_box.py:8-41 (itself compared with the reference
+    loop line by line in test_batched_host.py): same counts, same fp64 samples bit for bit, fp32 = rounded fp64."""
+    import torch
+
+    from skmp_b200.batched import edge_samples, edge_samples_device
+
+    rng = np.random.default_rng(0)
+    box = np.array([0.05, 0.05, 0.1, 0.2, 0.03, 0.1, 0.5])
+    q1s = rng.uniform(-2, 2, size=(3000, 7))
+    q2s = q1s + rng.normal(size=(3000, 7)) * rng.choice([1e-8, 0.01, 0.3, 2.0], size=(3000, 1))
+    q2s[5] = q1s[5]                                                   # identical points -> no sample
+    q2s[6] = q1s[6] + np.array([0.1, 0, 0, 0, 0, 0, 0])               # exactly two steps on the active axis
+    q2s[7] = q1s[7] + np.array([0.05 * 7, 0, 0, 0, 0, 0, 0])
+    if not include_q1:
+        # the reference raises IndexError for a step ratio of exactly 1.0 without q1 (empty list indexed); keep off it
+        q2s[6] = q1s[6] + np.array([0.11, 0, 0, 0, 0, 0, 0])
+    ref, off = edge_samples(box, q1s, q2s, include_q1)
+    got, goff = edge_samples_device(box, q1s, q2s, include_q1, dtype=np.float64)
+    assert np.array_equal(goff.cpu().numpy(), off)
+    assert np.array_equal(got.cpu().numpy(), ref)
+    got32, _ = edge_samples_device(box, torch.as_tensor(q1s, device="cuda"), torch.as_tensor(q2s, device="cuda"), include_q1)
+    assert got32.dtype == torch.float32 and np.array_equal(got32.cpu().numpy(), ref.astype(np.float32))
+    e0, o0 = edge_samples_device(box, q1s[:0], q2s[:0], include_q1)
+    assert e0.shape == (0, 7) and o0.tolist() == [0]
+
+
+def test_edge_validity_cuda_inputs_return_cuda_bools():
+    import torch
+
+    from skmp_b200.batched import is_valid_motion_step_batch
+
+    pr2, conf, colkin, box, const = _scene()
+    rng = np.random.default_rng(21)
+    q1s, q2s = sample_q(colkin, 2000, rng), sample_q(colkin, 2000, rng)
+    step_box = conf.get_default_motion_step_box()
+    a = is_valid_motion_step_batch(step_box, q1s, q2s, const)
+    b = is_valid_motion_step_batch(step_box, torch.as_tensor(q1s, device="cuda"), torch.as_tensor(q2s, device="cuda"), const)
+    assert isinstance(a, np.ndarray) and b.is_cuda and b.dtype == torch.bool
+    assert np.array_equal(a, b.cpu().numpy())
