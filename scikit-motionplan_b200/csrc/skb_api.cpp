@@ -118,6 +118,8 @@ int skb_fk(const skb_plan *p, int32_t dtype, const void *q_dev, int64_t N, int32
         if (sp) return launch_sphere(p, sp, KIND_MAP, dtype, q_dev, N, nullptr, nullptr, 0, 0.0, SKB_MODE_ALL, out_pts_dev,
                                      with_jacobian ? out_jac_dev : nullptr, nullptr, stream);
     }
+    else if (const skb_pose_program *pp = get_pose_program(const_cast<skb_plan *>(p)))   // RPY / XYZW rows (skb_pose.cu)
+        return launch_pose(p, pp, dtype, q_dev, N, out_pts_dev, with_jacobian ? out_jac_dev : nullptr, stream);
     const skb_schedule *sch = get_schedule(const_cast<skb_plan *>(p), p->T);
     if (!sch) return -1;
     return launch_tree(p, sch, KIND_MAP, dtype, q_dev, N, nullptr, 0, 0.0, SKB_MODE_ALL, out_pts_dev,

@@ -913,6 +913,95 @@ const skb_com_program *get_com_program(skb_plan *p) {
     return &cp;
 }
 
+
+// ------------------------------------------------------------------ pose program (skb_pose.cu)
+static int build_pose_program(skb_plan *p, skb_pose_program *pp) {
+    pp->built = true;
+    pp->supported = false;
+    const int n_nodes = (int)p->nodes.size(), nf = p->F, D = p->D;
+    if (p->rot_type == SKB_ROT_IGNORE || D < 1 || D > 64 || n_nodes > 255 || nf > 256) return 0;
+    const char *force = getenv("SKB_KERNEL");
+    if (force && std::string(force) == "tree") return 0;
+    int n_levels = 0;
+    std::vector<int> level(n_nodes, 0);
+    for (int k = 0; k < n_nodes; ++k) {
+        level[k] = p->nodes[k].parent < 0 ? 0 : level[p->nodes[k].parent] + 1;
+        n_levels = std::max(n_levels, level[k] + 1);
+    }
+    std::vector<std::vector<int>> lv(n_levels);
+    for (int k = 0; k < n_nodes; ++k) lv[level[k]].push_back(k);
+    std::vector<uint64_t> nmask(n_nodes, 0);
+    for (int k = 1; k < n_nodes; ++k) {
+        nmask[k] = nmask[p->nodes[k].parent];
+        if (p->nodes[k].col >= 0) nmask[k] |= (uint64_t)1 << p->nodes[k].col;
+    }
+    std::vector<int32_t> &I = pp->I;
+    std::vector<double> &Fv = pp->F;
+    I.assign(EHDR_WORDS, 0);
+    I[E_N_NODES] = n_nodes; I[E_N_LEVELS] = n_levels; I[E_N_FEAT] = nf; I[E_D] = D;
+    I[E_NODE_I] = (int)I.size();
+    for (int k = 0; k < n_nodes; ++k) { I.push_back(p->nodes[k].type); I.push_back(p->nodes[k].col); I.push_back(p->nodes[k].parent); I.push_back(0); }
+    I[E_LEVEL_I] = (int)I.size();
+    int cursor = 0;
+    for (auto &l : lv) { I.push_back(cursor); I.push_back((int)l.size()); cursor += (int)l.size(); }
+    I[E_LEVELNODE_I] = (int)I.size();
+    for (auto &l : lv) for (int k : l) I.push_back(k);
+    while (I.size() % 4) I.push_back(0);
+    I[E_FEAT_I] = (int)I.size();
+    for (int f = 0; f < nf; ++f) {
+        const uint64_t am = nmask[p->feat_node[f]];
+        I.push_back(p->feat_node[f]); I.push_back((int32_t)(uint32_t)(am & 0xffffffffu)); I.push_back((int32_t)(uint32_t)(am >> 32)); I.push_back(0);
+    }
+    I[E_I_TOTAL] = (int)I.size();
+    Fv.clear();
+    I[E_NODE_F] = 0;
+    for (int k = 0; k < n_nodes; ++k) {
+        double R[9];
+        quat_to_matrix(p->nodes[k].pre.q, R);
+        for (int r = 0; r < 3; ++r) { Fv.push_back(R[3 * r]); Fv.push_back(R[3 * r + 1]); Fv.push_back(R[3 * r + 2]); Fv.push_back(p->nodes[k].pre.t[r]); }
+    }
+    I[E_NODEQ_F] = (int)Fv.size();
+    for (int k = 0; k < n_nodes; ++k) for (int j = 0; j < 4; ++j) Fv.push_back(p->nodes[k].pre.q[j]);
+    I[E_FEAT_F] = (int)Fv.size();
+    for (int f = 0; f < nf; ++f) {
+        double R[9];
+        quat_to_matrix(p->feat_off[f].q, R);
+        for (int j = 0; j < 3; ++j) Fv.push_back(p->feat_off[f].t[j]);
+        Fv.push_back(0.0);
+        for (int j = 0; j < 9; ++j) Fv.push_back(R[j]);
+        for (int j = 0; j < 3; ++j) Fv.push_back(0.0);
+        for (int j = 0; j < 4; ++j) Fv.push_back(p->feat_off[f].q[j]);
+    }
+    I[E_F_TOTAL] = (int)Fv.size();
+    pp->n_nodes = n_nodes; pp->n_levels = n_levels;
+    pp->supported = true;
+    return 0;
+}
+
+static void free_pose(skb_pose_program &pp) {
+    if (pp.dI) cudaFree(pp.dI);
+    if (pp.dF32) cudaFree(pp.dF32);
+    if (pp.dF64) cudaFree(pp.dF64);
+    pp = skb_pose_program();
+}
+
+const skb_pose_program *get_pose_program(skb_plan *p) {
+    std::lock_guard<std::mutex> lk(p->mu);
+    skb_pose_program &pp = p->pose;
+    if (!pp.built && build_pose_program(p, &pp) != 0) return nullptr;
+    if (!pp.supported) return nullptr;
+    if (!pp.dI) {
+        if (cudaMalloc(&pp.dI, pp.I.size() * sizeof(int32_t)) != cudaSuccess ||
+            cudaMemcpy(pp.dI, pp.I.data(), pp.I.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("pose program upload failed (no CUDA device?)");
+            pp.dI = nullptr;
+            return nullptr;
+        }
+        if (upload_reals<float>(pp.F, &pp.dF32) != 0 || upload_reals<double>(pp.F, &pp.dF64) != 0) return nullptr;
+    }
+    return &pp;
+}
+
 template <typename T>
 static int upload_prims(skb_sdf *s, void **dst) {
     std::vector<DevPrim<T>> v(s->prims.size() ? s->prims.size() : 1);
@@ -1161,6 +1250,7 @@ static void drop_schedules(skb_plan *p) {
     free_s2(p->s2_collfree);
     free_s2(p->s2_pairs);
     free_com(p->com);
+    free_pose(p->pose);
 }
 static void drop_pairs(skb_plan *p) {
     free_s2(p->s2_pairs);

@@ -200,6 +200,25 @@ struct skb_com_program {
     bool built = false;
 };
 
+// pose program (skb_pose.cu): end-effector frames with RPY / XYZW rows on the warp-cooperative FK
+//   I: header (enum EHdr) | node records (4) | level records (2) | level node lists | feature records int4 {node, amask_lo, amask_hi, 0}
+//   F: node pre-transforms (12) | node pre-rotation quaternions (4) | per feature 20: off(3) pad | R_off(9) pad(3) | quat_off(4)
+enum EHdr {
+    E_N_NODES = 0, E_N_LEVELS, E_N_FEAT, E_D,
+    E_NODE_I, E_LEVEL_I, E_LEVELNODE_I, E_FEAT_I, E_I_TOTAL,
+    E_NODE_F, E_NODEQ_F, E_FEAT_F, E_F_TOTAL,
+    EHDR_WORDS = 16
+};
+struct skb_pose_program {
+    std::vector<int32_t> I;
+    std::vector<double> F;
+    void *dI = nullptr;
+    void *dF32 = nullptr;
+    void *dF64 = nullptr;
+    int n_nodes = 0, n_levels = 0;
+    bool built = false, supported = false;
+};
+
 struct skb_stream_ctx;           // host-pipeline scratch (skb_hostpipe.cpp)
 
 struct skb_plan {
@@ -224,6 +243,7 @@ struct skb_plan {
     skb_sphere_program sphere;
     skb_s2_program s2_collfree, s2_pairs;
     skb_com_program com;
+    skb_pose_program pose;
     std::vector<double> weights;     // per feature (COM plans), empty otherwise
     bool pairs_set = false;
     std::vector<int32_t> pair_idx;
@@ -255,6 +275,10 @@ int launch_sphere(const skb_plan *p, const skb_sphere_program *sp, int kind, int
                   const void *dev_prims, const void *host_prims, int n_prims, double margin, int mode, void *out_vals,
                   void *out_jac, uint8_t *out_valid, void *stream);
 int launch_expand_cells(const void *grid, int is_f64, const int32_t dims[3], void *cells);
+// skb_pose.cu
+const skb_pose_program *get_pose_program(skb_plan *p);     // nullptr when the plan is not eligible (not an error)
+int launch_pose(const skb_plan *p, const skb_pose_program *pp, int dtype, const void *q, int64_t N, void *out_pts, void *out_jac,
+                void *stream);
 // skb_com.cu
 const skb_com_program *get_com_program(skb_plan *p);
 int launch_com(const skb_plan *p, const skb_com_program *cp, int dtype, const void *q, int64_t N, const void *dev_prims,

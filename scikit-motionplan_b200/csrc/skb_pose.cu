@@ -1,0 +1,303 @@
+// skb_pose.cu -- pose features (position + roll-pitch-yaw or quaternion) and their Jacobians on the warp-cooperative
+// forward kinematics:
+//
+//     EndEffectorKinematicsMap.map with RotationType.RPY / XYZW          (skmp/kinematics.py:43-63,153-162)
+//     PoseConstraint._evaluate = flatten(map(qs)) - target               (skmp/constraint.py:451-472)
+//
+// One warp owns a tile of G configurations.
+//   phase 1   frames + twists, three lanes per (configuration, node)                     -> fk_phase (skb_device.cuh)
+//   phase 1q  (XYZW) node quaternions by the same level walk, Q = Q_parent * Q_pre * Qz(theta / 2): the quaternion is
+//             the PRODUCT along the chain like the reference's, not a conversion of the rotation matrix (sign!)
+//   phase 1c  lane per (configuration, feature): position, rpy angles / quaternion -> values out, and the few scalars the
+//             rotational Jacobian rows need into a small shared record
+//   phase 2   lane per (configuration, column) of the tile, flattened: the lane keeps ITS joint twist (omega, v) in
+//             registers and walks the features; row k of feature f is one value per lane, so every store instruction
+//             writes consecutive columns of one output row (coalesced), structural zeros included.
+//                 position rows   omega x p + v
+//                 RPY rows        [ (cy wx + sy wy) / cp,  cy wy - sy wx,  wz + sp (cy wx + sy wy) / cp ]
+//                 XYZW rows       1/2 Xi(q) omega
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+#include "skb_device.cuh"
+#include "skb_internal.h"
+
+namespace skb {
+
+template <typename T>
+struct PoseParams {
+    const int32_t *I;
+    const T *F;
+    const T *q;
+    long long N;
+    long long n_tiles;
+    T *out_pts;
+    T *out_jac;
+    int i_total, f_total;
+    int off_F, off_warp, warp_elems;
+    int woff_q, woff_sc, woff_sch, woff_frames, woff_tw, woff_quat, woff_feat;
+    int fstride, tstride, qstride, featstride;
+    int G, logG, slots3;
+    int D, n_feat, n_levels, rot_type, tdim;
+};
+
+template <typename T>
+__device__ __forceinline__ void qmul(const T a[4], const T b[4], T o[4]) {    // (x, y, z, w)
+    o[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    o[1] = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+    o[2] = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3];
+    o[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+}
+
+template <typename T, int ROT>
+__global__ void __launch_bounds__(256) pose_kernel(const PoseParams<T> prm) {
+    using V4 = Vec4<T>;
+    using Rl = Real<T>;
+    constexpr int TD = ROT == SKB_ROT_RPY ? 6 : 7;
+    extern __shared__ __align__(16) unsigned char smem[];
+    int32_t *sI = reinterpret_cast<int32_t *>(smem);
+    T *sF = reinterpret_cast<T *>(smem + prm.off_F);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+    for (int i = tid; i < prm.i_total; i += blockDim.x) sI[i] = prm.I[i];
+    for (int i = tid; i < prm.f_total; i += blockDim.x) sF[i] = prm.F[i];
+    __syncthreads();
+
+    const int D = prm.D, F = prm.n_feat, n_levels = prm.n_levels, G = prm.G, logG = prm.logG;
+    const int fstride = prm.fstride, tstride = prm.tstride, qstride = prm.qstride, featstride = prm.featstride;
+    const int32_t *nodeI = sI + sI[E_NODE_I];
+    const int32_t *levelI = sI + sI[E_LEVEL_I];
+    const int32_t *levelNodes = sI + sI[E_LEVELNODE_I];
+    const int4 *featI = reinterpret_cast<const int4 *>(sI + sI[E_FEAT_I]);
+    const V4 *nodeF = reinterpret_cast<const V4 *>(sF + sI[E_NODE_F]);
+    const V4 *nodeQ = reinterpret_cast<const V4 *>(sF + sI[E_NODEQ_F]);
+    const T *featF = sF + sI[E_FEAT_F];                 // 20 per feature: off(3) pad | R(9) pad(3) | quat(4)
+
+    T *wbase = reinterpret_cast<T *>(smem + prm.off_warp) + (size_t)warp * prm.warp_elems;
+    T *wq = wbase + prm.woff_q;
+    T *wsc = wbase + prm.woff_sc;
+    T *wsch = wbase + prm.woff_sch;
+    T *wframes = wbase + prm.woff_frames;
+    T *wtw = wbase + prm.woff_tw;
+    T *wquat = wbase + prm.woff_quat;
+    T *wfeat = wbase + prm.woff_feat;
+    const long long FTD = (long long)F * TD * D;
+
+    for (long long tile = (long long)blockIdx.x * n_warps + warp; tile < prm.n_tiles; tile += (long long)gridDim.x * n_warps) {
+        const long long n0 = tile * G;
+        const int g_live = (int)min((long long)G, prm.N - n0);
+        __syncwarp();
+        for (int i = lane; i < g_live * D; i += 32) {
+            const T th = prm.q[n0 * D + i];
+            T sn, cs;
+            Rl::sincos(th, &sn, &cs);
+            wq[i] = th;
+            wsc[2 * i] = sn; wsc[2 * i + 1] = cs;
+            if (ROT == SKB_ROT_XYZW) {
+                Rl::sincos(T(0.5) * th, &sn, &cs);
+                wsch[2 * i] = sn; wsch[2 * i + 1] = cs;
+            }
+        }
+        __syncwarp();
+        fk_phase<T, true, false>(lane, G, logG, prm.slots3, g_live, D, n_levels, nodeI, levelI, levelNodes, nodeF, wq, wsc,
+                                 wframes, fstride, wtw, tstride);
+
+        // ------------------------------------------------------------ phase 1q: node quaternions (XYZW)
+        if (ROT == SKB_ROT_XYZW) {
+            const int cfg = lane & (G - 1), slot = lane >> logG, slots = 32 >> logG;
+            const int ccfg = min(cfg, g_live - 1);
+            V4 *qd = reinterpret_cast<V4 *>(wquat + cfg * qstride);
+            for (int lv = 0; lv < n_levels; ++lv) {
+                const int lbeg = levelI[2 * lv], lcnt = levelI[2 * lv + 1];
+                for (int k0 = 0; k0 < lcnt; k0 += slots) {
+                    const int k = k0 + slot;
+                    if (k < lcnt) {
+                        const int node = levelNodes[lbeg + k];
+                        const int type = nodeI[4 * node], col = nodeI[4 * node + 1], par = nodeI[4 * node + 2];
+                        const V4 pre = nodeQ[node];
+                        T y[4] = {pre.x, pre.y, pre.z, pre.w};
+                        if (par >= 0) {
+                            const V4 pq = qd[par];
+                            const T a[4] = {pq.x, pq.y, pq.z, pq.w}, b[4] = {pre.x, pre.y, pre.z, pre.w};
+                            qmul<T>(a, b, y);
+                        }
+                        if (type == NODE_REVOLUTE) {
+                            const T sh = wsch[2 * (ccfg * D + col)], ch = wsch[2 * (ccfg * D + col) + 1];
+                            const T qz[4] = {T(0), T(0), sh, ch};
+                            T o[4];
+                            qmul<T>(y, qz, o);
+                            y[0] = o[0]; y[1] = o[1]; y[2] = o[2]; y[3] = o[3];
+                        }
+                        V4 out; out.x = y[0]; out.y = y[1]; out.z = y[2]; out.w = y[3];
+                        qd[node] = out;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ------------------------------------------------------------ phase 1c: feature poses -> values + Jacobian scalars
+        for (int i = lane; i < g_live * F; i += 32) {
+            const int c = i / F, f = i - c * F;
+            const int node = featI[f].x;
+            const T *ff = featF + f * 20;
+            const V4 *fr = reinterpret_cast<const V4 *>(wframes + c * fstride);
+            const V4 f0 = fr[3 * node], f1 = fr[3 * node + 1], f2 = fr[3 * node + 2];
+            const T px = f0.w + f0.x * ff[0] + f0.y * ff[1] + f0.z * ff[2];
+            const T py = f1.w + f1.x * ff[0] + f1.y * ff[1] + f1.z * ff[2];
+            const T pz = f2.w + f2.x * ff[0] + f2.y * ff[1] + f2.z * ff[2];
+            T *vr = prm.out_pts + ((n0 + c) * F + f) * TD;
+            T *fb = wfeat + (c * F + f) * featstride;
+            vr[0] = px; vr[1] = py; vr[2] = pz;
+            fb[0] = px; fb[1] = py; fb[2] = pz;
+            if (ROT == SKB_ROT_RPY) {
+                const T *Ro = ff + 4;      // feature rotation = R_node * R_off; URDF roll-pitch-yaw of it
+                const T r00 = f0.x * Ro[0] + f0.y * Ro[3] + f0.z * Ro[6];
+                const T r10 = f1.x * Ro[0] + f1.y * Ro[3] + f1.z * Ro[6];
+                const T r20 = f2.x * Ro[0] + f2.y * Ro[3] + f2.z * Ro[6];
+                const T r21 = f2.x * Ro[1] + f2.y * Ro[4] + f2.z * Ro[7];
+                const T r22 = f2.x * Ro[2] + f2.y * Ro[5] + f2.z * Ro[8];
+                const T roll = Rl::atan2(r21, r22);
+                const T sarg = -r20;
+                const T pitch = sarg <= T(-1) ? T(-1.5707963267948966) : (sarg >= T(1) ? T(1.5707963267948966) : Rl::asin(sarg));
+                const T yaw = Rl::atan2(r10, r00);
+                vr[3] = roll; vr[4] = pitch; vr[5] = yaw;
+                T sp, cp, sy, cy;
+                Rl::sincos(pitch, &sp, &cp);
+                Rl::sincos(yaw, &sy, &cy);
+                fb[3] = cy; fb[4] = sy; fb[5] = T(1) / cp; fb[6] = sp;
+            } else {
+                const V4 nq = reinterpret_cast<const V4 *>(wquat + c * qstride)[node];
+                const T a[4] = {nq.x, nq.y, nq.z, nq.w};
+                T qf[4];
+                qmul<T>(a, ff + 16, qf);
+                vr[3] = qf[0]; vr[4] = qf[1]; vr[5] = qf[2]; vr[6] = qf[3];
+                fb[3] = qf[0]; fb[4] = qf[1]; fb[5] = qf[2]; fb[6] = qf[3];
+            }
+        }
+        __syncwarp();
+        if (prm.out_jac == nullptr) continue;
+
+        // ------------------------------------------------------------ phase 2: lane per (configuration, column)
+        for (int i = lane; i < g_live * D; i += 32) {
+            const int c = i / D, d = i - c * D;
+            const T *tw = wtw + c * tstride + d * 8;
+            const V4 w = *reinterpret_cast<const V4 *>(tw), v = *reinterpret_cast<const V4 *>(tw + 4);
+            T *g = prm.out_jac + (n0 + c) * FTD + d;
+            for (int f = 0; f < F; ++f) {
+                const int4 fi = featI[f];
+                const unsigned long long am = ((unsigned long long)(unsigned)fi.z << 32) | (unsigned)fi.y;
+                const bool mine = (am >> d) & 1ull;
+                const T *fb = wfeat + (c * F + f) * featstride;
+                const T px = fb[0], py = fb[1], pz = fb[2], a0 = fb[3], a1 = fb[4], a2 = fb[5], a3 = fb[6];
+                const T wx = mine ? w.x : T(0), wy = mine ? w.y : T(0), wz = mine ? w.z : T(0);
+                const T vx = mine ? v.x : T(0), vy = mine ? v.y : T(0), vz = mine ? v.z : T(0);
+                T *row = g + (long long)f * TD * D;
+                row[0] = wy * pz - wz * py + vx;
+                row[D] = wz * px - wx * pz + vy;
+                row[2 * D] = wx * py - wy * px + vz;
+                if (ROT == SKB_ROT_RPY) {
+                    const T rr = (a0 * wx + a1 * wy) * a2;          // (cy wx + sy wy) / cp
+                    row[3 * D] = rr;
+                    row[4 * D] = a0 * wy - a1 * wx;
+                    row[5 * D] = wz + a3 * rr;
+                } else {
+                    row[3 * D] = T(0.5) * (a3 * wx + (wy * a2 - wz * a1));
+                    row[4 * D] = T(0.5) * (a3 * wy + (wz * a0 - wx * a2));
+                    row[5 * D] = T(0.5) * (a3 * wz + (wx * a1 - wy * a0));
+                    row[6 * D] = T(-0.5) * (wx * a0 + wy * a1 + wz * a2);
+                }
+            }
+        }
+    }
+}
+
+#define CUDA_OK(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+    } while (0)
+
+static int align_up(int x, int a) { return (x + a - 1) / a * a; }
+static int odd_quads(int words) { int q = (words + 3) / 4; if (q % 2 == 0) q += 1; return q * 4; }
+
+template <typename T, int ROT>
+static int launch_pose_inst(const skb_plan *p, const skb_pose_program *pp, const void *q, int64_t N, void *out_pts, void *out_jac,
+                            cudaStream_t stream) {
+    PoseParams<T> prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.I = reinterpret_cast<const int32_t *>(pp->dI);
+    prm.F = reinterpret_cast<const T *>(sizeof(T) == 4 ? pp->dF32 : pp->dF64);
+    prm.q = reinterpret_cast<const T *>(q);
+    prm.N = N;
+    prm.out_pts = reinterpret_cast<T *>(out_pts);
+    prm.out_jac = reinterpret_cast<T *>(out_jac);
+    prm.i_total = (int)pp->I.size();
+    prm.f_total = (int)pp->F.size();
+    const int D = p->D, F = p->F;
+    prm.D = D; prm.n_feat = F; prm.n_levels = pp->n_levels; prm.rot_type = ROT; prm.tdim = ROT == SKB_ROT_RPY ? 6 : 7;
+    prm.off_F = align_up(prm.i_total * 4, 16);
+    prm.off_warp = align_up(prm.off_F + prm.f_total * (int)sizeof(T), 128);
+    const int al = 16 / (int)sizeof(T);
+    prm.fstride = odd_quads(pp->n_nodes * 12);
+    prm.tstride = odd_quads(D * 8);
+    prm.qstride = ROT == SKB_ROT_XYZW ? odd_quads(pp->n_nodes * 4) : 0;
+    prm.featstride = 8;
+    const size_t smem_limit = 227 * 1024;
+    auto layout = [&](int g, int warps) {
+        int e = 0;
+        prm.woff_q = e;      e += align_up(g * D, al);
+        prm.woff_sc = e;     e += align_up(2 * g * D, al);
+        prm.woff_sch = e;    e += ROT == SKB_ROT_XYZW ? align_up(2 * g * D, al) : 0;
+        prm.woff_frames = e; e += g * prm.fstride;
+        prm.woff_tw = e;     e += g * prm.tstride;
+        prm.woff_quat = e;   e += g * prm.qstride;
+        prm.woff_feat = e;   e += align_up(g * F * prm.featstride, al);
+        prm.warp_elems = align_up(e, al);
+        return (size_t)prm.off_warp + (size_t)warps * prm.warp_elems * sizeof(T);
+    };
+    static const int cand[][2] = {{8, 8}, {4, 8}, {4, 6}, {4, 4}, {2, 8}, {2, 4}, {1, 8}, {1, 4}, {1, 2}, {1, 1}};
+    int G = 0, warps = 0;
+    for (int ctas = 3; ctas >= 1 && G == 0; --ctas)
+        for (auto &c : cand)
+            if ((layout(c[0], c[1]) + 1024) * ctas <= smem_limit) { G = c[0]; warps = c[1]; break; }
+    if (G == 0) return set_error("pose kernel: shared-memory footprint exceeds 227 KB");
+    const size_t smem = layout(G, warps);
+    prm.G = G;
+    prm.logG = 0;
+    while ((1 << prm.logG) < G) ++prm.logG;
+    prm.slots3 = 32 / (3 * G);
+    prm.n_tiles = (N + G - 1) / G;
+    auto kern = pose_kernel<T, ROT>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, sms = 148, dev = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    if (per_sm < 1) return set_error("pose kernel: zero occupancy");
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long want = (prm.n_tiles + warps - 1) / warps;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sms * per_sm));
+    kern<<<grid, warps * 32, smem, stream>>>(prm);
+    CUDA_OK(cudaGetLastError());
+    ++g_launch_count;
+    return 0;
+}
+
+int launch_pose(const skb_plan *p, const skb_pose_program *pp, int dtype, const void *q, int64_t N, void *out_pts, void *out_jac,
+                void *stream_) {
+    if (N <= 0) return 0;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    const bool rpy = p->rot_type == SKB_ROT_RPY;
+    if (dtype == SKB_F32)
+        return rpy ? launch_pose_inst<float, SKB_ROT_RPY>(p, pp, q, N, out_pts, out_jac, stream)
+                   : launch_pose_inst<float, SKB_ROT_XYZW>(p, pp, q, N, out_pts, out_jac, stream);
+    if (dtype == SKB_F64)
+        return rpy ? launch_pose_inst<double, SKB_ROT_RPY>(p, pp, q, N, out_pts, out_jac, stream)
+                   : launch_pose_inst<double, SKB_ROT_XYZW>(p, pp, q, N, out_pts, out_jac, stream);
+    return set_error("bad dtype");
+}
+
+}  // namespace skb
