@@ -232,27 +232,32 @@ __device__ __forceinline__ void fk_phase(const int lane, const int G, const int 
     const int row = lane % 3, t = lane / 3;
     const int cfg = t & (G - 1), slot = t >> logG;
     const bool act = slot < slots3;
-    const int base = lane - row;
-    const int src1 = base + (row == 2 ? 0 : row + 1), src2 = base + (row == 0 ? 2 : row - 1);
+    // lane-constant quantities of the walk, made opaque so they are computed once per tile instead of being
+    // rematerialised inside the level loop
+    int src1 = lane - row + (row == 2 ? 0 : row + 1), src2 = lane - row + (row == 0 ? 2 : row - 1);
+    asm volatile("" : "+r"(src1), "+r"(src2));
     const int ccfg = min(cfg, g_live - 1);          // dead configurations of a ragged last tile recompute a live one
     const T *myq = wq + ccfg * D;
-    const T *mysc = wsc + 2 * ccfg * D;
-    V4 *fr = reinterpret_cast<V4 *>(wframes + cfg * fstride);
-    T *tw = wtw + cfg * tstride;
+    struct alignas(2 * sizeof(T)) SC { T s, c; };
+    const SC *mysc = reinterpret_cast<const SC *>(wsc + 2 * ccfg * D);
+    V4 *frr = reinterpret_cast<V4 *>(wframes + cfg * fstride) + row;          // this lane's row of every node frame
+    const V4 *nodeFr = nodeF + row;
+    T *twr = wtw + cfg * tstride + (PAIR ? 2 * row : row);
+    const int4 *nodeI4 = reinterpret_cast<const int4 *>(nodeI);
+    const int2 *levelI2 = reinterpret_cast<const int2 *>(levelI);
     for (int lv = 0; lv < n_levels; ++lv) {
-        const int2 lrec = reinterpret_cast<const int2 *>(levelI)[lv];       // {first index into levelNodes, count}
+        const int2 lrec = levelI2[lv];                                      // {first index into levelNodes, count}
         const int lbeg = lrec.x, lcnt = lrec.y;
         for (int k0 = 0; k0 < lcnt; k0 += slots3) {
             const int k = k0 + slot;
             const bool on = act && k < lcnt;
             const int node = levelNodes[lbeg + (on ? k : 0)];
-            const int4 nrec = reinterpret_cast<const int4 *>(nodeI)[node];  // {type, column, parent, -}
+            const int4 nrec = nodeI4[node];                                 // {type, column, parent, -}
             const int type = nrec.x, col = nrec.y, par = nrec.z;
-            V4 y;
-            if (par < 0) y = nodeF[3 * node + row];
-            else {
+            V4 y = nodeFr[3 * node];
+            if (par >= 0) {
                 const V4 c0 = nodeF[3 * node], c1 = nodeF[3 * node + 1], c2 = nodeF[3 * node + 2];
-                const V4 P = fr[3 * par + row];
+                const V4 P = frr[3 * par];
                 y.x = P.x * c0.x + P.y * c1.x + P.z * c2.x;
                 y.y = P.x * c0.y + P.y * c1.y + P.z * c2.y;
                 y.z = P.x * c0.z + P.y * c1.z + P.z * c2.z;
@@ -263,8 +268,7 @@ __device__ __forceinline__ void fk_phase(const int lane, const int G, const int 
             const T w1 = __shfl_sync(0xffffffffu, y.z, src1), w2 = __shfl_sync(0xffffffffu, y.z, src2);
             T wr = T(0), vr = T(0);
             if (type == NODE_REVOLUTE) {
-                struct alignas(2 * sizeof(T)) SC { T s, c; };
-                const SC sc = reinterpret_cast<const SC *>(mysc)[col];
+                const SC sc = mysc[col];
                 const T s = sc.s, c = sc.c;
                 wr = y.z;
                 vr = o1 * w2 - o2 * w1;                       // v = o x omega, component `row`
@@ -275,14 +279,11 @@ __device__ __forceinline__ void fk_phase(const int lane, const int G, const int 
                 y.w += myq[col] * y.z;
             }
             if (on) {
-                fr[3 * node + row] = y;
+                frr[3 * node] = y;
                 if (WITH_JAC && col >= 0) {
-                    if (PAIR) {
-                        T *t2 = tw + (col >> 1) * 12 + (col & 1);
-                        t2[2 * row] = wr; t2[6 + 2 * row] = vr;
-                    } else {
-                        tw[col * 8 + row] = wr; tw[col * 8 + 4 + row] = vr;
-                    }
+                    T *t2 = PAIR ? twr + (col >> 1) * 12 + (col & 1) : twr + col * 8;
+                    t2[0] = wr;
+                    t2[PAIR ? 6 : 4] = vr;
                 }
             }
         }
