@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <string>
 
@@ -259,11 +260,26 @@ static int launch_pose_inst(const skb_plan *p, const skb_pose_program *pp, const
         prm.warp_elems = align_up(e, al);
         return (size_t)prm.off_warp + (size_t)warps * prm.warp_elems * sizeof(T);
     };
-    static const int cand[][2] = {{8, 8}, {4, 8}, {4, 6}, {4, 4}, {2, 8}, {2, 4}, {1, 8}, {1, 4}, {1, 2}, {1, 1}};
-    int G = 0, warps = 0;
-    for (int ctas = 3; ctas >= 1 && G == 0; --ctas)
-        for (auto &c : cand)
-            if ((layout(c[0], c[1]) + 1024) * ctas <= smem_limit) { G = c[0]; warps = c[1]; break; }
+    // (G, warps per CTA) by the same issue-slot score as the step kernel: resident warps^0.75 / slots per configuration
+    auto kern = pose_kernel<T, ROT>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+    static const int cand[][2] = {{8, 8}, {8, 4}, {4, 8}, {4, 6}, {4, 4}, {2, 8}, {2, 6}, {2, 4}, {1, 8}, {1, 4}, {1, 2}, {1, 1}};
+    auto fk_slots = [&](int g) {
+        const int s3 = 32 / (3 * g);
+        double it = 0;
+        for (int lv = 0; lv < pp->n_levels; ++lv) it += (pp->I[pp->I[E_LEVEL_I] + 2 * lv + 1] + s3 - 1) / s3;
+        return (ROT == SKB_ROT_XYZW ? 130.0 : 90.0) * it / g;
+    };
+    int G = 0, warps = 0, per_sm = 0;
+    double best_score = -1.0;
+    for (auto &c : cand) {
+        const size_t sm = layout(c[0], c[1]);
+        if (sm > smem_limit) continue;
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c[1] * 32, sm) != cudaSuccess || occ < 1) continue;
+        const double score = std::pow((double)std::min(c[1] * occ, 48), 0.75) / (fk_slots(c[0]) + 10.0 * F * (ROT == SKB_ROT_RPY ? 6 : 7) * ((D + 31) / 32));
+        if (score > best_score * 1.0001) { best_score = score; G = c[0]; warps = c[1]; per_sm = occ; }
+    }
     if (G == 0) return set_error("pose kernel: shared-memory footprint exceeds 227 KB");
     const size_t smem = layout(G, warps);
     prm.G = G;
@@ -271,11 +287,7 @@ static int launch_pose_inst(const skb_plan *p, const skb_pose_program *pp, const
     while ((1 << prm.logG) < G) ++prm.logG;
     prm.slots3 = 32 / (3 * G);
     prm.n_tiles = (N + G - 1) / G;
-    auto kern = pose_kernel<T, ROT>;
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0, sms = 148, dev = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
-    if (per_sm < 1) return set_error("pose kernel: zero occupancy");
+    int sms = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long want = (prm.n_tiles + warps - 1) / warps;

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -503,15 +504,34 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
         prm.warp_elems = align_up(e, 4);
         return (size_t)prm.off_warp + (size_t)warps * prm.warp_elems * sizeof(float);
     };
-    // configurations per tile G (more lanes busy in the tree walk) against warps per CTA, at SKB_S2_BLOCKS CTAs per SM
-    static const int cand[][2] = {{8, 8}, {4, 8}, {4, 7}, {4, 6}, {2, 8}, {2, 6}, {1, 8}, {1, 6}, {1, 4}, {1, 2}, {1, 1}};
-    int G = 0, warps = 0;
-    for (int ctas = p->tune_ctas > 0 ? p->tune_ctas : SKB_S2_BLOCKS; ctas >= 1 && G == 0; --ctas)
-        for (auto &c : cand) {
-            if (p->tune_chunk > 0 && c[0] != p->tune_chunk) continue;
-            if (p->tune_warps > 0 && c[1] != p->tune_warps) continue;
-            if ((layout(c[0], c[1]) + 1024) * ctas <= smem_limit) { G = c[0]; warps = c[1]; break; }
-        }
+    // Configurations per tile G against warps per CTA and CTAs per SM.  A larger G fills more lanes of the tree walk
+    // (three lanes per node, `slots3` nodes of a level at once) but costs shared memory, i.e. resident warps.  Every
+    // candidate is scored with a small issue-slot model:  (resident warps)^0.75 / (FK slots + phase-2 slots per
+    // configuration);  the occupancy comes from the runtime (registers and shared memory).
+    auto kern = s2_kernel<KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+    static const int cand[][2] = {{8, 8}, {8, 6}, {8, 4}, {4, 8}, {4, 7}, {4, 6}, {4, 4}, {2, 8}, {2, 6}, {2, 4}, {1, 8}, {1, 6}, {1, 4}, {1, 2}, {1, 1}};
+    int halves = 0;
+    for (auto &st : sp->steps) halves += st.cntB > 0 ? 2 : 1;
+    auto fk_slots = [&](int g) {
+        const int s3 = 32 / (3 * g);
+        double it = 0;
+        for (int lv = 0; lv < sp->n_levels; ++lv) it += (sp->I[sp->I[Q_LEVEL_I] + 2 * lv + 1] + s3 - 1) / s3;
+        return 90.0 * it / g;
+    };
+    int G = 0, warps = 0, per_sm = 0;
+    double best_score = -1.0;
+    for (auto &c : cand) {
+        if (p->tune_chunk > 0 && c[0] != p->tune_chunk) continue;
+        if (p->tune_warps > 0 && c[1] != p->tune_warps) continue;
+        const size_t sm = layout(c[0], c[1]);
+        if (sm > smem_limit) continue;
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c[1] * 32, sm) != cudaSuccess || occ < 1) continue;
+        if (p->tune_ctas > 0) occ = std::min(occ, p->tune_ctas);
+        const double score = std::pow((double)std::min(c[1] * occ, 48), 0.75) / (fk_slots(c[0]) + (RED ? 40.0 : 150.0) * halves);
+        if (score > best_score * 1.0001) { best_score = score; G = c[0]; warps = c[1]; per_sm = occ; }
+    }
     if (G == 0) return set_error("step kernel: shared-memory footprint exceeds 227 KB");
     const size_t smem = layout(G, warps);
     prm.G = G;
@@ -519,12 +539,6 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
     while ((1 << prm.logG) < G) ++prm.logG;
     prm.slots3 = 32 / (3 * G);
     prm.n_tiles = (N + G - 1) / G;
-    auto kern = s2_kernel<KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>;
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
-    if (per_sm < 1) return set_error("step kernel: zero occupancy");
-    if (p->tune_ctas > 0) per_sm = std::min(per_sm, p->tune_ctas);
     const long long want = (prm.n_tiles + warps - 1) / warps;
     const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count_cached() * per_sm));
     kern<<<grid, warps * 32, smem, stream>>>(prm);

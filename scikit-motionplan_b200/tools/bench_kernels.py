@@ -91,6 +91,30 @@ def workloads():
             return (lambda: const.evaluate(qs, True)), n, 4 * (D + 1 + D), f"PR2 dual arm vs 128^3 grid, closest + Jacobian, N={n}"
         const = CollFreeConst(colkin, grid, pr2)
         return (lambda: const.is_valid_batch(qs)), n, 4 * D + 1, f"PR2 dual arm vs 128^3 grid, validity bytes, N={n}"
+    def cfg3_f64():
+        pr2, colkin, grid = bench.make_problem()
+        n = 400_000
+        qs = device_samples(colkin, n, 3).double()
+        S, D = colkin.n_feature, colkin.dim_cspace
+        const = CollFreeConst(colkin, grid, pr2)
+        return (lambda: const.evaluate(qs, True)), n, 8 * (D + S + S * D), f"PR2 dual arm vs 128^3 grid, all + Jacobian, fp64, N={n}"
+    W["cfg3_f64"] = cfg3_f64
+
+    def cfg2_f64():
+        fetch = Fetch(); fetch.reset_pose()
+        const = FetchConfig().get_pairwise_selcol_consts(fetch)
+        n = 200_000
+        qs = device_samples(const.colkin, n, 8).double()
+        P, D = len(const.check_sphere_id_pairs), const.colkin.dim_cspace
+        return (lambda: const.evaluate(qs, True)), n, 8 * (D + P + P * D), f"Fetch pairwise all pairs + Jacobian, fp64, N={n}"
+    W["cfg2_f64"] = cfg2_f64
+
+    def com(n=1_000_000):
+        jaxon = Jaxon(); jaxon.reset_manip_pose()
+        const = JaxonConfig().get_com_stability_const(jaxon, Box([0.2, 0.6, 5.0]), ["RARM_LINK7", "LARM_LINK7"], [5.0, 5.0])
+        qs = (torch.rand((n, 37), device="cuda", generator=torch.Generator("cuda").manual_seed(2)) - 0.5) * 0.6
+        return (lambda: const.evaluate(qs, True)), n, 4 * (37 + 1 + 37), f"JAXON COMStabilityConst (40 weighted points) + Jacobian, N={n}"
+    W["cfg5_com"] = com
     W["cfg3"] = lambda: cfg3("all")
     W["cfg3_closest"] = lambda: cfg3("closest")
     W["cfg3_valid"] = lambda: cfg3("valid")
