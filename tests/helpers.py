@@ -58,3 +58,26 @@ def numpy_fk_positions(solver, q_full_angles, base_pose, link_ids):
         return T
 
     return np.array([world(l)[:3, 3] for l in link_ids]), [world(l)[:3, :3] for l in link_ids]
+
+
+def random_urdf(rng, n_links: int, path) -> str:
+    """A random kinematic tree written as URDF: random parents (branching), revolute / prismatic / fixed joints,
+    arbitrary (non axis-aligned) joint axes, origins with full xyz + rpy, random masses.  Returns the file path."""
+    lines = ['<robot name="fuzz">']
+    for i in range(n_links):
+        m = float(rng.uniform(0.2, 3.0)) if rng.uniform() < 0.8 else 0.0
+        c = rng.uniform(-0.1, 0.1, 3)
+        lines.append(f'  <link name="L{i}"><inertial><origin xyz="{c[0]} {c[1]} {c[2]}" rpy="0 0 0"/><mass value="{m}"/></inertial></link>')
+    for i in range(1, n_links):
+        par = int(rng.integers(max(0, i - 4), i))
+        kind = rng.choice(["revolute", "continuous", "prismatic", "fixed"], p=[0.5, 0.15, 0.15, 0.2])
+        xyz, rpy = rng.uniform(-0.3, 0.3, 3), rng.uniform(-np.pi, np.pi, 3)
+        ax = rng.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        lim = '' if kind in ("continuous", "fixed") else f'<limit lower="{-rng.uniform(0.5, 2.5)}" upper="{rng.uniform(0.5, 2.5)}" effort="1" velocity="1"/>'
+        lines.append(f'  <joint name="J{i}" type="{kind}"><parent link="L{par}"/><child link="L{i}"/>'
+                     f'<origin xyz="{xyz[0]} {xyz[1]} {xyz[2]}" rpy="{rpy[0]} {rpy[1]} {rpy[2]}"/>'
+                     f'<axis xyz="{ax[0]} {ax[1]} {ax[2]}"/>{lim}</joint>')
+    lines.append('</robot>')
+    path.write_text("\n".join(lines))
+    return str(path)
