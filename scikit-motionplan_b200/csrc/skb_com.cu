@@ -38,6 +38,7 @@ struct ComParams {
     T *out_jac;
     int i_total, f_total;
     int off_F, off_prims, off_warp, warp_elems;
+    int off_lv, n_nodes;
     int woff_q, woff_sc, woff_frames, woff_tw, woff_prefix;
     int fstride, tstride;
     int G, logG, slots3;
@@ -65,9 +66,10 @@ __global__ void __launch_bounds__(256) com_kernel(const ComParams<T> prm) {
 
     const int D = prm.D, n_points = prm.n_points, n_levels = prm.n_levels;
     const int fstride = prm.fstride, tstride = prm.tstride, G = prm.G, logG = prm.logG;
-    const int32_t *nodeI = sI + sI[C_NODE_I];
     const int32_t *levelI = sI + sI[C_LEVEL_I];
-    const int32_t *levelNodes = sI + sI[C_LEVELNODE_I];
+    int4 *lvrec = reinterpret_cast<int4 *>(smem + prm.off_lv);
+    build_level_records(lvrec, sI + sI[C_NODE_I], sI + sI[C_LEVELNODE_I], prm.n_nodes);
+    __syncthreads();
     const int32_t *ptNode = sI + sI[C_PTNODE_I];
     const int2 *colRange = reinterpret_cast<const int2 *>(sI + sI[C_COLRANGE_I]);
     const V4 *nodeF = reinterpret_cast<const V4 *>(sF + sI[C_NODE_F]);
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(256) com_kernel(const ComParams<T> prm) {
             wsc[2 * i] = sn; wsc[2 * i + 1] = cs;
         }
         __syncwarp();
-        fk_phase<T, true, false>(lane, G, logG, prm.slots3, g_live, D, n_levels, nodeI, levelI, levelNodes, nodeF, wq, wsc,
+        fk_phase<T, true, false>(lane, G, logG, prm.slots3, g_live, D, n_levels, lvrec, levelI, nodeF, wq, wsc,
                                  wframes, fstride, wtw, tstride);
 
         for (int c = 0; c < g_live; ++c) {
@@ -188,7 +190,9 @@ static int launch_com_t(const skb_plan *p, const skb_com_program *cp, const void
     prm.D = D; prm.n_points = cp->n_points; prm.n_levels = cp->n_levels;
     prm.off_F = align_up(prm.i_total * 4, 16);
     prm.off_prims = align_up(prm.off_F + prm.f_total * (int)sizeof(T), 16);
-    prm.off_warp = align_up(prm.off_prims + std::max(1, n_prims) * (int)sizeof(DevPrim<T>), 128);
+    prm.off_lv = align_up(prm.off_prims + std::max(1, n_prims) * (int)sizeof(DevPrim<T>), 16);
+    prm.n_nodes = cp->n_nodes;
+    prm.off_warp = align_up(prm.off_lv + cp->n_nodes * 16, 128);
     const int al = 16 / (int)sizeof(T);
     prm.fstride = odd_quads(cp->n_nodes * 12);     // elements of T per configuration
     prm.tstride = odd_quads(D * 8);

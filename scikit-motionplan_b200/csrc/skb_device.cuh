@@ -223,10 +223,21 @@ template <typename T> struct alignas(16) Vec4 { T x, y, z, w; };
 // `slots3` = 32 / (3 G) nodes of a level are processed at once (G <= 8).  Frames go to `wframes` (rows of 4, 12 per node),
 // twists to `wtw` in the scalar layout [wx wy wz . | vx vy vz .] per column or, PAIR, component-interleaved per column
 // pair [wx_j wx_j1 wy_j wy_j1 | wz_j wz_j1 vx_j vx_j1 | vy_j vy_j1 vz_j vz_j1].
+// Per-CTA derived table for the walk, built once in the kernel prologue: entry e of the level-ordered node list ->
+// {type, column, 3 * parent (-1 for the world node), 3 * node}, so the level loop does one 16-byte load per node instead
+// of chasing levelNodes -> node record and re-deriving the frame row indices.
+__device__ __forceinline__ void build_level_records(int4 *lvrec, const int32_t *nodeI, const int32_t *levelNodes, int n_nodes) {
+    for (int e = threadIdx.x; e < n_nodes; e += blockDim.x) {
+        const int node = levelNodes[e];
+        const int4 nd = reinterpret_cast<const int4 *>(nodeI)[node];
+        lvrec[e] = make_int4(nd.x, nd.y, nd.z < 0 ? -1 : 3 * nd.z, 3 * node);
+    }
+}
+
 template <typename T, bool WITH_JAC, bool PAIR>
 __device__ __forceinline__ void fk_phase(const int lane, const int G, const int logG, const int slots3, const int g_live,
-                                         const int D, const int n_levels, const int32_t *nodeI, const int32_t *levelI,
-                                         const int32_t *levelNodes, const Vec4<T> *nodeF, const T *wq, const T *wsc,
+                                         const int D, const int n_levels, const int4 *lvrec, const int32_t *levelI,
+                                         const Vec4<T> *nodeF, const T *wq, const T *wsc,
                                          T *wframes, const int fstride, T *wtw, const int tstride) {
     using V4 = Vec4<T>;
     const int row = lane % 3, t = lane / 3;
@@ -243,21 +254,19 @@ __device__ __forceinline__ void fk_phase(const int lane, const int G, const int 
     V4 *frr = reinterpret_cast<V4 *>(wframes + cfg * fstride) + row;          // this lane's row of every node frame
     const V4 *nodeFr = nodeF + row;
     T *twr = wtw + cfg * tstride + (PAIR ? 2 * row : row);
-    const int4 *nodeI4 = reinterpret_cast<const int4 *>(nodeI);
     const int2 *levelI2 = reinterpret_cast<const int2 *>(levelI);
     for (int lv = 0; lv < n_levels; ++lv) {
-        const int2 lrec = levelI2[lv];                                      // {first index into levelNodes, count}
+        const int2 lrec = levelI2[lv];                                      // {first entry of the level, count}
         const int lbeg = lrec.x, lcnt = lrec.y;
         for (int k0 = 0; k0 < lcnt; k0 += slots3) {
             const int k = k0 + slot;
             const bool on = act && k < lcnt;
-            const int node = levelNodes[lbeg + (on ? k : 0)];
-            const int4 nrec = nodeI4[node];                                 // {type, column, parent, -}
-            const int type = nrec.x, col = nrec.y, par = nrec.z;
-            V4 y = nodeFr[3 * node];
-            if (par >= 0) {
-                const V4 c0 = nodeF[3 * node], c1 = nodeF[3 * node + 1], c2 = nodeF[3 * node + 2];
-                const V4 P = frr[3 * par];
+            const int4 rec = lvrec[lbeg + (on ? k : 0)];                    // {type, column, 3 parent, 3 node}
+            const int type = rec.x, col = rec.y, par3 = rec.z, node3 = rec.w;
+            V4 y = nodeFr[node3];
+            if (par3 >= 0) {
+                const V4 c0 = nodeF[node3], c1 = nodeF[node3 + 1], c2 = nodeF[node3 + 2];
+                const V4 P = frr[par3];
                 y.x = P.x * c0.x + P.y * c1.x + P.z * c2.x;
                 y.y = P.x * c0.y + P.y * c1.y + P.z * c2.y;
                 y.z = P.x * c0.z + P.y * c1.z + P.z * c2.z;
@@ -279,7 +288,7 @@ __device__ __forceinline__ void fk_phase(const int lane, const int G, const int 
                 y.w += myq[col] * y.z;
             }
             if (on) {
-                frr[3 * node] = y;
+                frr[node3] = y;
                 if (WITH_JAC && col >= 0) {
                     T *t2 = PAIR ? twr + (col >> 1) * 12 + (col & 1) : twr + col * 8;
                     t2[0] = wr;

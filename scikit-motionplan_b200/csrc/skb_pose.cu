@@ -39,6 +39,7 @@ struct PoseParams {
     T *out_jac;
     int i_total, f_total;
     int off_F, off_warp, warp_elems;
+    int off_lv, n_nodes;
     int woff_q, woff_sc, woff_sch, woff_frames, woff_tw, woff_quat, woff_feat;
     int fstride, tstride, qstride, featstride;
     int G, logG, slots3;
@@ -71,6 +72,9 @@ __global__ void __launch_bounds__(256) pose_kernel(const PoseParams<T> prm) {
     const int32_t *nodeI = sI + sI[E_NODE_I];
     const int32_t *levelI = sI + sI[E_LEVEL_I];
     const int32_t *levelNodes = sI + sI[E_LEVELNODE_I];
+    int4 *lvrec = reinterpret_cast<int4 *>(smem + prm.off_lv);
+    build_level_records(lvrec, nodeI, levelNodes, prm.n_nodes);
+    __syncthreads();
     const int4 *featI = reinterpret_cast<const int4 *>(sI + sI[E_FEAT_I]);
     const V4 *nodeF = reinterpret_cast<const V4 *>(sF + sI[E_NODE_F]);
     const V4 *nodeQ = reinterpret_cast<const V4 *>(sF + sI[E_NODEQ_F]);
@@ -102,7 +106,7 @@ __global__ void __launch_bounds__(256) pose_kernel(const PoseParams<T> prm) {
             }
         }
         __syncwarp();
-        fk_phase<T, true, false>(lane, G, logG, prm.slots3, g_live, D, n_levels, nodeI, levelI, levelNodes, nodeF, wq, wsc,
+        fk_phase<T, true, false>(lane, G, logG, prm.slots3, g_live, D, n_levels, lvrec, levelI, nodeF, wq, wsc,
                                  wframes, fstride, wtw, tstride);
 
         // ------------------------------------------------------------ phase 1q: node quaternions (XYZW)
@@ -241,7 +245,9 @@ static int launch_pose_inst(const skb_plan *p, const skb_pose_program *pp, const
     const int D = p->D, F = p->F;
     prm.D = D; prm.n_feat = F; prm.n_levels = pp->n_levels; prm.rot_type = ROT; prm.tdim = ROT == SKB_ROT_RPY ? 6 : 7;
     prm.off_F = align_up(prm.i_total * 4, 16);
-    prm.off_warp = align_up(prm.off_F + prm.f_total * (int)sizeof(T), 128);
+    prm.off_lv = align_up(prm.off_F + prm.f_total * (int)sizeof(T), 16);
+    prm.n_nodes = pp->n_nodes;
+    prm.off_warp = align_up(prm.off_lv + pp->n_nodes * 16, 128);
     const int al = 16 / (int)sizeof(T);
     prm.fstride = odd_quads(pp->n_nodes * 12);
     prm.tstride = odd_quads(D * 8);

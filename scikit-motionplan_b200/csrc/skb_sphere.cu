@@ -56,6 +56,7 @@ struct SphereParams {
     uint8_t *out_valid;
     int i_total, f_total;
     int off_F, off_prims, off_warp, warp_elems;   // bytes, bytes, bytes, elements of T per warp
+    int off_lv, n_nodes;                          // per-CTA level-record table (bytes), node count
     int woff_q, woff_sc, woff_frames, woff_tw, woff_stage; // element offsets inside a warp slab
     int fstride, tstride;                         // elements of T per configuration: frames, twists
     int G, logG, slots3;                          // configurations per tile (power of two <= 8), nodes per FK pass
@@ -155,9 +156,10 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
 
     const int n_levels = prm.n_levels, n_rounds = prm.n_rounds, D = prm.D, S = prm.S;
     const int fstride = prm.fstride, tstride = prm.tstride;
-    const int32_t *nodeI = sI + sI[S_NODE_I];
     const int32_t *levelI = sI + sI[S_LEVEL_I];
-    const int32_t *levelNodes = sI + sI[S_LEVELNODE_I];
+    int4 *lvrec = reinterpret_cast<int4 *>(smem + prm.off_lv);
+    build_level_records(lvrec, sI + sI[S_NODE_I], sI + sI[S_LEVELNODE_I], prm.n_nodes);
+    __syncthreads();
     const int4 *roundI = reinterpret_cast<const int4 *>(sI + sI[S_ROUND_I]);
     const int4 *tabB = reinterpret_cast<const int4 *>(sI + sI[S_TABB_I]);
     const V4 *nodeF = reinterpret_cast<const V4 *>(sF + sI[S_NODE_F]);
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
         __syncwarp();
 
         // ------------------------------------------------------------ phase 1: frames + twists (three lanes per node)
-        fk_phase<T, WITH_JAC, PAIR>(lane, G, logG, prm.slots3, g_live, D, n_levels, nodeI, levelI, levelNodes, nodeF, wq, wsc,
+        fk_phase<T, WITH_JAC, PAIR>(lane, G, logG, prm.slots3, g_live, D, n_levels, lvrec, levelI, nodeF, wq, wsc,
                                     wframes, fstride, wtw, tstride);
 
         // ------------------------------------------------------------ phase 2: one lane per sphere
@@ -474,7 +476,9 @@ static int launch_sphere_inst(const skb_plan *p, const skb_sphere_program *sp, c
     const bool stage = WITH_JAC && !CLOSEST;
     prm.off_F = align_up(prm.i_total * 4, 16);
     prm.off_prims = align_up(prm.off_F + prm.f_total * (int)sizeof(T), 16);
-    prm.off_warp = align_up(prm.off_prims + ((KIND == KIND_COLLFREE && SDFK == SDF_UNION) ? n_prims : 0) * (int)sizeof(DevPrim<T>), 128);
+    prm.off_lv = align_up(prm.off_prims + ((KIND == KIND_COLLFREE && SDFK == SDF_UNION) ? n_prims : 0) * (int)sizeof(DevPrim<T>), 16);
+    prm.n_nodes = sp->n_nodes;
+    prm.off_warp = align_up(prm.off_lv + sp->n_nodes * 16, 128);
     const int al = 16 / (int)sizeof(T);
     const int PER = al;
     // every round block [s0*ROWS*D, +cnt*ROWS*D) of every configuration must be 16-byte aligned for vector copy-out

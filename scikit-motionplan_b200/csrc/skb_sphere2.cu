@@ -63,6 +63,7 @@ struct S2Params {
     uint8_t *out_valid;
     int i_total, f_total;
     int off_F, off_prims, off_warp, warp_elems;                       // bytes, bytes, bytes, floats per warp
+    int off_lv, n_nodes;                                              // per-CTA level-record table (bytes), node count
     int woff_q, woff_sc, woff_frames, woff_tw, woff_cen, woff_stage;  // float offsets inside a warp slab
     int fstride, tstride, cstride;                                    // floats per configuration: frames, twists, centres
     int G, logG, slots3;
@@ -145,9 +146,10 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
 
     const int n_levels = prm.n_levels, n_steps = prm.n_steps, D = prm.D, NP = prm.NP, R = prm.R;
     const int fstride = prm.fstride, tstride = prm.tstride, cstride = prm.cstride;
-    const int32_t *nodeI = sI + sI[Q_NODE_I];
     const int32_t *levelI = sI + sI[Q_LEVEL_I];
-    const int32_t *levelNodes = sI + sI[Q_LEVELNODE_I];
+    int4 *lvrec = reinterpret_cast<int4 *>(smem + prm.off_lv);
+    build_level_records(lvrec, sI + sI[Q_NODE_I], sI + sI[Q_LEVELNODE_I], prm.n_nodes);
+    __syncthreads();
     const int4 *tabB = reinterpret_cast<const int4 *>(sI + sI[Q_TABB_I]);
     const int4 *tabC = reinterpret_cast<const int4 *>(sI + sI[Q_TABC_I]);
     const int32_t *cenNode = sI + sI[Q_CENNODE_I];
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
         __syncwarp();
 
         // ------------------------------------------------------------ phase 1: frames + twists
-        fk_phase<float, JAC, true>(lane, G, logG, prm.slots3, g_live, D, n_levels, nodeI, levelI, levelNodes, nodeF, wq, wsc,
+        fk_phase<float, JAC, true>(lane, G, logG, prm.slots3, g_live, D, n_levels, lvrec, levelI, nodeF, wq, wsc,
                                     wframes, fstride, wtw, tstride);
 
         // ------------------------------------------------------------ phase 1b: sphere centres (pairwise)
@@ -488,7 +490,9 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
     }
     prm.off_F = align_up(prm.i_total * 4, 16);
     prm.off_prims = align_up(prm.off_F + prm.f_total * 4, 16);
-    prm.off_warp = align_up(prm.off_prims + ((KIND == KIND_COLLFREE && SDFK == SDF_UNION) ? n_prims : 0) * (int)sizeof(DevPrim<float>), 128);
+    prm.off_lv = align_up(prm.off_prims + ((KIND == KIND_COLLFREE && SDFK == SDF_UNION) ? n_prims : 0) * (int)sizeof(DevPrim<float>), 16);
+    prm.n_nodes = sp->n_nodes;
+    prm.off_warp = align_up(prm.off_lv + sp->n_nodes * 16, 128);
     prm.fstride = sp->frame_stride;
     prm.tstride = odd_quads(NP * 12);
     prm.cstride = KIND == KIND_PAIRWISE ? odd_quads(4 * sp->n_cen) : 0;
