@@ -155,11 +155,40 @@ class IneqCompositeConst(AbstractIneqConst, _CompositeConst[AbstractIneqConst]):
         return True
 
     def is_valid_batch(self, qs):
-        ok = None
+        """``is_valid`` for every row: invalid iff some member has a value < 0 (:167-176).  Like the reference's loop it
+        short-circuits in ``const_list`` order -- rows already rejected are not shown to the later members -- and the
+        collision members reduce to their row minimum on the GPU (one float per configuration leaves the kernel)."""
+        def bad_rows(const, q):
+            if hasattr(const, "_min_values"):
+                m = const._min_values(q)
+                return (m < 0.0).reshape(-1)
+            values, _ = const.evaluate(q, False)
+            return (values < 0.0).any(dim=1) if _is_torch(values) else (values < 0.0).any(axis=1)
+
+        if _is_torch(qs):
+            ok = torch.ones(qs.shape[0], dtype=torch.bool, device=qs.device)
+            alive = None                                    # indices of the rows still valid (None = all)
+            for const in self.const_list:
+                sub = qs if alive is None else qs[alive]
+                if sub.shape[0] == 0:
+                    break
+                bad = bad_rows(const, sub)
+                bad = torch.as_tensor(bad, device=qs.device)
+                if alive is None:
+                    ok &= ~bad
+                    alive = torch.nonzero(ok, as_tuple=False).reshape(-1)
+                else:
+                    ok[alive[bad]] = False
+                    alive = alive[~bad]
+            return ok
+        qs = np.asarray(qs)
+        ok = np.ones(len(qs), dtype=bool)
         for const in self.const_list:
-            values, _ = const.evaluate(qs, False)
-            good = ~((values < 0.0).any(axis=1)) if not _is_torch(values) else ~((values < 0.0).any(dim=1))
-            ok = good if ok is None else (ok & good)
+            alive = np.nonzero(ok)[0]
+            if len(alive) == 0:
+                break
+            bad = np.asarray(bad_rows(const, qs[alive]))
+            ok[alive[bad]] = False
         return ok
 
 
@@ -258,6 +287,17 @@ class CollFreeConst(AbstractIneqConst):
     def _evaluate(self, qs, with_jacobian: bool):
         b, vals, jac, _ = self._run(qs, True, with_jacobian, False)
         return b.out(vals), (b.out(jac) if with_jacobian else self.dummy_jacobian())
+
+    def _min_values(self, qs):
+        """Row minimum of the values, (N, 1): the closest-mode kernel without Jacobian (what a composite needs)."""
+        if not self.reflect_robot_flag:
+            raise RuntimeError("{}: you need to call reflect_skrobot_model beforehand".format(type(self).__name__))
+        saved, self.only_closest_feature = self.only_closest_feature, True
+        try:
+            b, vals, _, _ = self._run(qs, True, False, False)
+        finally:
+            self.only_closest_feature = saved
+        return b.out(vals)
 
     def is_valid_batch(self, qs):
         """Validity bytes straight from the kernel (1 byte per configuration leaves the GPU)."""
@@ -475,6 +515,8 @@ class PairWiseSelfCollFreeConst(AbstractIneqConst):
     def _evaluate(self, qs, with_jacobian: bool):
         b, vals, jac, _ = self._run(qs, True, with_jacobian, False)
         return b.out(vals), (b.out(jac) if with_jacobian else self.dummy_jacobian())
+
+    _min_values = CollFreeConst._min_values
 
     def is_valid_batch(self, qs):
         if not self.reflect_robot_flag:
