@@ -53,6 +53,12 @@ class AbstractConst(ABC):
     reflect_robot_flag: bool = False
     id_value: str
 
+    def __getstate__(self):
+        # native plan handles are per-object caches: never copied or pickled (copy.deepcopy / ParallelSolver forks)
+        d = dict(self.__dict__)
+        d.pop("_plan_cache", None)
+        return d
+
     def assign_id_value(self):
         self.id_value = str(uuid.uuid4())
 
@@ -261,9 +267,15 @@ class CollFreeConst(AbstractIneqConst):
         self.assign_id_value()
 
     def _plan(self):
+        # the plan is a snapshot of the solver's sticky state: rebuilt only after the solver changed (set_q / add_new_link)
         k = self.colkin
-        return k.fksolver.get_plan(k.tinyfk_feature_ids, k.tinyfk_joint_ids, k.base_type, RotationType.IGNORE,
+        cached = self.__dict__.get("_plan_cache")
+        if cached is not None and cached[0] is k.fksolver and cached[1] == k.fksolver._version:
+            return cached[2]
+        plan = k.fksolver.get_plan(k.tinyfk_feature_ids, k.tinyfk_joint_ids, k.base_type, RotationType.IGNORE,
                                    radii=k.get_radius_list())
+        self.__dict__["_plan_cache"] = (k.fksolver, k.fksolver._version, plan)
+        return plan
 
     def _run(self, qs, want_vals: bool, with_jacobian: bool, want_valid: bool):
         assert self.sdf is not None
@@ -491,10 +503,16 @@ class PairWiseSelfCollFreeConst(AbstractIneqConst):
 
     def _plan(self):
         k = self.colkin
+        cached = self.__dict__.get("_plan_cache")
+        if (cached is not None and cached[0] is k.fksolver and cached[1] == k.fksolver._version
+                and cached[3] is self.check_sphere_id_pairs and cached[4] is self.check_sphere_pair_sqdists):
+            return cached[2]
         local = {fid: i for i, fid in enumerate(k.tinyfk_feature_ids)}
         pairs = np.array([[local[a], local[b]] for a, b in self.check_sphere_id_pairs], dtype=np.int32)
-        return k.fksolver.get_plan(k.tinyfk_feature_ids, k.tinyfk_joint_ids, k.base_type, RotationType.IGNORE,
+        plan = k.fksolver.get_plan(k.tinyfk_feature_ids, k.tinyfk_joint_ids, k.base_type, RotationType.IGNORE,
                                    radii=None, pairs=pairs, pair_sqdists=self.check_sphere_pair_sqdists)
+        self.__dict__["_plan_cache"] = (k.fksolver, k.fksolver._version, plan, self.check_sphere_id_pairs, self.check_sphere_pair_sqdists)
+        return plan
 
     def _run(self, qs, want_vals: bool, with_jacobian: bool, want_valid: bool):
         plan = self._plan()
