@@ -58,8 +58,8 @@ def main():
                 return "phase 1: FK walk (3 lanes per node)"
             if l < A["wrench_hi"]:
                 return "wrench moment (explicit mul/fma)"
-            if "ldg_cell" in "ldg_cell" and 100 <= l <= 125:
-                return "grid SDF (gather + trilinear + gradient)"
+            if l < A["fk_lo"]:
+                return "SDF primitives (box / cylinder / sphere / generic grid, skb_device.cuh)"
             return "bulk-store / fence helpers"
         if f == "skb_sphere2.cu":
             if A["fma2_lo"] <= l < A["fma2_hi"]:
@@ -67,7 +67,7 @@ def main():
             if A["grid_lo"] <= l < A["grid_hi"]:
                 return "grid SDF (gather + trilinear + gradient)"
             if A["prologue_lo"] <= l < A["prologue_hi"]:
-                return "CTA prologue (tables -> shared memory)"
+                return "kernel-parameter / shared-base re-materialisation (attributed to the prologue lines)"
             if A["q_lo"] <= l < A["q_hi"]:
                 return "q fetch + sin/cos pass"
             if A["front_lo"] <= l < A["front_hi"]:
