@@ -137,10 +137,10 @@ int skb_collfree(const skb_plan *p, const skb_sdf *s, int32_t dtype, const void 
     const void *dp = get_dev_prims(const_cast<skb_sdf *>(s), dtype);
     if (!dp) return -1;
     // full-output fp32 mode: the two-rows-per-lane step kernel (skb_sphere2.cu)
-    // fp32: the step kernel (skb_sphere2.cu) serves every mode
-    if (dtype == SKB_F32 && (mode == SKB_MODE_CLOSEST || !out_valid_dev || (!out_vals_dev && !out_jac_dev)))
+    // the step kernel (skb_sphere2.cu) serves every mode in fp32 and fp64
+    if (mode == SKB_MODE_CLOSEST || !out_valid_dev || (!out_vals_dev && !out_jac_dev))
         if (const skb_s2_program *s2 = get_s2_program(const_cast<skb_plan *>(p), KIND_COLLFREE))
-            return launch_s2(p, s2, KIND_COLLFREE, q_dev, N, dp, get_host_prims(s, dtype), (int)s->prims.size(), margin, mode,
+            return launch_s2(p, s2, KIND_COLLFREE, dtype, q_dev, N, dp, get_host_prims(s, dtype), (int)s->prims.size(), margin, mode,
                              out_vals_dev, out_jac_dev, out_valid_dev, stream);
     if (const skb_sphere_program *sp = get_sphere_program(const_cast<skb_plan *>(p)))
         return launch_sphere(p, sp, KIND_COLLFREE, dtype, q_dev, N, dp, get_host_prims(s, dtype), (int)s->prims.size(), margin, mode, out_vals_dev,
@@ -156,9 +156,9 @@ int skb_pairwise(const skb_plan *p, int32_t dtype, const void *q_dev, int64_t N,
     if (!p || N < 0 || (N > 0 && !q_dev)) return set_error("pairwise: bad arguments");
     if (mode != SKB_MODE_ALL && mode != SKB_MODE_CLOSEST) return set_error("pairwise: bad mode");
     if (!p->pairs_set) return set_error("pairwise: skb_plan_set_pairs was not called");
-    if (dtype == SKB_F32 && (mode == SKB_MODE_CLOSEST || !out_valid_dev || (!out_vals_dev && !out_jac_dev)))
+    if (mode == SKB_MODE_CLOSEST || !out_valid_dev || (!out_vals_dev && !out_jac_dev))
         if (const skb_s2_program *s2 = get_s2_program(const_cast<skb_plan *>(p), KIND_PAIRWISE))
-            return launch_s2(p, s2, KIND_PAIRWISE, q_dev, N, nullptr, nullptr, 0, 0.0, mode, out_vals_dev, out_jac_dev,
+            return launch_s2(p, s2, KIND_PAIRWISE, dtype, q_dev, N, nullptr, nullptr, 0, 0.0, mode, out_vals_dev, out_jac_dev,
                              out_valid_dev, stream);
     const skb_pair_program *pp = get_pair_program(const_cast<skb_plan *>(p));
     if (!pp) return -1;

@@ -786,6 +786,15 @@ static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp) {
                 }
     I[Q_CENA_F] = (int)Fv.size();
     if (pairs) for (int f = 0; f < nf; ++f) { for (int j = 0; j < 3; ++j) Fv.push_back(p->feat_off[f].t[j]); Fv.push_back(p->radii[f]); }
+    I[Q_THR_F] = (int)Fv.size();
+    if (pairs)
+        for (int s = 0; s < n_steps; ++s)
+            for (int h = 0; h < (sp->steps[s].cntB > 0 ? 2 : 1); ++h)
+                for (int l = 0; l < 32; ++l) {
+                    const int r = sp->steps[s].s0 + 32 * h + l;
+                    const int cnt = h == 0 ? sp->steps[s].cntA : sp->steps[s].cntB;
+                    Fv.push_back(l < cnt ? p->pair_thr[r] : 0.0);
+                }
     I[Q_F_TOTAL] = (int)Fv.size();
     sp->n_nodes = n_nodes; sp->n_levels = n_levels; sp->rows = rows; sp->n_cen = pairs ? nf : 0;
     sp->frame_stride = odd_quads(n_nodes * 12);
@@ -796,6 +805,7 @@ static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp) {
 static void free_s2(skb_s2_program &sp) {
     if (sp.dI) cudaFree(sp.dI);
     if (sp.dF32) cudaFree(sp.dF32);
+    if (sp.dF64) cudaFree(sp.dF64);
     sp = skb_s2_program();
 }
 
@@ -812,7 +822,7 @@ const skb_s2_program *get_s2_program(skb_plan *p, int kind) {
             sp.dI = nullptr;
             return nullptr;
         }
-        if (upload_reals<float>(sp.F, &sp.dF32) != 0) return nullptr;
+        if (upload_reals<float>(sp.F, &sp.dF32) != 0 || upload_reals<double>(sp.F, &sp.dF64) != 0) return nullptr;
     }
     return &sp;
 }

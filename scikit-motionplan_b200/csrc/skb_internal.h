@@ -163,6 +163,7 @@ enum QHdr {
     Q_N_NODES = 0, Q_N_LEVELS, Q_N_STEPS, Q_D, Q_ROWS, Q_N_CEN,
     Q_NODE_I, Q_LEVEL_I, Q_LEVELNODE_I, Q_TABB_I, Q_CENNODE_I, Q_I_TOTAL,
     Q_NODE_F, Q_TABA_F, Q_CENA_F, Q_F_TOTAL,
+    Q_THR_F,       // pairwise: (r_i + r_j)^2 per (step, half, lane) as a real (read by the fp64 kernel; fp32 packs it in table B)
     Q_TABC_I,      // pairwise with D > 32: int4 per (step, half, lane) {plus_mask_hi, minus_mask_hi, 0, 0}
     QHDR_WORDS = 20
 };
@@ -175,6 +176,7 @@ struct skb_s2_program {
     std::vector<skb_s2_step> steps;
     void *dI = nullptr;
     void *dF32 = nullptr;
+    void *dF64 = nullptr;
     int n_nodes = 0, n_levels = 0, rows = 0, n_cen = 0;
     int frame_stride = 0;            // floats per configuration
     bool built = false, supported = false;
@@ -284,7 +286,7 @@ const skb_com_program *get_com_program(skb_plan *p);
 int launch_com(const skb_plan *p, const skb_com_program *cp, int dtype, const void *q, int64_t N, const void *dev_prims,
                int n_prims, int what, void *out_vals, void *out_jac, void *stream);
 // skb_sphere2.cu (fp32, full-output modes)
-int launch_s2(const skb_plan *p, const skb_s2_program *sp, int kind, const void *q, int64_t N, const void *dev_prims,
+int launch_s2(const skb_plan *p, const skb_s2_program *sp, int kind, int dtype, const void *q, int64_t N, const void *dev_prims,
               const void *host_prims, int n_prims, double margin, int mode, void *out_vals, void *out_jac, uint8_t *out_valid,
               void *stream);
 enum { KIND_MAP = 0, KIND_COLLFREE = 1, KIND_PAIRWISE = 2 };

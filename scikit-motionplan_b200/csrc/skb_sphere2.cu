@@ -49,33 +49,35 @@ struct GridFast {
     const float *cells;
 };
 
+template <typename T>
 struct S2Params {
     const int32_t *I;
-    const float *F;
-    const float *q;
+    const T *F;
+    const T *q;
     long long N;
     long long n_tiles;
-    const DevPrim<float> *prims;
+    const DevPrim<T> *prims;
     int n_prims;
-    float margin;
-    float *out_vals;
-    float *out_jac;
+    T margin;
+    T *out_vals;
+    T *out_jac;
     uint8_t *out_valid;
     int i_total, f_total;
-    int off_F, off_prims, off_warp, warp_elems;                       // bytes, bytes, bytes, floats per warp
+    int off_F, off_prims, off_warp, warp_elems;                       // bytes, bytes, bytes, elements of T per warp
     int off_lv, n_nodes;                                              // per-CTA level-record table (bytes), node count
-    int woff_q, woff_sc, woff_frames, woff_tw, woff_cen, woff_stage;  // float offsets inside a warp slab
-    int fstride, tstride, cstride;                                    // floats per configuration: frames, twists, centres
+    int woff_q, woff_sc, woff_frames, woff_tw, woff_cen, woff_stage;  // element offsets inside a warp slab
+    int fstride, tstride, cstride;                                    // elements of T per configuration: frames, twists, centres
     int G, logG, slots3;
     int D, NP, R, n_steps, n_levels, n_cen;                           // R = output rows per configuration
     int copy_vec;                                                     // 1: every step block is 16-byte aligned in out_jac
     // warp-uniform data of the hot loop lives in the kernel parameters (constant bank -> uniform datapath)
     skb_s2_step steps[S2_MAX_STEPS];
-    DevPrim<float> prim0;
+    DevPrim<T> prim0;
     GridFast grid;
 };
 
 __device__ __forceinline__ void st_stream(float *p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
 
 // packed fp32x2 FMA (sm_100: SASS FFMA2 / FMUL2): both halves in one issue slot
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
@@ -115,8 +117,32 @@ __device__ __forceinline__ float s2_grid_fast(const GridFast &gr, float px, floa
     return inside ? c0 + fz * h : gr.fill;
 }
 
-template <typename MaskT> struct RowState {   // what phase 2 keeps of one output row
-    float gx, gy, gz, mx, my, mz;
+// two adjacent columns of a Jacobian row: packed f32x2 arithmetic for float, two scalar chains for double -- the same
+// mul, then five fma per half in both cases (bit-identical to dot6)
+template <typename T> struct Pair2;
+template <> struct Pair2<float> {
+    using type = float2;
+    static __device__ __forceinline__ float2 make(float x, float y) { return make_float2(x, y); }
+    static __device__ __forceinline__ float2 mul(float2 a, float s) { return mul2(a, make_float2(s, s)); }
+    static __device__ __forceinline__ float2 fma(float2 a, float s, float2 c) { return fma2(a, make_float2(s, s), c); }
+};
+template <> struct Pair2<double> {
+    using type = double2;
+    static __device__ __forceinline__ double2 make(double x, double y) { return make_double2(x, y); }
+    static __device__ __forceinline__ double2 mul(double2 a, double s) { return make_double2(__dmul_rn(a.x, s), __dmul_rn(a.y, s)); }
+    static __device__ __forceinline__ double2 fma(double2 a, double s, double2 c) { return make_double2(__fma_rn(a.x, s, c.x), __fma_rn(a.y, s, c.y)); }
+};
+
+// the corner-pack fast path exists for fp32 only; the fp64 instantiation of SDF_GRID_FAST is never launched
+__device__ __forceinline__ float grid_fast_or_generic(const S2Params<float> &prm, float px, float py, float pz, float &gx, float &gy, float &gz) {
+    return s2_grid_fast(prm.grid, px, py, pz, gx, gy, gz);
+}
+__device__ __forceinline__ double grid_fast_or_generic(const S2Params<double> &prm, double px, double py, double pz, double &gx, double &gy, double &gz) {
+    return sdf_prim_world<double>(prm.prim0, px, py, pz, gx, gy, gz);
+}
+
+template <typename T, typename MaskT> struct RowState {   // what phase 2 keeps of one output row
+    T gx, gy, gz, mx, my, mz;
     MaskT pm, mm;
 };
 
@@ -124,20 +150,23 @@ template <typename MaskT> struct RowState {   // what phase 2 keeps of one outpu
 // RED = true : per-configuration reduction -- closest row (np.argmin: first index wins ties) and / or validity byte
 // NPMAX: compile-time bound on the number of column pairs (the Jacobian loop is fully unrolled against it, so twist
 // addresses and column bits become immediates)
-template <int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX>
-__global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const __grid_constant__ S2Params prm) {
-    using V4 = Vec4<float>;
+template <typename T, int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX>
+__global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const __grid_constant__ S2Params<T> prm) {
+    using V4 = Vec4<T>;
+    using Rl = Real<T>;
+    using P2 = Pair2<T>;
+    using V2 = typename P2::type;
     extern __shared__ __align__(16) unsigned char smem[];
     int32_t *sI = reinterpret_cast<int32_t *>(smem);
-    float *sF = reinterpret_cast<float *>(smem + prm.off_F);
-    DevPrim<float> *sP = reinterpret_cast<DevPrim<float> *>(smem + prm.off_prims);
+    T *sF = reinterpret_cast<T *>(smem + prm.off_F);
+    DevPrim<T> *sP = reinterpret_cast<DevPrim<T> *>(smem + prm.off_prims);
 
     // the warp index goes through a shuffle so the compiler treats it (and everything derived from it) as warp-uniform
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), n_warps = blockDim.x >> 5;
     for (int i = tid; i < prm.i_total; i += blockDim.x) sI[i] = prm.I[i];
     for (int i = tid; i < prm.f_total; i += blockDim.x) sF[i] = prm.F[i];
     if (KIND == KIND_COLLFREE && SDFK == SDF_UNION) {
-        const int words = prm.n_prims * (int)(sizeof(DevPrim<float>) / 4);
+        const int words = prm.n_prims * (int)(sizeof(DevPrim<T>) / 4);
         const int32_t *src = reinterpret_cast<const int32_t *>(prm.prims);
         int32_t *dst = reinterpret_cast<int32_t *>(sP);
         for (int i = tid; i < words; i += blockDim.x) dst[i] = src[i];
@@ -156,26 +185,27 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
     const V4 *nodeF = reinterpret_cast<const V4 *>(sF + sI[Q_NODE_F]);
     const V4 *tabA = reinterpret_cast<const V4 *>(sF + sI[Q_TABA_F]);
     const V4 *cenA = reinterpret_cast<const V4 *>(sF + sI[Q_CENA_F]);
+    const T *tabThr = sF + sI[Q_THR_F];               // pairwise, fp64 only: (r_i + r_j)^2 per (step, half, lane)
     const int G = prm.G, logG = prm.logG;
 
-    float *wbase = reinterpret_cast<float *>(smem + prm.off_warp) + (size_t)warp * prm.warp_elems;
-    float *wq = wbase + prm.woff_q;
-    float *wsc = wbase + prm.woff_sc;
-    float *wframes = wbase + prm.woff_frames;
-    float *wtw = wbase + prm.woff_tw;
-    float *wcen = wbase + prm.woff_cen;
-    float *wstage = wbase + prm.woff_stage;
+    T *wbase = reinterpret_cast<T *>(smem + prm.off_warp) + (size_t)warp * prm.warp_elems;
+    T *wq = wbase + prm.woff_q;
+    T *wsc = wbase + prm.woff_sc;
+    T *wframes = wbase + prm.woff_frames;
+    T *wtw = wbase + prm.woff_tw;
+    T *wcen = wbase + prm.woff_cen;
+    T *wstage = wbase + prm.woff_stage;
     const uint64_t l2_policy = l2_evict_first_policy();
 
     // the next tile's joint values are fetched while the current tile is being processed (first 128 of the G * D values
     // of a tile; longer tiles read the rest directly), so the DRAM latency of q never sits on the critical path
     const long long tile_step = (long long)gridDim.x * n_warps;
-    float qn[4];
+    T qn[4];
     auto fetch_q = [&](const long long t) {
         const long long b = t * G * D;
         const int cnt = t < prm.n_tiles ? (int)min((long long)G, prm.N - t * G) * D : 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) qn[k] = (lane + 32 * k < cnt) ? __ldg(prm.q + b + lane + 32 * k) : 0.f;
+        for (int k = 0; k < 4; ++k) qn[k] = (lane + 32 * k < cnt) ? __ldg(prm.q + b + lane + 32 * k) : T(0);
     };
     fetch_q((long long)blockIdx.x * n_warps + warp);
 
@@ -188,16 +218,16 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
         for (int k = 0; k < 4; ++k) {
             const int i = lane + 32 * k;
             if (i < g_live * D) {
-                float sn, cs;
-                sincosf(qn[k], &sn, &cs);
+                T sn, cs;
+                Rl::sincos(qn[k], &sn, &cs);
                 wq[i] = qn[k];
                 wsc[2 * i] = sn; wsc[2 * i + 1] = cs;
             }
         }
         for (int i = lane + 128; i < g_live * D; i += 32) {
-            const float th = prm.q[n0 * D + i];
-            float sn, cs;
-            sincosf(th, &sn, &cs);
+            const T th = prm.q[n0 * D + i];
+            T sn, cs;
+            Rl::sincos(th, &sn, &cs);
             wq[i] = th;
             wsc[2 * i] = sn; wsc[2 * i + 1] = cs;
         }
@@ -205,7 +235,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
         __syncwarp();
 
         // ------------------------------------------------------------ phase 1: frames + twists
-        fk_phase<float, JAC, true>(lane, G, logG, prm.slots3, g_live, D, n_levels, lvrec, levelI, nodeF, wq, wsc,
+        fk_phase<T, JAC, true>(lane, G, logG, prm.slots3, g_live, D, n_levels, lvrec, levelI, nodeF, wq, wsc,
                                     wframes, fstride, wtw, tstride);
 
         // ------------------------------------------------------------ phase 1b: sphere centres (pairwise)
@@ -220,7 +250,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                     x.x = f0.w + f0.x * A.x + f0.y * A.y + f0.z * A.z;
                     x.y = f1.w + f1.x * A.x + f1.y * A.y + f1.z * A.z;
                     x.z = f2.w + f2.x * A.x + f2.y * A.y + f2.z * A.z;
-                    x.w = 0.f;
+                    x.w = T(0);
                     reinterpret_cast<V4 *>(wcen + c * cstride)[s] = x;
                 }
             }
@@ -229,28 +259,28 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
 
         // ------------------------------------------------------------ phase 2: steps of up to 64 rows
         // value + wrench + masks of one row of configuration c
-        auto front = [&](const int c, const V4 &A, const int4 &B, const int tslot, RowState<MaskT> &rs) -> float {
-            float val;
+        auto front = [&](const int c, const V4 &A, const int4 &B, const int tslot, RowState<T, MaskT> &rs) -> T {
+            T val;
             if (KIND == KIND_COLLFREE) {
                 const V4 *fr = reinterpret_cast<const V4 *>(wframes + c * fstride);
                 const V4 f0 = fr[3 * B.x], f1 = fr[3 * B.x + 1], f2 = fr[3 * B.x + 2];
-                const float px = f0.w + f0.x * A.x + f0.y * A.y + f0.z * A.z;
-                const float py = f1.w + f1.x * A.x + f1.y * A.y + f1.z * A.z;
-                const float pz = f2.w + f2.x * A.x + f2.y * A.y + f2.z * A.z;
-                const float d = SDFK == SDF_GRID_FAST ? s2_grid_fast(prm.grid, px, py, pz, rs.gx, rs.gy, rs.gz)
-                              : SDFK == SDF_SINGLE    ? sdf_prim_world<float>(prm.prim0, px, py, pz, rs.gx, rs.gy, rs.gz)
-                                                      : sdf_union<float>(sP, prm.n_prims, px, py, pz, rs.gx, rs.gy, rs.gz);
+                const T px = f0.w + f0.x * A.x + f0.y * A.y + f0.z * A.z;
+                const T py = f1.w + f1.x * A.x + f1.y * A.y + f1.z * A.z;
+                const T pz = f2.w + f2.x * A.x + f2.y * A.y + f2.z * A.z;
+                const T d = SDFK == SDF_GRID_FAST ? grid_fast_or_generic(prm, px, py, pz, rs.gx, rs.gy, rs.gz)
+                              : SDFK == SDF_SINGLE    ? sdf_prim_world<T>(prm.prim0, px, py, pz, rs.gx, rs.gy, rs.gz)
+                                                      : sdf_union<T>(sP, prm.n_prims, px, py, pz, rs.gx, rs.gy, rs.gz);
                 val = d - A.w - prm.margin;
-                if (JAC) wrench_moment<float>(px, py, pz, rs.gx, rs.gy, rs.gz, rs.mx, rs.my, rs.mz);
+                if (JAC) wrench_moment<T>(px, py, pz, rs.gx, rs.gy, rs.gz, rs.mx, rs.my, rs.mz);
                 rs.pm = sizeof(MaskT) == 8 ? (MaskT)(((unsigned long long)(unsigned)B.z << 32) | (unsigned)B.y) : (MaskT)(unsigned)B.y;
                 rs.mm = 0;
             } else {
                 const V4 *cen = reinterpret_cast<const V4 *>(wcen + c * cstride);
                 const V4 xi = cen[B.x & 0xffff], xj = cen[(unsigned)B.x >> 16];
-                const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-                val = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))) - __int_as_float(B.w);
-                rs.gx = 2.f * dx; rs.gy = 2.f * dy; rs.gz = 2.f * dz;
-                if (JAC) wrench_moment<float>(xi.x, xi.y, xi.z, rs.gx, rs.gy, rs.gz, rs.mx, rs.my, rs.mz);
+                const T dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                val = Rl::fma(dz, dz, Rl::fma(dy, dy, Rl::mul(dx, dx))) - (sizeof(T) == 4 ? (T)__int_as_float(B.w) : tabThr[tslot * 32 + lane]);
+                rs.gx = T(2) * dx; rs.gy = T(2) * dy; rs.gz = T(2) * dz;
+                if (JAC) wrench_moment<T>(xi.x, xi.y, xi.z, rs.gx, rs.gy, rs.gz, rs.mx, rs.my, rs.mz);
                 rs.pm = (MaskT)(unsigned)B.y;
                 rs.mm = (MaskT)(unsigned)B.z;
                 if (sizeof(MaskT) == 8) {                     // D > 32: the high mask words live in a second table
@@ -266,8 +296,8 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
             // 64-bit output bases once per tile; (configuration, step) offsets stay 32-bit (G * R * D < 2^31)
             int row_off = lane * D;                         // opaque: computed once, not rematerialised per column pair
             asm volatile("" : "+r"(row_off));
-            float *tile_vals = prm.out_vals + n0 * R;
-            float *tile_jac = JAC ? prm.out_jac + n0 * R * (long long)D : nullptr;
+            T *tile_vals = prm.out_vals + n0 * R;
+            T *tile_jac = JAC ? prm.out_jac + n0 * R * (long long)D : nullptr;
             int slot = 0;                                   // running index into the per-(half, lane) tables
             for (int st = 0; st < n_steps; ++st) {
                 // pair-activity bits of the step (bit jp: some row needs column 2 jp or 2 jp + 1); made opaque so it stays in one
@@ -283,21 +313,21 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                 slot += cntB > 0 ? 2 : 1;
 
                 // twist pair x wrench for the columns (col, col + 1), masked / signed
-                auto contract = [&](const float4 &t0, const float4 &t1, const float4 &t2, const RowState<MaskT> &rs, const int col) -> float2 {
-                    float2 a = mul2(make_float2(t0.x, t0.y), make_float2(rs.mx, rs.mx));
-                    a = fma2(make_float2(t0.z, t0.w), make_float2(rs.my, rs.my), a);
-                    a = fma2(make_float2(t1.x, t1.y), make_float2(rs.mz, rs.mz), a);
-                    a = fma2(make_float2(t1.z, t1.w), make_float2(rs.gx, rs.gx), a);
-                    a = fma2(make_float2(t2.x, t2.y), make_float2(rs.gy, rs.gy), a);
-                    a = fma2(make_float2(t2.z, t2.w), make_float2(rs.gz, rs.gz), a);
+                auto contract = [&](const V4 &t0, const V4 &t1, const V4 &t2, const RowState<T, MaskT> &rs, const int col) -> V2 {
+                    V2 a = P2::mul(P2::make(t0.x, t0.y), rs.mx);
+                    a = P2::fma(P2::make(t0.z, t0.w), rs.my, a);
+                    a = P2::fma(P2::make(t1.x, t1.y), rs.mz, a);
+                    a = P2::fma(P2::make(t1.z, t1.w), rs.gx, a);
+                    a = P2::fma(P2::make(t2.x, t2.y), rs.gy, a);
+                    a = P2::fma(P2::make(t2.z, t2.w), rs.gz, a);
                     // column bits are warp-uniform operands: one LOP3 (predicate) + one FSEL per element
                     const MaskT b0 = (MaskT)1 << col, b1 = (MaskT)2 << col;
                     if (KIND == KIND_PAIRWISE) {
-                        a.x = (rs.pm & b0) ? a.x : ((rs.mm & b0) ? -a.x : 0.f);
-                        a.y = (rs.pm & b1) ? a.y : ((rs.mm & b1) ? -a.y : 0.f);
+                        a.x = (rs.pm & b0) ? a.x : ((rs.mm & b0) ? -a.x : T(0));
+                        a.y = (rs.pm & b1) ? a.y : ((rs.mm & b1) ? -a.y : T(0));
                     } else {
-                        a.x = (rs.pm & b0) ? a.x : 0.f;
-                        a.y = (rs.pm & b1) ? a.y : 0.f;
+                        a.x = (rs.pm & b0) ? a.x : T(0);
+                        a.y = (rs.pm & b1) ? a.y : T(0);
                     }
                     return a;
                 };
@@ -306,36 +336,36 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                     constexpr bool HAS_B = decltype(has_b)::value;
                     int tw_off = c * tstride;                      // opaque: one address register for the whole unrolled loop
                     asm volatile("" : "+r"(tw_off));
-                    const float *tw = wtw + tw_off;
-                    RowState<MaskT> ra, rb;
-                    const float va = front(c, A0, B0, slotA, ra);
-                    float vb = 0.f;
+                    const T *tw = wtw + tw_off;
+                    RowState<T, MaskT> ra, rb;
+                    const T va = front(c, A0, B0, slotA, ra);
+                    T vb = T(0);
                     if (HAS_B) vb = front(c, A1, B1, slotB, rb);
                     if (prm.out_vals != nullptr) {
-                        float *gv = tile_vals + (unsigned)(c * R + s0 + lane);
+                        T *gv = tile_vals + (unsigned)(c * R + s0 + lane);
                         if (lane < cntA) st_stream(gv, va);
                         if (HAS_B && lane < cntB) st_stream(gv + 32, vb);
                     }
                     if (!JAC) return;
-                    float *rowA = wstage + row_off;
-                    float *rowB = rowA + 32 * D;
+                    T *rowA = wstage + row_off;
+                    T *rowB = rowA + 32 * D;
                     // the bulk store of the previous step must have finished reading the staging block
                     if (lane == 0) bulk_wait_read<0>();
                     __syncwarp();
-                    const float4 *t4 = reinterpret_cast<const float4 *>(tw);
+                    const V4 *t4 = reinterpret_cast<const V4 *>(tw);
 #pragma unroll
                     for (int jp = 0; jp < NPMAX; ++jp) {
                         if (jp < NP) {                                    // uniform
                             const int col = 2 * jp;
-                            float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+                            V2 a = P2::make(T(0), T(0)), b = P2::make(T(0), T(0));
                             if (pact & (1u << jp)) {                      // uniform: some row of this step needs col or col + 1
-                                const float4 t0 = t4[3 * jp], t1 = t4[3 * jp + 1], t2 = t4[3 * jp + 2];
+                                const V4 t0 = t4[3 * jp], t1 = t4[3 * jp + 1], t2 = t4[3 * jp + 2];
                                 a = contract(t0, t1, t2, ra, col);
                                 if (HAS_B) b = contract(t0, t1, t2, rb, col);
                             }
                             if (VW == 2) {
-                                *reinterpret_cast<float2 *>(rowA + col) = a;
-                                if (HAS_B) *reinterpret_cast<float2 *>(rowB + col) = b;
+                                *reinterpret_cast<V2 *>(rowA + col) = a;
+                                if (HAS_B) *reinterpret_cast<V2 *>(rowB + col) = b;
                             } else {
                                 rowA[col] = a.x;
                                 if (HAS_B) rowB[col] = b.x;
@@ -348,12 +378,12 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                     }
                     // ship: the dense [rows][D] block is contiguous in HBM
                     const int len = (cntA + (HAS_B ? cntB : 0)) * D;
-                    float *g = tile_jac + (unsigned)((c * R + s0) * D);
+                    T *g = tile_jac + (unsigned)((c * R + s0) * D);
                     if (prm.copy_vec) {
                         fence_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            bulk_store_hint(g, wstage, (uint32_t)(len * sizeof(float)), l2_policy);
+                            bulk_store_hint(g, wstage, (uint32_t)(len * sizeof(T)), l2_policy);
                             bulk_commit();
                         }
                     } else {
@@ -371,50 +401,50 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
             // ---- per-configuration reduction: closest row (value, Jacobian row) and / or validity byte
             for (int c = 0; c < g_live; ++c) {
                 const long long n = n0 + c;
-                float best = __int_as_float(0x7f800000);
+                T best = Rl::inf();
                 int bidx = 0x7fffffff;
-                RowState<MaskT> brs;
-                brs.gx = brs.gy = brs.gz = brs.mx = brs.my = brs.mz = 0.f; brs.pm = 0; brs.mm = 0;
+                RowState<T, MaskT> brs;
+                brs.gx = brs.gy = brs.gz = brs.mx = brs.my = brs.mz = T(0); brs.pm = 0; brs.mm = 0;
                 int slot = 0;
                 for (int st = 0; st < n_steps; ++st) {
                     const int s0 = prm.steps[st].s0, cntA = prm.steps[st].cntA, cntB = prm.steps[st].cntB;
                     // both rows of the lane are evaluated before either is compared, so their gathers overlap
-                    RowState<MaskT> rsa, rsb;
+                    RowState<T, MaskT> rsa, rsb;
                     V4 Aa, Ab;
                     const int slot_b = slot + (cntB > 0 ? 1 : 0);
                     if (KIND == KIND_COLLFREE) { Aa = tabA[slot * 32 + lane]; Ab = tabA[slot_b * 32 + lane]; }
-                    const float va = front(c, Aa, tabB[slot * 32 + lane], slot, rsa);
-                    float vb = __int_as_float(0x7f800000);
+                    const T va = front(c, Aa, tabB[slot * 32 + lane], slot, rsa);
+                    T vb = Rl::inf();
                     if (cntB > 0) vb = front(c, Ab, tabB[slot_b * 32 + lane], slot_b, rsb);
                     if (lane < cntA && va < best) { best = va; bidx = s0 + lane; brs = rsa; }
                     if (lane < cntB && vb < best) { best = vb; bidx = s0 + 32 + lane; brs = rsb; }
                     slot = slot_b + 1;
                     // validity only: one row at or below zero decides the configuration (the reference's composite
                     // short-circuits the same way, skmp/constraint.py:167-176)
-                    if (!JAC && prm.out_vals == nullptr && __any_sync(0xffffffffu, best <= 0.f)) break;
+                    if (!JAC && prm.out_vals == nullptr && __any_sync(0xffffffffu, best <= T(0))) break;
                 }
-                float m = best; int mi = bidx;
+                T m = best; int mi = bidx;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
-                    const float x = __shfl_xor_sync(0xffffffffu, m, o);
+                    const T x = __shfl_xor_sync(0xffffffffu, m, o);
                     const int xi = __shfl_xor_sync(0xffffffffu, mi, o);
                     if (x < m || (x == m && xi < mi)) { m = x; mi = xi; }
                 }
                 if (lane == 0) {
                     if (prm.out_vals != nullptr) prm.out_vals[n] = m;
-                    if (prm.out_valid != nullptr) prm.out_valid[n] = m > 0.f ? 1 : 0;
+                    if (prm.out_valid != nullptr) prm.out_valid[n] = m > T(0) ? 1 : 0;
                 }
                 if (JAC) {
                     const int src = max(0, __ffs(__ballot_sync(0xffffffffu, bidx == mi && best == m)) - 1);
-                    const float gx = __shfl_sync(0xffffffffu, brs.gx, src), gy = __shfl_sync(0xffffffffu, brs.gy, src), gz = __shfl_sync(0xffffffffu, brs.gz, src);
-                    const float mx = __shfl_sync(0xffffffffu, brs.mx, src), my = __shfl_sync(0xffffffffu, brs.my, src), mz = __shfl_sync(0xffffffffu, brs.mz, src);
+                    const T gx = __shfl_sync(0xffffffffu, brs.gx, src), gy = __shfl_sync(0xffffffffu, brs.gy, src), gz = __shfl_sync(0xffffffffu, brs.gz, src);
+                    const T mx = __shfl_sync(0xffffffffu, brs.mx, src), my = __shfl_sync(0xffffffffu, brs.my, src), mz = __shfl_sync(0xffffffffu, brs.mz, src);
                     const MaskT pm = __shfl_sync(0xffffffffu, brs.pm, src);
                     const MaskT mm = __shfl_sync(0xffffffffu, brs.mm, src);
-                    const float *tw = wtw + c * tstride;
+                    const T *tw = wtw + c * tstride;
                     for (int col = lane; col < D; col += 32) {     // one lane per column of the single row
-                        const float *t2 = tw + (col >> 1) * 12 + (col & 1);
-                        float jv = dot6<float>(t2[0], t2[2], t2[4], t2[6], t2[8], t2[10], mx, my, mz, gx, gy, gz);
-                        jv = ((pm >> col) & 1) ? jv : (((mm >> col) & 1) ? -jv : 0.f);
+                        const T *t2 = tw + (col >> 1) * 12 + (col & 1);
+                        T jv = dot6<T>(t2[0], t2[2], t2[4], t2[6], t2[8], t2[10], mx, my, mz, gx, gy, gz);
+                        jv = ((pm >> col) & 1) ? jv : (((mm >> col) & 1) ? -jv : T(0));
                         prm.out_jac[n * D + col] = jv;
                     }
                 }
@@ -446,27 +476,27 @@ static int sm_count_cached() {
     return sms;
 }
 
-template <int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX = 1>
+template <typename T, int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX = 1>
 static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const void *q, int64_t N, const void *dev_prims,
                           const void *host_prims, int n_prims, double margin, void *out_vals, void *out_jac, uint8_t *out_valid,
                           cudaStream_t stream) {
-    S2Params prm;
+    S2Params<T> prm;
     memset(&prm, 0, sizeof(prm));
     prm.I = reinterpret_cast<const int32_t *>(sp->dI);
-    prm.F = reinterpret_cast<const float *>(sp->dF32);
-    prm.q = reinterpret_cast<const float *>(q);
+    prm.F = reinterpret_cast<const T *>(sizeof(T) == 4 ? sp->dF32 : sp->dF64);
+    prm.q = reinterpret_cast<const T *>(q);
     prm.N = N;
-    prm.prims = reinterpret_cast<const DevPrim<float> *>(dev_prims);
+    prm.prims = reinterpret_cast<const DevPrim<T> *>(dev_prims);
     prm.n_prims = n_prims;
-    prm.margin = (float)margin;
-    prm.out_vals = reinterpret_cast<float *>(out_vals);
-    prm.out_jac = reinterpret_cast<float *>(out_jac);
+    prm.margin = (T)margin;
+    prm.out_vals = reinterpret_cast<T *>(out_vals);
+    prm.out_jac = reinterpret_cast<T *>(out_jac);
     prm.out_valid = out_valid;
     prm.i_total = (int)sp->I.size();
-    prm.f_total = (int)sp->F.size();
-    if (KIND == KIND_COLLFREE && host_prims) prm.prim0 = *reinterpret_cast<const DevPrim<float> *>(host_prims);
+    prm.f_total = sizeof(T) == 4 ? sp->I[Q_THR_F] : (int)sp->F.size();     // the fp64-only threshold table is the tail of F
+    if (KIND == KIND_COLLFREE && host_prims) prm.prim0 = *reinterpret_cast<const DevPrim<T> *>(host_prims);
     if (KIND == KIND_COLLFREE && SDFK == SDF_GRID_FAST) {
-        const DevPrim<float> &pr = prm.prim0;
+        const DevPrim<T> &pr = prm.prim0;
         GridFast &g = prm.grid;
         g.ox = (float)((double)pr.pos[0] + (double)pr.par[0]); g.oy = (float)((double)pr.pos[1] + (double)pr.par[1]);
         g.oz = (float)((double)pr.pos[2] + (double)pr.par[2]);
@@ -479,18 +509,19 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
     }
     const int D = p->D, R = sp->rows, NP = (D + 1) / 2;
     prm.D = D; prm.NP = NP; prm.R = R; prm.n_steps = (int)sp->steps.size(); prm.n_levels = sp->n_levels; prm.n_cen = sp->n_cen;
-    prm.copy_vec = (((long long)R * D) % 4 == 0 && reinterpret_cast<uintptr_t>(out_jac) % 16 == 0) ? 1 : 0;
+    const int al = 16 / (int)sizeof(T);          // elements of T per 16 bytes
+    prm.copy_vec = (((long long)R * D) % al == 0 && reinterpret_cast<uintptr_t>(out_jac) % 16 == 0) ? 1 : 0;
     for (int s = 0; s < prm.n_steps; ++s) {
         prm.steps[s] = sp->steps[s];
         unsigned long long pact = 0;            // the kernel wants pair-activity bits, not column bits
         for (int jp = 0; jp < NP; ++jp) if ((sp->steps[s].cm >> (2 * jp)) & 3ull) pact |= 1ull << jp;
         prm.steps[s].cm = pact;
         const int len = (sp->steps[s].cntA + sp->steps[s].cntB) * D;
-        if ((sp->steps[s].s0 * D) % 4 != 0 || len % 4 != 0) prm.copy_vec = 0;
+        if ((sp->steps[s].s0 * D) % al != 0 || len % al != 0) prm.copy_vec = 0;
     }
     prm.off_F = align_up(prm.i_total * 4, 16);
-    prm.off_prims = align_up(prm.off_F + prm.f_total * 4, 16);
-    prm.off_lv = align_up(prm.off_prims + ((KIND == KIND_COLLFREE && SDFK == SDF_UNION) ? n_prims : 0) * (int)sizeof(DevPrim<float>), 16);
+    prm.off_prims = align_up(prm.off_F + prm.f_total * (int)sizeof(T), 16);
+    prm.off_lv = align_up(prm.off_prims + ((KIND == KIND_COLLFREE && SDFK == SDF_UNION) ? n_prims : 0) * (int)sizeof(DevPrim<T>), 16);
     prm.n_nodes = sp->n_nodes;
     prm.off_warp = align_up(prm.off_lv + sp->n_nodes * 16, 128);
     prm.fstride = sp->frame_stride;
@@ -499,20 +530,20 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
     const size_t smem_limit = 227 * 1024;
     auto layout = [&](int g, int warps) {
         int e = 0;
-        prm.woff_q = e;      e += align_up(g * D, 4);
-        prm.woff_sc = e;     e += align_up(2 * g * D, 4);
+        prm.woff_q = e;      e += align_up(g * D, al);
+        prm.woff_sc = e;     e += align_up(2 * g * D, al);
         prm.woff_frames = e; e += g * prm.fstride;
         prm.woff_tw = e;     e += JAC ? g * prm.tstride : 0;
         prm.woff_cen = e;    e += g * prm.cstride;
-        prm.woff_stage = e;  e += (JAC && !RED) ? align_up(64 * D, 4) : 0;
-        prm.warp_elems = align_up(e, 4);
-        return (size_t)prm.off_warp + (size_t)warps * prm.warp_elems * sizeof(float);
+        prm.woff_stage = e;  e += (JAC && !RED) ? align_up(64 * D, al) : 0;
+        prm.warp_elems = align_up(e, al);
+        return (size_t)prm.off_warp + (size_t)warps * prm.warp_elems * sizeof(T);
     };
     // Configurations per tile G against warps per CTA and CTAs per SM.  A larger G fills more lanes of the tree walk
     // (three lanes per node, `slots3` nodes of a level at once) but costs shared memory, i.e. resident warps.  Every
     // candidate is scored with a small issue-slot model:  (resident warps)^0.75 / (FK slots + phase-2 slots per
     // configuration);  the occupancy comes from the runtime (registers and shared memory).
-    auto kern = s2_kernel<KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>;
+    auto kern = s2_kernel<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
     static const int cand[][2] = {{8, 8}, {8, 6}, {8, 4}, {4, 8}, {4, 7}, {4, 6}, {4, 4}, {2, 8}, {2, 6}, {2, 4}, {1, 8}, {1, 6}, {1, 4}, {1, 2}, {1, 1}};
     int halves = 0;
@@ -555,20 +586,20 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
 #define S2_SIG const skb_plan *p, const skb_s2_program *sp, const void *q, int64_t N, const void *dev_prims, const void *host_prims, \
                int n_prims, double margin, void *out_vals, void *out_jac, uint8_t *out_valid, cudaStream_t stream
 
-template <int KIND, int SDFK>
+template <typename T, int KIND, int SDFK>
 static int launch_s2_mode(S2_SIG, int mode) {
     const bool even = p->D % 2 == 0, wide = p->D > 32, jac = out_jac != nullptr;
     if (mode == SKB_MODE_CLOSEST || out_valid != nullptr) {
         if (mode != SKB_MODE_CLOSEST && (out_vals != nullptr || jac))
             return set_error("step kernel: validity bytes come with the closest mode or alone");
-        if (wide) return jac ? launch_s2_inst<KIND, SDFK, 1, unsigned long long, true, true>(S2_ARGS)
-                             : launch_s2_inst<KIND, SDFK, 1, unsigned long long, true, false>(S2_ARGS);
-        return jac ? launch_s2_inst<KIND, SDFK, 1, unsigned, true, true>(S2_ARGS)
-                   : launch_s2_inst<KIND, SDFK, 1, unsigned, true, false>(S2_ARGS);
+        if (wide) return jac ? launch_s2_inst<T, KIND, SDFK, 1, unsigned long long, true, true>(S2_ARGS)
+                             : launch_s2_inst<T, KIND, SDFK, 1, unsigned long long, true, false>(S2_ARGS);
+        return jac ? launch_s2_inst<T, KIND, SDFK, 1, unsigned, true, true>(S2_ARGS)
+                   : launch_s2_inst<T, KIND, SDFK, 1, unsigned, true, false>(S2_ARGS);
     }
-    if (!jac) return launch_s2_inst<KIND, SDFK, 1, unsigned, false, false>(S2_ARGS);
+    if (!jac) return launch_s2_inst<T, KIND, SDFK, 1, unsigned, false, false>(S2_ARGS);
     const int NP = (p->D + 1) / 2;
-#define S2_FULL(VWv, MT, NPM) launch_s2_inst<KIND, SDFK, VWv, MT, false, true, NPM>(S2_ARGS)
+#define S2_FULL(VWv, MT, NPM) launch_s2_inst<T, KIND, SDFK, VWv, MT, false, true, NPM>(S2_ARGS)
     if (NP <= 4) return even ? S2_FULL(2, unsigned, 4) : S2_FULL(1, unsigned, 4);
     if (NP <= 8) return even ? S2_FULL(2, unsigned, 8) : S2_FULL(1, unsigned, 8);
     if (NP <= 16) return even ? S2_FULL(2, unsigned, 16) : S2_FULL(1, unsigned, 16);
@@ -577,21 +608,28 @@ static int launch_s2_mode(S2_SIG, int mode) {
 #undef S2_FULL
 }
 
-int launch_s2(const skb_plan *p, const skb_s2_program *sp, int kind, const void *q, int64_t N, const void *dev_prims,
+template <typename T>
+static int launch_s2_t(S2_SIG, int kind, int mode) {
+    if (kind == KIND_PAIRWISE) return launch_s2_mode<T, KIND_PAIRWISE, SDF_SINGLE>(S2_ARGS, mode);
+    if (n_prims == 1) {
+        const DevPrim<T> *pr = reinterpret_cast<const DevPrim<T> *>(host_prims);
+        const long long cells = (long long)(pr->dims[0] - 1) * (pr->dims[1] - 1) * (pr->dims[2] - 1);
+        if (sizeof(T) == 4 && pr->type == PRIM_GRID && (pr->flags & PF_GRID_CELLS) && (pr->flags & PF_IDENTITY) &&
+            !(pr->flags & PF_GRID_F64) && cells < (1ll << 31))
+            return launch_s2_mode<T, KIND_COLLFREE, SDF_GRID_FAST>(S2_ARGS, mode);
+        return launch_s2_mode<T, KIND_COLLFREE, SDF_SINGLE>(S2_ARGS, mode);
+    }
+    return launch_s2_mode<T, KIND_COLLFREE, SDF_UNION>(S2_ARGS, mode);
+}
+
+int launch_s2(const skb_plan *p, const skb_s2_program *sp, int kind, int dtype, const void *q, int64_t N, const void *dev_prims,
               const void *host_prims, int n_prims, double margin, int mode, void *out_vals, void *out_jac, uint8_t *out_valid,
               void *stream_) {
     if (N <= 0) return 0;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    if (kind == KIND_PAIRWISE) return launch_s2_mode<KIND_PAIRWISE, SDF_SINGLE>(S2_ARGS, mode);
-    if (n_prims == 1) {
-        const DevPrim<float> *pr = reinterpret_cast<const DevPrim<float> *>(host_prims);
-        const long long cells = (long long)(pr->dims[0] - 1) * (pr->dims[1] - 1) * (pr->dims[2] - 1);
-        if (pr->type == PRIM_GRID && (pr->flags & PF_GRID_CELLS) && (pr->flags & PF_IDENTITY) && !(pr->flags & PF_GRID_F64) &&
-            cells < (1ll << 31))
-            return launch_s2_mode<KIND_COLLFREE, SDF_GRID_FAST>(S2_ARGS, mode);
-        return launch_s2_mode<KIND_COLLFREE, SDF_SINGLE>(S2_ARGS, mode);
-    }
-    return launch_s2_mode<KIND_COLLFREE, SDF_UNION>(S2_ARGS, mode);
+    if (dtype == SKB_F32) return launch_s2_t<float>(S2_ARGS, kind, mode);
+    if (dtype == SKB_F64) return launch_s2_t<double>(S2_ARGS, kind, mode);
+    return set_error("bad dtype");
 }
 
 }  // namespace skb
