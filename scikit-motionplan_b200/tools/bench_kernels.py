@@ -115,6 +115,13 @@ def workloads():
         qs = (torch.rand((n, 37), device="cuda", generator=torch.Generator("cuda").manual_seed(2)) - 0.5) * 0.6
         return (lambda: const.evaluate(qs, True)), n, 4 * (37 + 1 + 37), f"JAXON COMStabilityConst (40 weighted points) + Jacobian, N={n}"
     W["cfg5_com"] = com
+    def cfg3_map():
+        pr2, colkin, grid = bench.make_problem()
+        n = 400_000
+        qs = device_samples(colkin, n, 3)
+        S, D = colkin.n_feature, colkin.dim_cspace
+        return (lambda: colkin.map(qs)), n, 4 * (D + 3 * S + 3 * S * D), f"PR2 dual arm KinematicsMap.map: 152 points + (152,3,14) Jacobians, N={n}"
+    W["cfg3_map"] = cfg3_map
     W["cfg3"] = lambda: cfg3("all")
     W["cfg3_closest"] = lambda: cfg3("closest")
     W["cfg3_valid"] = lambda: cfg3("valid")

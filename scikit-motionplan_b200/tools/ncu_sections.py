@@ -30,7 +30,8 @@ def anchors():
 
     a = {}
     a["fma2_lo"], a["fma2_hi"] = find(s2, "__device__ __forceinline__ float2 fma2"), find(s2, "enum { SDF_UNION")
-    a["grid_lo"], a["grid_hi"] = find(s2, "float s2_grid_fast("), find(s2, "template <typename MaskT> struct RowState")
+    a["pair_lo"], a["pair_hi"] = find(s2, "template <typename T> struct Pair2;"), find(s2, "the corner-pack fast path exists for fp32 only")
+    a["grid_lo"], a["grid_hi"] = find(s2, "float s2_grid_fast("), find(s2, "the corner-pack fast path exists for fp32 only")
     a["prologue_lo"], a["prologue_hi"] = find(s2, "extern __shared__"), find(s2, "auto fetch_q")
     a["q_lo"], a["q_hi"] = find(s2, "auto fetch_q"), find(s2, "phase 1: frames + twists")
     a["front_lo"], a["front_hi"] = find(s2, "auto front = "), find(s2, "if (!RED) {")
@@ -62,7 +63,7 @@ def main():
                 return "SDF primitives (box / cylinder / sphere / generic grid, skb_device.cuh)"
             return "bulk-store / fence helpers"
         if f == "skb_sphere2.cu":
-            if A["fma2_lo"] <= l < A["fma2_hi"]:
+            if A["fma2_lo"] <= l < A["fma2_hi"] or A["pair_lo"] <= l < A["pair_hi"]:
                 return "phase 2: packed FFMA2 chains"
             if A["grid_lo"] <= l < A["grid_hi"]:
                 return "grid SDF (gather + trilinear + gradient)"
