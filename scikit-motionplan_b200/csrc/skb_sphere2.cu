@@ -162,7 +162,10 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
     DevPrim<T> *sP = reinterpret_cast<DevPrim<T> *>(smem + prm.off_prims);
 
     // the warp index goes through a shuffle so the compiler treats it (and everything derived from it) as warp-uniform
-    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), n_warps = blockDim.x >> 5;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), n_warps = blockDim.x >> 5;
+    int lane = tid & 31;
+    if (sizeof(T) == 4) asm volatile("" : "+r"(lane));   // opaque: kept in a register instead of being re-derived from %tid at
+                                                         // every use (the fp64 instantiations are register-bound and keep the remat)
     for (int i = tid; i < prm.i_total; i += blockDim.x) sI[i] = prm.I[i];
     for (int i = tid; i < prm.f_total; i += blockDim.x) sF[i] = prm.F[i];
     if (KIND == KIND_COLLFREE && SDFK == SDF_UNION) {
@@ -355,14 +358,14 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                     const V4 *t4 = reinterpret_cast<const V4 *>(tw);
 #pragma unroll
                     for (int jp = 0; jp < NPMAX; ++jp) {
-                        if (jp < NP) {                                    // uniform
+                        // one uniform test per pair: pairs no row of the step needs (and pairs beyond D) were zero-filled
+                        // once per (tile, step) below, so there is nothing to compute or store for them
+                        if (pact & (1u << jp)) {
                             const int col = 2 * jp;
-                            V2 a = P2::make(T(0), T(0)), b = P2::make(T(0), T(0));
-                            if (pact & (1u << jp)) {                      // uniform: some row of this step needs col or col + 1
-                                const V4 t0 = t4[3 * jp], t1 = t4[3 * jp + 1], t2 = t4[3 * jp + 2];
-                                a = contract(t0, t1, t2, ra, col);
-                                if (HAS_B) b = contract(t0, t1, t2, rb, col);
-                            }
+                            const V4 t0 = t4[3 * jp], t1 = t4[3 * jp + 1], t2 = t4[3 * jp + 2];
+                            const V2 a = contract(t0, t1, t2, ra, col);
+                            V2 b = a;
+                            if (HAS_B) b = contract(t0, t1, t2, rb, col);
                             if (VW == 2) {
                                 *reinterpret_cast<V2 *>(rowA + col) = a;
                                 if (HAS_B) *reinterpret_cast<V2 *>(rowB + col) = b;
@@ -394,6 +397,16 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                     }
                 };
 
+                if (JAC) {
+                    // zero fill of the step's staging block, once per (tile, step): the columns no row of the step needs
+                    // keep their structural zeros while the configurations of the tile pass through
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                    const int len16 = ((cntA + cntB) * D * (int)sizeof(T) + 15) >> 4;
+                    float4 *z = reinterpret_cast<float4 *>(wstage);
+                    for (int i = lane; i < len16; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    __syncwarp();
+                }
                 if (cntB > 0) for (int c = 0; c < g_live; ++c) body(std::true_type{}, c);
                 else          for (int c = 0; c < g_live; ++c) body(std::false_type{}, c);
             }
