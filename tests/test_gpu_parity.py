@@ -350,3 +350,73 @@ def test_ragged_and_empty_batches_bit_exact(pr2):
         if hasattr(const, "is_valid_batch"):
             assert torch.equal(const.is_valid_batch(qs), (v > 0).all(dim=1))
             assert const.is_valid_batch(qs[:0]).shape == (0,)
+
+
+@pytest.mark.parametrize("GUARD", [4096, 4099])       # 16-byte aligned outputs (TMA bulk stores) / misaligned (fallback stores)
+def test_outputs_stay_inside_their_buffers(pr2, GUARD):
+    """Canary test through the raw C ABI (compute-sanitizer is not available on the pool): every output sits in the middle
+    of a larger buffer pre-filled with a sentinel; after the launch the guard bands must be untouched and the payload fully
+    written, for batch sizes that leave ragged tiles and for TMA-stored as well as fallback-stored Jacobians."""
+    import ctypes as C
+
+    from skmp_b200 import _lib
+    from skmp_b200.constraint import CollFreeConst, PairWiseSelfCollFreeConst, PoseConstraint
+    from skmp_b200.robot.fetch import FetchConfig
+    from skmp_b200.robot.jaxon import JaxonConfig
+    from skmp_b200.robot.pr2 import PR2Config
+    from skmp_b200.robot_model import Fetch, Jaxon
+    from skmp_b200.sdf import Box, UnionSDF
+
+    torch = _torch()
+    L = _lib.lib()
+    SENT = -777.25
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+
+    def guarded(n_elems, dtype):
+        buf = torch.full((GUARD + n_elems + GUARD,), SENT, dtype=dtype, device="cuda")
+        return buf, buf[GUARD: GUARD + n_elems]
+
+    def check(buf, n_elems, what):
+        assert (buf[:GUARD] == SENT).all() and (buf[GUARD + n_elems:] == SENT).all(), what + ": guard band overwritten"
+        assert not (buf[GUARD: GUARD + n_elems] == SENT).any(), what + ": payload not fully written"
+
+    fetch = Fetch(); fetch.reset_pose()
+    jaxon = Jaxon(); jaxon.reset_manip_pose()
+    jk = JaxonConfig().get_collision_kin()
+    box = box_scene()
+    env = UnionSDF([Box([4.0, 4.0, 0.2], pos=[0.0, 0.0, -0.1]), Box([0.6, 1.0, 0.8], pos=[0.9, 0.0, 0.4])])
+    coll = [(CollFreeConst(PR2Config().get_collision_kin(), box.sdf, pr2), 7),            # TMA-aligned rows
+            (CollFreeConst(jk, env, jaxon), 37)]                                            # unaligned rows: fallback stores
+    g = torch.Generator("cuda").manual_seed(9)
+    for dtype, code in ((torch.float32, _lib.F32), (torch.float64, _lib.F64)):
+        for n in (1, 5, 131):
+            for const, d in coll:
+                plan, S = const._plan(), const.colkin.n_feature
+                q = ((torch.rand((n, d), generator=g, device="cuda") - 0.5) * 1.2).to(dtype)
+                for mode, m in ((_lib.MODE_ALL, S), (_lib.MODE_CLOSEST, 1)):
+                    vb, v = guarded(n * m, dtype)
+                    jb, j = guarded(n * m * d, dtype)
+                    _lib.check(L.skb_collfree(plan.handle, const.sdf.native(), code, ptr(q), n, 0.0, mode, ptr(v), ptr(j), None, st))
+                    torch.cuda.synchronize()
+                    check(vb, n * m, f"collfree values mode {mode} n {n}"); check(jb, n * m * d, f"collfree jac mode {mode} n {n}")
+                ob = torch.full((GUARD + n + GUARD,), 7, dtype=torch.uint8, device="cuda")
+                _lib.check(L.skb_collfree(plan.handle, const.sdf.native(), code, ptr(q), n, 0.0, _lib.MODE_ALL, None, None,
+                                          C.c_void_p(ob.data_ptr() + GUARD), st))
+                torch.cuda.synchronize()
+                assert (ob[:GUARD] == 7).all() and (ob[GUARD + n:] == 7).all() and (ob[GUARD: GUARD + n] <= 1).all()
+            pw = FetchConfig().get_pairwise_selcol_consts(fetch)
+            plan, P = pw._plan(), len(pw.check_sphere_id_pairs)
+            q = ((torch.rand((n, 8), generator=g, device="cuda") - 0.5) * 1.2).to(dtype)
+            vb, v = guarded(n * P, dtype); jb, j = guarded(n * P * 8, dtype)
+            _lib.check(L.skb_pairwise(plan.handle, code, ptr(q), n, _lib.MODE_ALL, ptr(v), ptr(j), None, st))
+            torch.cuda.synchronize()
+            check(vb, n * P, "pairwise values"); check(jb, n * P * 8, "pairwise jac")
+            ef = PR2Config().get_endeffector_kin()
+            ef.reflect_skrobot_model(pr2)
+            plan = ef.fksolver.get_plan(ef.tinyfk_feature_ids, ef.tinyfk_joint_ids, ef.base_type, ef.rot_type)
+            q = ((torch.rand((n, 7), generator=g, device="cuda") - 0.5) * 1.2).to(dtype)
+            vb, v = guarded(n * 6, dtype); jb, j = guarded(n * 6 * 7, dtype)
+            _lib.check(L.skb_fk(plan.handle, code, ptr(q), n, 1, ptr(v), ptr(j), st))
+            torch.cuda.synchronize()
+            check(vb, n * 6, "pose values"); check(jb, n * 6 * 7, "pose jac")
