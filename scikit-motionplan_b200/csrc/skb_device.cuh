@@ -234,39 +234,78 @@ __device__ __forceinline__ void build_level_records(int4 *lvrec, const int32_t *
     }
 }
 
+// Shared-window loads / stores by 32-bit address: the walk below keeps its lane-constant base addresses in registers and
+// every access is [base + offset], with no generic-pointer arithmetic for the compiler to re-materialise.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int4 lds_i4(uint32_t a) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int2 lds_i2(uint32_t a) {
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ Vec4<float> lds_v4(uint32_t a, float) {
+    Vec4<float> v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ Vec4<double> lds_v4(uint32_t a, double) {
+    Vec4<double> v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.z), "=d"(v.w) : "r"(a + 16u));
+    return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, const Vec4<float> &v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, const Vec4<double> &v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory");
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a + 16u), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ void lds_sc(uint32_t a, float &s, float &c) { asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(s), "=f"(c) : "r"(a)); }
+__device__ __forceinline__ void lds_sc(uint32_t a, double &s, double &c) { asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(s), "=d"(c) : "r"(a)); }
+__device__ __forceinline__ float lds_1(uint32_t a, float) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double lds_1(uint32_t a, double) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_1(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_1(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
 template <typename T, bool WITH_JAC, bool PAIR>
 __device__ __forceinline__ void fk_phase(const int lane, const int G, const int logG, const int slots3, const int g_live,
                                          const int D, const int n_levels, const int4 *lvrec, const int32_t *levelI,
                                          const Vec4<T> *nodeF, const T *wq, const T *wsc,
                                          T *wframes, const int fstride, T *wtw, const int tstride) {
     using V4 = Vec4<T>;
+    constexpr uint32_t ES = sizeof(T), VS = 4 * sizeof(T);     // element / 4-vector size in bytes
     const int row = lane % 3, t = lane / 3;
     const int cfg = t & (G - 1), slot = t >> logG;
     const bool act = slot < slots3;
-    // lane-constant quantities of the walk, made opaque so they are computed once per tile instead of being
-    // rematerialised inside the level loop
     int src1 = lane - row + (row == 2 ? 0 : row + 1), src2 = lane - row + (row == 0 ? 2 : row - 1);
-    asm volatile("" : "+r"(src1), "+r"(src2));
     const int ccfg = min(cfg, g_live - 1);          // dead configurations of a ragged last tile recompute a live one
-    const T *myq = wq + ccfg * D;
-    struct alignas(2 * sizeof(T)) SC { T s, c; };
-    const SC *mysc = reinterpret_cast<const SC *>(wsc + 2 * ccfg * D);
-    V4 *frr = reinterpret_cast<V4 *>(wframes + cfg * fstride) + row;          // this lane's row of every node frame
-    const V4 *nodeFr = nodeF + row;
-    T *twr = wtw + cfg * tstride + (PAIR ? 2 * row : row);
-    const int2 *levelI2 = reinterpret_cast<const int2 *>(levelI);
+    // lane-constant shared-window addresses, made opaque so that each is formed once per tile and held in a register
+    uint32_t a_lv = smem_addr(lvrec), a_lev = smem_addr(levelI), a_nodeF = smem_addr(nodeF);
+    uint32_t a_nodeFr = a_nodeF + row * VS;
+    uint32_t a_q = smem_addr(wq) + ccfg * D * ES, a_sc = smem_addr(wsc) + 2 * ccfg * D * ES;
+    uint32_t a_fr = smem_addr(wframes) + cfg * fstride * ES + row * VS;     // this lane's row of every node frame
+    uint32_t a_tw = smem_addr(wtw) + (cfg * tstride + (PAIR ? 2 * row : row)) * ES;
+    if (sizeof(T) == 4)      // the fp64 instantiations are register-bound: let the compiler re-derive there
+        asm volatile("" : "+r"(src1), "+r"(src2), "+r"(a_lv), "+r"(a_lev), "+r"(a_nodeF), "+r"(a_nodeFr), "+r"(a_q), "+r"(a_sc),
+                     "+r"(a_fr), "+r"(a_tw));
     for (int lv = 0; lv < n_levels; ++lv) {
-        const int2 lrec = levelI2[lv];                                      // {first entry of the level, count}
+        const int2 lrec = lds_i2(a_lev + 8u * lv);                          // {first entry of the level, count}
         const int lbeg = lrec.x, lcnt = lrec.y;
         for (int k0 = 0; k0 < lcnt; k0 += slots3) {
             const int k = k0 + slot;
             const bool on = act && k < lcnt;
-            const int4 rec = lvrec[lbeg + (on ? k : 0)];                    // {type, column, 3 parent, 3 node}
+            const int4 rec = lds_i4(a_lv + 16u * (lbeg + (on ? k : 0)));    // {type, column, 3 parent, 3 node}
             const int type = rec.x, col = rec.y, par3 = rec.z, node3 = rec.w;
-            V4 y = nodeFr[node3];
+            V4 y = lds_v4(a_nodeFr + node3 * VS, T());
             if (par3 >= 0) {
-                const V4 c0 = nodeF[node3], c1 = nodeF[node3 + 1], c2 = nodeF[node3 + 2];
-                const V4 P = frr[par3];
+                const uint32_t ac = a_nodeF + node3 * VS;
+                const V4 c0 = lds_v4(ac, T()), c1 = lds_v4(ac + VS, T()), c2 = lds_v4(ac + 2 * VS, T());
+                const V4 P = lds_v4(a_fr + par3 * VS, T());
                 y.x = P.x * c0.x + P.y * c1.x + P.z * c2.x;
                 y.y = P.x * c0.y + P.y * c1.y + P.z * c2.y;
                 y.z = P.x * c0.z + P.y * c1.z + P.z * c2.z;
@@ -277,22 +316,22 @@ __device__ __forceinline__ void fk_phase(const int lane, const int G, const int 
             const T w1 = __shfl_sync(0xffffffffu, y.z, src1), w2 = __shfl_sync(0xffffffffu, y.z, src2);
             T wr = T(0), vr = T(0);
             if (type == NODE_REVOLUTE) {
-                const SC sc = mysc[col];
-                const T s = sc.s, c = sc.c;
+                T s, c;
+                lds_sc(a_sc + 2 * col * ES, s, c);
                 wr = y.z;
                 vr = o1 * w2 - o2 * w1;                       // v = o x omega, component `row`
                 const T a = y.x, b = y.y;
                 y.x = c * a + s * b; y.y = c * b - s * a;
             } else if (type == NODE_PRISMATIC) {
                 vr = y.z;
-                y.w += myq[col] * y.z;
+                y.w += lds_1(a_q + col * ES, T()) * y.z;
             }
             if (on) {
-                frr[node3] = y;
+                sts_v4(a_fr + node3 * VS, y);
                 if (WITH_JAC && col >= 0) {
-                    T *t2 = PAIR ? twr + (col >> 1) * 12 + (col & 1) : twr + col * 8;
-                    t2[0] = wr;
-                    t2[PAIR ? 6 : 4] = vr;
+                    const uint32_t at = a_tw + (PAIR ? ((col >> 1) * 12 + (col & 1)) : col * 8) * ES;
+                    sts_1(at, wr);
+                    sts_1(at + (PAIR ? 6 : 4) * ES, vr);
                 }
             }
         }
