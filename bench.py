@@ -53,13 +53,19 @@ GRID_LB, GRID_UB, GRID_DIMS = np.array([-0.5, -1.5, 0.0]), np.array([1.5, 1.5, 2
 
 
 def grid_values_cpu(union) -> np.ndarray:
-    """128^3 fp32 samples of the union, evaluated by the CPU oracle (no GPU involved)."""
-    from oracle import oracle
-
+    """128^3 fp32 samples of the union of boxes, in plain numpy (scene generation only: neither the CUDA engine nor the
+    oracle is involved).  Box SDF: |max(|p| - h, 0)| + min(max_i(|p_i| - h_i), 0) in the box frame; union = min."""
     spacing = (GRID_UB - GRID_LB) / (np.array(GRID_DIMS) - 1)
     axes = [GRID_LB[i] + spacing[i] * np.arange(GRID_DIMS[i]) for i in range(3)]
     pts = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, 3)
-    return oracle.Sdf(union.primitives())(pts).reshape(GRID_DIMS).astype(np.float32)
+    best = np.full(len(pts), np.inf)
+    for kind, pos, rot, half in union.primitives():
+        assert kind == "box"
+        local = (pts - np.asarray(pos)) @ np.asarray(rot)            # R^T (p - pos), row-vector form
+        s = np.abs(local) - np.asarray(half)
+        d = np.linalg.norm(np.maximum(s, 0.0), axis=1) + np.minimum(s.max(axis=1), 0.0)
+        best = np.minimum(best, d)
+    return best.reshape(GRID_DIMS).astype(np.float32)
 
 
 def make_problem():
