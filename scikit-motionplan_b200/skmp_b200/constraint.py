@@ -36,9 +36,23 @@ from .tinyfk import BaseType, RotationType
 from .urdf import parse_urdf
 
 
+_CONST_CACHE: dict = {}
+
+
 def _to_kind(ref, arr: np.ndarray):
-    """numpy constant -> same array kind / dtype / device as ``ref``."""
+    """numpy constant -> same array kind / dtype / device as ``ref``.  Device copies of small constants (targets, bounds,
+    identity blocks) are cached by content: no host-to-device copy per call, and nothing a CUDA-graph capture of the
+    caller would have to record."""
     if _is_torch(ref):
+        arr = np.ascontiguousarray(arr)
+        if arr.nbytes <= 1 << 16:
+            key = (arr.tobytes(), arr.shape, str(arr.dtype), ref.dtype, str(ref.device))
+            t = _CONST_CACHE.get(key)
+            if t is None:
+                if len(_CONST_CACHE) > 256:
+                    _CONST_CACHE.clear()
+                t = _CONST_CACHE[key] = torch.as_tensor(arr, dtype=ref.dtype, device=ref.device)
+            return t
         return torch.as_tensor(arr, dtype=ref.dtype, device=ref.device)
     return arr
 

@@ -11,7 +11,7 @@ with a per-seed damping factor; violated inequality rows enter as hinge residual
 The success test is the reference's (:108-112): |e|^2 < acceptable_error, inequality rows valid, inside the box.
 Same public names: SatisfactionConfig, SatisfactionResult, satisfy_by_optimization(_with_budget); the batch entry
 point is satisfy_by_optimization_batch.  The step itself (normal equations, Cholesky, bound projection) is the CUDA
-kernel ``skb_lm_step`` (csrc/skb_lm.cu), one warp per seed.
+kernel ``skb_lm_step`` (csrc/skb_lm.cu), one warp per seed; a whole iteration is captured in a CUDA graph and replayed.
 """
 import time
 from dataclasses import dataclass
@@ -33,6 +33,7 @@ class SatisfactionConfig:
     n_seeds: int = 64
     ineq_weight: float = 30.0
     margin_numerical: float = 1e-6
+    use_cuda_graph: bool = True
 
 
 @dataclass
@@ -123,35 +124,61 @@ def satisfy_by_optimization_batch(eq_const: Optional[AbstractEqConst], box_const
 
     lam = torch.full((B,), 1e-2, dtype=f64, device=dev)
     r, J, eq_err, gmin = residuals(Q)
+    r, J, eq_err, gmin = r.clone(), J.contiguous().clone(), eq_err.clone(), gmin.clone()
     cost = (r * r).sum(dim=1)
     n_eval, n_iter = 1, 0
     done = torch.zeros(B, dtype=torch.bool, device=dev)
+    stalled = torch.zeros(B, dtype=torch.bool, device=dev)
     need_eq = eq_const is not None
+
     def finished():
         if need_eq:
             return (eq_err < config.acceptable_error) & (gmin > m)
         hinge_off = (r[:, D:] == 0).all(dim=1) if r.shape[1] > D else torch.ones_like(done)
         return (gmin > m) & hinge_off            # projection: feasible with every hinge term inactive
 
-    for n_iter in range(1, config.n_max_eval):
-        done = finished()
-        if bool(done.all()):
-            break
+    def iteration():
+        """One LM iteration on the persistent state, no host synchronisation (so it can be captured in a CUDA graph)."""
+        done.copy_(finished())
         Qn = _lm_step(J, r, lam, Q, lb, ub)      # CUDA: normal equations + Cholesky + bound projection, warp per seed
         Qn = torch.where(done[:, None], Q, Qn)
         rn, Jn, eq_n, gmin_n = residuals(Qn)
-        n_eval += 1
         cost_n = (rn * rn).sum(dim=1)
         better = (cost_n < cost) & ~done
-        stalled = ~better & ~done & (lam >= 1e6)
-        lam = torch.where(better, lam / 3.0, lam * 4.0).clamp(1e-9, 1e6)
-        Q = torch.where(better[:, None], Qn, Q)
-        r = torch.where(better[:, None], rn, r)
-        J = torch.where(better[:, None, None], Jn, J)
-        eq_err = torch.where(better, eq_n, eq_err)
-        gmin = torch.where(better, gmin_n, gmin)
-        cost = torch.where(better, cost_n, cost)
-        if bool((done | stalled).all()):
+        stalled.copy_(~better & ~done & (lam >= 1e6))
+        lam.copy_(torch.where(better, lam / 3.0, lam * 4.0).clamp(1e-9, 1e6))
+        Q.copy_(torch.where(better[:, None], Qn, Q))
+        r.copy_(torch.where(better[:, None], rn, r))
+        J.copy_(torch.where(better[:, None, None], Jn, J))
+        eq_err.copy_(torch.where(better, eq_n, eq_err))
+        gmin.copy_(torch.where(better, gmin_n, gmin))
+        cost.copy_(torch.where(better, cost_n, cost))
+
+    # The iteration is launch-bound (two constraint kernels, the LM step and a dozen element-wise updates on B x D data),
+    # so it is captured once in a CUDA graph and replayed; convergence is polled every CHECK replays.
+    CHECK = 8
+    graph = None
+    if config.use_cuda_graph:
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                iteration()                       # warm-up: lazy plan uploads, allocator pools
+                n_eval += 1
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                iteration()
+        except Exception:
+            graph = None                          # capture not possible (e.g. a host-side constraint): eager replays
+            torch.cuda.synchronize(dev)
+    n_iter = 1 if graph is not None else 0
+    while n_iter < config.n_max_eval - 1:
+        for _ in range(min(CHECK, config.n_max_eval - 1 - n_iter)):
+            graph.replay() if graph is not None else iteration()
+            n_iter += 1
+            n_eval += 1
+        if bool((finished() | stalled).all()):
             break
     ok_eq = eq_err < config.acceptable_error if need_eq else torch.ones_like(done)
     inside = ((Q >= lb) & (Q <= ub)).all(dim=1)
