@@ -48,12 +48,15 @@ def main():
     rng = np.random.default_rng(0)
     seeds = rng.uniform(size=(args.seeds, 7)) * (box_const.ub - box_const.lb) + box_const.lb
 
-    satisfy_by_optimization_batch(eq, box_const, ineq, seeds[:64])          # warm-up (plans, JIT-free but lazy uploads)
+    satisfy_by_optimization_batch(eq, box_const, ineq, seeds[:64])          # warm-up: plans, lazy uploads, module load
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    res = satisfy_by_optimization_batch(eq, box_const, ineq, seeds, SatisfactionConfig())
-    torch.cuda.synchronize()
-    gpu_s = time.perf_counter() - t0
+    times = []
+    for _ in range(3):                                                       # every call captures its own CUDA graph
+        t0 = time.perf_counter()
+        res = satisfy_by_optimization_batch(eq, box_const, ineq, seeds, SatisfactionConfig())
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    gpu_s = float(np.median(times))
 
     # ---- the reference algorithm on the CPU (oracle constraints + scipy SLSQP), sequential like the reference
     tree_c, feat_c, jl_c, base_c = oracle_args(colkin)
@@ -92,7 +95,7 @@ def main():
     print(json.dumps({
         "problem": "PR2 right-arm pose IK with box obstacle (tests/test_satisfy.py:22-53)",
         "gpu": {"seeds": args.seeds, "seconds": gpu_s, "seeds_per_s": args.seeds / gpu_s, "success_rate": float(res.success.mean()),
-                "solutions_per_s": float(res.success.sum()) / gpu_s, "iterations": res.n_iter, "constraint_evals": res.n_eval},
+                "solutions_per_s": float(res.success.sum()) / gpu_s, "iterations": res.n_iter, "constraint_evals": res.n_eval, "seconds_each_of_3_calls": times},
         "cpu_reference_algorithm": {"seeds": n_cpu, "seconds": cpu_s, "seeds_per_s": n_cpu / cpu_s, "success_rate": ok_cpu / n_cpu,
                                     "solutions_per_s": ok_cpu / cpu_s, "threads": 1,
                                     "what": "scipy SLSQP over the oracle's constraint values / Jacobians (fp64, FD gradient), sequential"},
