@@ -203,6 +203,29 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Pin this rank's host threads (and therefore its first-touch pinned buffers) to the NUMA node its GPU hangs on, so
+    that the D2H streams of several ranks do not all land in one socket's memory.  Best effort; returns a description."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text().strip())
+        if node < 0:
+            return f"gpu {bus}: no NUMA information"
+        cpus = []
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return f"gpu {bus} -> NUMA node {node}, {len(allowed)} cpus"
+    except Exception as e:      # pragma: no cover
+        return f"not bound ({type(e).__name__})"
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -216,6 +239,7 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -318,7 +342,7 @@ def run_b200(args):
                          "kernel_ms": kernel_ms, "kernel": "skb::s2_kernel<COLLFREE, grid-fast, VW2, u32, all, jac, NP<=8> (skb_sphere2.cu)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "configs/s", "h2d_bytes_per_step": n_e2e * D * 4, "d2h_bytes_per_step": n_e2e * (S + S * D) * 4,
-                    "steps": e2e_steps, "configs_per_step": n_e2e, "api": "CollFreeConst.evaluate(numpy (N,14) float32, with_jacobian=True) -> numpy", "check": chk},
+                    "steps": e2e_steps, "configs_per_step": n_e2e, "host_affinity_rank0": numa, "api": "CollFreeConst.evaluate(numpy (N,14) float32, with_jacobian=True) -> numpy", "check": chk},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
