@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -701,11 +702,13 @@ static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp) {
     // dynamic programme over "single" / "fused with the next half-round"
     std::vector<double> best(n_hr + 2, 0.0);
     std::vector<char> fuse(n_hr + 1, 0);
+    double c_s0 = 30.0, c_s1 = 17.0, c_f0 = 40.0, c_f1 = 29.0;      // issue-slot model of one half-round / one fused step
+    if (const char *e = getenv("SKB_S2_DP")) sscanf(e, "%lf,%lf,%lf,%lf", &c_s0, &c_s1, &c_f0, &c_f1);   // tuning knob
     for (int i = n_hr - 1; i >= 0; --i) {
-        const double single = 30.0 + 17.0 * npairs(hcm[i]) + best[i + 1];
+        const double single = c_s0 + c_s1 * npairs(hcm[i]) + best[i + 1];
         best[i] = single; fuse[i] = 0;
         if (i + 1 < n_hr) {
-            const double both = 40.0 + 29.0 * npairs(hcm[i] | hcm[i + 1]) + best[i + 2];
+            const double both = c_f0 + c_f1 * npairs(hcm[i] | hcm[i + 1]) + best[i + 2];
             if (both < single) { best[i] = both; fuse[i] = 1; }
         }
     }
