@@ -336,7 +336,7 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD.format(n=n), "configs_per_gpu": n, "spheres": S, "dof": D, "grid": "128^3 fp32",
                        "l2": "outputs (11.5 GB/step) and inputs (70 MB) exceed the 126 MB L2; no flush needed",
-                       "valid_fraction": valid_frac},
+                       "valid_fraction": valid_frac, "sphere_evals_per_s": value * S},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_config": BYTES_PER_CONFIG,
                          "kernel_ms": kernel_ms, "kernel": "skb::s2_kernel<COLLFREE, grid-fast, VW2, u32, all, jac, NP<=8> (skb_sphere2.cu)"},

@@ -171,6 +171,10 @@ SKB_API int skb_edge_samples(const double *q1_dev, const double *q2_dev, const d
                              void *stream);
 SKB_API int skb_segment_all(const uint8_t *valid_dev, const int64_t *offsets_dev, int64_t E, uint8_t *out_dev, void *stream);
 
+/* Measurement aid: FMA-pipe peak of the current device in TFLOP/s, the roofline denominator of the
+ * compute-bound modes (closest row, validity bytes).  kind 0: fp32 FFMA, 1: packed fma.rn.f32x2, 2: fp64 DFMA. */
+SKB_API int skb_fma_peak(int32_t kind, int32_t iters, double *tflops_out);
+
 /* ---------------------------------------------------------------- hot path (host pointers)
  * Same semantics with host buffers: what a numpy caller of the reference sees.  Chunked
  * H2D -> kernel -> D2H over internal streams; synchronous on return. */

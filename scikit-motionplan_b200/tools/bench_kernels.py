@@ -73,8 +73,10 @@ def workloads():
         qs = device_samples(kin, n, 8)
         P, D = len(const.check_sphere_id_pairs), kin.dim_cspace
         M = 1 if closest else P
+        S = kin.n_feature
+        flops = (126 * D + 18 * S + 8 * P + 17 * D) if closest else None
         return (lambda: const.evaluate(qs, True)), n, 4 * (D + M + M * D), \
-            f"Fetch PairWiseSelfCollFreeConst P={P} D={D}, {'closest' if closest else 'all pairs'} + Jacobian, N={n}"
+            f"Fetch PairWiseSelfCollFreeConst P={P} D={D}, {'closest' if closest else 'all pairs'} + Jacobian, N={n}", flops
     W["cfg2_all"] = lambda: cfg2(False, 1_000_000)
     W["cfg2_closest"] = lambda: cfg2(True, 1_000_000)
 
@@ -88,9 +90,11 @@ def workloads():
             return (lambda: const.evaluate(qs, True)), n, 4 * (D + S + S * D), f"PR2 dual arm vs 128^3 grid, all + Jacobian, N={n}"
         if mode == "closest":
             const = CollFreeConst(colkin, grid, pr2, only_closest_feature=True)
-            return (lambda: const.evaluate(qs, True)), n, 4 * (D + 1 + D), f"PR2 dual arm vs 128^3 grid, closest + Jacobian, N={n}"
+            return (lambda: const.evaluate(qs, True)), n, 4 * (D + 1 + D), f"PR2 dual arm vs 128^3 grid, closest + Jacobian, N={n}", \
+                126 * D + (18 + 60) * S + 17 * D
         const = CollFreeConst(colkin, grid, pr2)
-        return (lambda: const.is_valid_batch(qs)), n, 4 * D + 1, f"PR2 dual arm vs 128^3 grid, validity bytes, N={n}"
+        return (lambda: const.is_valid_batch(qs)), n, 4 * D + 1, f"PR2 dual arm vs 128^3 grid, validity bytes, N={n}", \
+            126 * D + (18 + 60) * S
     def cfg3_f64():
         pr2, colkin, grid = bench.make_problem()
         n = 400_000
@@ -135,7 +139,8 @@ def workloads():
         if mode == "valid":
             n = 10_000_000
             qs = device_samples(colkin, n, 11, scale=0.5); qs[:, 33] += 1.0
-            return (lambda: env.is_valid_batch(qs)), n, 4 * D + 1, f"JAXON 37-DoF env CollFreeConst validity bytes, N={n}"
+            return (lambda: env.is_valid_batch(qs)), n, 4 * D + 1, f"JAXON 37-DoF env CollFreeConst validity bytes, N={n}", \
+                126 * D + (18 + 2 * 40) * S
         n = 1_000_000
         qs = device_samples(colkin, n, 11, scale=0.5); qs[:, 33] += 1.0
         if mode == "all":
@@ -143,11 +148,13 @@ def workloads():
         if mode == "self_valid":
             selfc = PairWiseSelfCollFreeConst(colkin, jaxon, only_closest_feature=True)
             P = len(selfc.check_sphere_id_pairs)
-            return (lambda: selfc.is_valid_batch(qs)), n, 4 * D + 1, f"JAXON self collision P={P} validity bytes, N={n}"
+            return (lambda: selfc.is_valid_batch(qs)), n, 4 * D + 1, f"JAXON self collision P={P} validity bytes, N={n}", \
+                126 * D + 18 * S + 8 * P
         if mode == "self":
             selfc = PairWiseSelfCollFreeConst(colkin, jaxon, only_closest_feature=True)
             P = len(selfc.check_sphere_id_pairs)
-            return (lambda: selfc.evaluate(qs, True)), n, 4 * (D + 1 + D), f"JAXON self collision P={P} closest + Jacobian, N={n}"
+            return (lambda: selfc.evaluate(qs, True)), n, 4 * (D + 1 + D), f"JAXON self collision P={P} closest + Jacobian, N={n}", \
+                126 * D + 18 * S + 8 * P + 17 * D
         if mode == "edges":
             # RRT edge validity (BASELINE config 5): env + self collision over every interpolated sample of every edge
             from skmp_b200.batched import edge_samples_device, is_valid_motion_step_batch
@@ -187,13 +194,35 @@ def main():
         peak = float(json.loads(pp.read_text())["hbm_gbs"])
     W = workloads()
     names = [s for s in args.only.split(",") if s] or list(W)
+    # FMA-pipe peaks of this device (the denominator of the compute-bound modes), best of three
+    import ctypes
+
+    from skmp_b200 import _lib
+    torch.cuda.init()
+    fma = {}
+    for kind, key in ((0, "fp32_ffma"), (1, "fp32_ffma2"), (2, "fp64_dfma")):
+        t = ctypes.c_double(0.0)
+        best = 0.0
+        for _ in range(3):
+            _lib.check(_lib.lib().skb_fma_peak(kind, 4096 if kind < 2 else 256, ctypes.byref(t)))
+            best = max(best, t.value)
+        fma[key] = best
+    print(json.dumps({"workload": "fma_peak", "desc": "FMA-pipe micro-benchmark (skb_fma_peak), TFLOP/s", **fma}), flush=True)
     for name in names:
-        fn, n, bpc, desc = W[name]()
+        fn, n, bpc, desc, *rest = W[name]()
         mean_ms, min_ms, _ = timed(fn, args.reps)
         gbs = bpc * n / (mean_ms * 1e-3) / 1e9
-        print(json.dumps({"workload": name, "desc": desc, "configs": n, "ms": mean_ms, "ms_min": min_ms,
-                          "configs_per_s": n / (mean_ms * 1e-3), "bytes_per_config": bpc, "achieved_gbs": gbs,
-                          "hbm_peak_gbs": peak, "frac_of_hbm": gbs / peak}), flush=True)
+        rec = {"workload": name, "desc": desc, "configs": n, "ms": mean_ms, "ms_min": min_ms,
+               "configs_per_s": n / (mean_ms * 1e-3), "bytes_per_config": bpc, "achieved_gbs": gbs,
+               "hbm_peak_gbs": peak, "frac_of_hbm": gbs / peak}
+        if rest and rest[0]:
+            # compute-bound mode: algorithmic flop per configuration by SURVEY.md 8(d)'s count (126 per joint, 18 per sphere
+            # transform, 60 per trilinear / 40 per box SDF value + gradient, 8 per pair, 17 per column of the one Jacobian
+            # row); an upper bound on the work done, the validity modes stop at the first colliding step of a configuration
+            tf = rest[0] * n / (mean_ms * 1e-3) / 1e12
+            rec.update({"flop_per_config": rest[0], "achieved_tflops": tf, "fp32_peak_tflops": fma["fp32_ffma"],
+                        "frac_of_fp32": tf / fma["fp32_ffma"]})
+        print(json.dumps(rec), flush=True)
         del fn
         torch.cuda.empty_cache()
 
