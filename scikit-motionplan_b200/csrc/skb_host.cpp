@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <limits>
 
 #include "skb_internal.h"
 
@@ -799,6 +800,30 @@ static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp) {
                     Fv.push_back(l < cnt ? p->pair_thr[r] : 0.0);
                 }
     I[Q_F_TOTAL] = (int)Fv.size();
+    sp->I_lean.clear();
+    sp->masks.clear();
+    if (pairs) {
+        // lean program of the reducing modes: header, nodes, levels | node per centre | table P
+        std::vector<int32_t> &L = sp->I_lean;
+        L.assign(I.begin(), I.begin() + I[Q_TABB_I]);
+        L[Q_TABB_I] = L[Q_TABC_I] = 0;
+        L[Q_CENNODE_I] = (int)L.size();
+        for (int f = 0; f < nf; ++f) L.push_back(p->feat_node[f]);
+        while (L.size() % 4) L.push_back(0);
+        const int n_hr4 = (n_hr + 3) / 4 * 4;
+        L[Q_N_HR] = n_hr4;
+        L[Q_TABP_I] = (int)L.size();
+        const float ninf = -std::numeric_limits<float>::infinity();      // padding rows evaluate to +inf and never win
+        for (int r = 0; r < n_hr4 * 32; ++r) {
+            const float thr = r < rows ? (float)p->pair_thr[r] : ninf;
+            int32_t bits;
+            memcpy(&bits, &thr, 4);
+            L.push_back(r < rows ? (p->pair_idx[2 * r] | (p->pair_idx[2 * r + 1] << 16)) : 0);
+            L.push_back(bits);
+        }
+        L[Q_I_TOTAL] = (int)L.size();
+        for (int r = 0; r < rows; ++r) { sp->masks.push_back(plus[r]); sp->masks.push_back(minus[r]); }
+    }
     sp->n_nodes = n_nodes; sp->n_levels = n_levels; sp->rows = rows; sp->n_cen = pairs ? nf : 0;
     sp->frame_stride = odd_quads(n_nodes * 12);
     sp->supported = true;
@@ -809,6 +834,8 @@ static void free_s2(skb_s2_program &sp) {
     if (sp.dI) cudaFree(sp.dI);
     if (sp.dF32) cudaFree(sp.dF32);
     if (sp.dF64) cudaFree(sp.dF64);
+    if (sp.dI_lean) cudaFree(sp.dI_lean);
+    if (sp.dMasks) cudaFree(sp.dMasks);
     sp = skb_s2_program();
 }
 
@@ -826,6 +853,15 @@ const skb_s2_program *get_s2_program(skb_plan *p, int kind) {
             return nullptr;
         }
         if (upload_reals<float>(sp.F, &sp.dF32) != 0 || upload_reals<double>(sp.F, &sp.dF64) != 0) return nullptr;
+        if (!sp.I_lean.empty()) {
+            if (cudaMalloc(&sp.dI_lean, sp.I_lean.size() * sizeof(int32_t)) != cudaSuccess ||
+                cudaMemcpy(sp.dI_lean, sp.I_lean.data(), sp.I_lean.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMalloc(&sp.dMasks, sp.masks.size() * sizeof(uint64_t)) != cudaSuccess ||
+                cudaMemcpy(sp.dMasks, sp.masks.data(), sp.masks.size() * sizeof(uint64_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+                set_error("step program upload failed (lean pair tables)");
+                return nullptr;
+            }
+        }
     }
     return &sp;
 }

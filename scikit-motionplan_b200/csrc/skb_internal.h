@@ -165,6 +165,8 @@ enum QHdr {
     Q_NODE_F, Q_TABA_F, Q_CENA_F, Q_F_TOTAL,
     Q_THR_F,       // pairwise: (r_i + r_j)^2 per (step, half, lane) as a real (read by the fp64 kernel; fp32 packs it in table B)
     Q_TABC_I,      // pairwise with D > 32: int4 per (step, half, lane) {plus_mask_hi, minus_mask_hi, 0, 0}
+    Q_TABP_I,      // pairwise, lean program only: int2 per row {centre_i | centre_j << 16, float bits of (r_i + r_j)^2}
+    Q_N_HR,        // pairwise, lean program only: half-rounds of 32 rows in table P, padded to a multiple of 4
     QHDR_WORDS = 20
 };
 enum { S2_MAX_STEPS = 96 };
@@ -177,6 +179,12 @@ struct skb_s2_program {
     void *dI = nullptr;
     void *dF32 = nullptr;
     void *dF64 = nullptr;
+    // pairwise, reducing modes (closest row / validity byte): the "lean" program replaces lane tables B and C by the 8-byte
+    // table P (a third of the shared memory); the column masks of the one winning row come from `masks` in global memory
+    std::vector<int32_t> I_lean;
+    std::vector<uint64_t> masks;     // {plus, minus} per row
+    void *dI_lean = nullptr;
+    void *dMasks = nullptr;
     int n_nodes = 0, n_levels = 0, rows = 0, n_cen = 0;
     int frame_stride = 0;            // floats per configuration
     bool built = false, supported = false;

@@ -53,6 +53,7 @@ template <typename T>
 struct S2Params {
     const int32_t *I;
     const T *F;
+    const unsigned long long *pair_masks;                             // pairwise reducing modes: {plus, minus} per row
     const T *q;
     long long N;
     long long n_tiles;
@@ -410,6 +411,67 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                 if (cntB > 0) for (int c = 0; c < g_live; ++c) body(std::true_type{}, c);
                 else          for (int c = 0; c < g_live; ++c) body(std::false_type{}, c);
             }
+        } else if (KIND == KIND_PAIRWISE) {
+            // ---- per-configuration reduction over the pairs, lean form: an 8-byte table entry and two centre loads per
+            // pair, four half-rounds in flight; only the winning row's wrench and column masks are formed (afterwards)
+            const int2 *tabP = reinterpret_cast<const int2 *>(sI + sI[Q_TABP_I]);
+            const int n_hr = sI[Q_N_HR];
+            for (int c = 0; c < g_live; ++c) {
+                const long long n = n0 + c;
+                const V4 *cen = reinterpret_cast<const V4 *>(wcen + c * cstride);
+                auto pair_value = [&](const int row, V4 &xi, T &dx, T &dy, T &dz) -> T {
+                    const int2 P = tabP[row];
+                    xi = cen[P.x & 0xffff];
+                    const V4 xj = cen[(unsigned)P.x >> 16];
+                    dx = xi.x - xj.x; dy = xi.y - xj.y; dz = xi.z - xj.z;
+                    const T thr = sizeof(T) == 4 ? (T)__int_as_float(P.y) : (row < R ? tabThr[row] : -Rl::inf());
+                    return Rl::fma(dz, dz, Rl::fma(dy, dy, Rl::mul(dx, dx))) - thr;
+                };
+                T best = Rl::inf();
+                int bidx = 0x7fffffff;
+                for (int h = 0; h < n_hr; h += 4) {
+                    T v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        V4 xi;
+                        T dx, dy, dz;
+                        v[k] = pair_value((h + k) * 32 + lane, xi, dx, dy, dz);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (v[k] < best) { best = v[k]; bidx = (h + k) * 32 + lane; }
+                    // validity only: one pair at or below zero decides the configuration
+                    if (!JAC && prm.out_vals == nullptr && __any_sync(0xffffffffu, best <= T(0))) break;
+                }
+                T m = best; int mi = bidx;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const T x = __shfl_xor_sync(0xffffffffu, m, o);
+                    const int xi = __shfl_xor_sync(0xffffffffu, mi, o);
+                    if (x < m || (x == m && xi < mi)) { m = x; mi = xi; }
+                }
+                if (lane == 0) {
+                    if (prm.out_vals != nullptr) prm.out_vals[n] = m;
+                    if (prm.out_valid != nullptr) prm.out_valid[n] = m > T(0) ? 1 : 0;
+                }
+                if (JAC) {
+                    // the closest pair's row: g = 2 (x_i - x_j), m = x_i x g; columns of i's chain +, of j's chain -
+                    V4 xi;
+                    T dx, dy, dz, mx, my, mz;
+                    mi = mi < R ? mi : 0;                          // no row won (NaN input): any row, the values are NaN anyway
+                    pair_value(mi, xi, dx, dy, dz);
+                    const T gx = T(2) * dx, gy = T(2) * dy, gz = T(2) * dz;
+                    wrench_moment<T>(xi.x, xi.y, xi.z, gx, gy, gz, mx, my, mz);
+                    const unsigned long long pm = __ldg(prm.pair_masks + 2 * mi), mm = __ldg(prm.pair_masks + 2 * mi + 1);
+                    const T *tw = wtw + c * tstride;
+                    for (int col = lane; col < D; col += 32) {     // one lane per column of the single row
+                        const T *t2 = tw + (col >> 1) * 12 + (col & 1);
+                        T jv = dot6<T>(t2[0], t2[2], t2[4], t2[6], t2[8], t2[10], mx, my, mz, gx, gy, gz);
+                        jv = ((pm >> col) & 1) ? jv : (((mm >> col) & 1) ? -jv : T(0));
+                        prm.out_jac[n * D + col] = jv;
+                    }
+                }
+            }
         } else {
             // ---- per-configuration reduction: closest row (value, Jacobian row) and / or validity byte
             for (int c = 0; c < g_live; ++c) {
@@ -495,7 +557,9 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
                           cudaStream_t stream) {
     S2Params<T> prm;
     memset(&prm, 0, sizeof(prm));
-    prm.I = reinterpret_cast<const int32_t *>(sp->dI);
+    const bool lean = KIND == KIND_PAIRWISE && RED;      // reducing modes of the pairwise constraint run the lean program
+    prm.I = reinterpret_cast<const int32_t *>(lean ? sp->dI_lean : sp->dI);
+    prm.pair_masks = reinterpret_cast<const unsigned long long *>(sp->dMasks);
     prm.F = reinterpret_cast<const T *>(sizeof(T) == 4 ? sp->dF32 : sp->dF64);
     prm.q = reinterpret_cast<const T *>(q);
     prm.N = N;
@@ -505,7 +569,7 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
     prm.out_vals = reinterpret_cast<T *>(out_vals);
     prm.out_jac = reinterpret_cast<T *>(out_jac);
     prm.out_valid = out_valid;
-    prm.i_total = (int)sp->I.size();
+    prm.i_total = (int)(lean ? sp->I_lean.size() : sp->I.size());
     prm.f_total = sizeof(T) == 4 ? sp->I[Q_THR_F] : (int)sp->F.size();     // the fp64-only threshold table is the tail of F
     if (KIND == KIND_COLLFREE && host_prims) prm.prim0 = *reinterpret_cast<const DevPrim<T> *>(host_prims);
     if (KIND == KIND_COLLFREE && SDFK == SDF_GRID_FAST) {
