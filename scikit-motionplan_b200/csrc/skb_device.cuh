@@ -20,6 +20,7 @@ template <> struct Real<float> {
     static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }   // never contracted
     static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+    static __device__ __forceinline__ float max() { return __int_as_float(0x7f7fffff); }
 };
 template <> struct Real<double> {
     static __device__ __forceinline__ void sincos(double x, double *s, double *c) { ::sincos(x, s, c); }
@@ -32,6 +33,7 @@ template <> struct Real<double> {
     static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+    static __device__ __forceinline__ double max() { return __longlong_as_double(0x7fefffffffffffffLL); }
 };
 
 // Fixed-association building blocks of the chain rule.  Every kernel instantiation (all-spheres, closest, packed

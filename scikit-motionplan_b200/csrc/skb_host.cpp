@@ -813,7 +813,7 @@ static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp) {
         const int n_hr4 = (n_hr + 3) / 4 * 4;
         L[Q_N_HR] = n_hr4;
         L[Q_TABP_I] = (int)L.size();
-        const float ninf = -std::numeric_limits<float>::infinity();      // padding rows evaluate to +inf and never win
+        const float ninf = -std::numeric_limits<float>::max();           // padding rows evaluate to FLT_MAX: finite, never the minimum
         for (int r = 0; r < n_hr4 * 32; ++r) {
             const float thr = r < rows ? (float)p->pair_thr[r] : ninf;
             int32_t bits;

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) tree_kernel(const TreeParams<T> prm) {
                         T gx, gy, gz;
                         const T d = sdf_union<T>(sP, prm.n_prims, px, py, pz, gx, gy, gz);
                         const T val = d - fr[3] - prm.margin;
-                        vmin = val < vmin ? val : vmin;
+                        vmin = (val < vmin || val != val) ? val : vmin;      // NaN sticks (np.min)
                         // wrench of the unit "force" g applied at p: (p x g, g)
                         const T mx = py * gz - pz * gy, my = pz * gx - px * gz, mz = px * gy - py * gx;
                         if (!closest) {
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(256) tree_kernel(const TreeParams<T> prm) {
                     __syncwarp();
                 }
             }
-            if (prm.out_valid != nullptr && live) prm.out_valid[n] = (closest ? best : vmin) > T(0) ? 1 : 0;
+            if (prm.out_valid != nullptr && live) prm.out_valid[n] = vmin > T(0) ? 1 : 0;
         }
     }   // tiles
     if (WITH_JAC) bulk_wait_read<0>();   // shared memory must outlive the last bulk reads
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(128) pairwise_kernel(const PairParams<T> prm) 
             const T xj = wpos[(fj * 3 + 0) * 32], yj = wpos[(fj * 3 + 1) * 32], zj = wpos[(fj * 3 + 2) * 32];
             const T dx = xi - xj, dy = yi - yj, dz = zi - zj;
             const T val = dx * dx + dy * dy + dz * dz - sF[pair_f + pi];
-            vmin = val < vmin ? val : vmin;
+            vmin = (val < vmin || val != val) ? val : vmin;      // NaN sticks (np.min)
             if (closest) {
                 if (val < best) { best = val; best_pair = pi; }   // first index wins ties (np.argmin)
                 continue;

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
                               : SDFK == SDF_SINGLE    ? sdf_prim_world<T>(prm.prim0, px, py, pz, gx, gy, gz)
                                                       : sdf_union<T>(sP, prm.n_prims, px, py, pz, gx, gy, gz);
                     const T val = d - A.w - prm.margin;
-                    if (has) vmin = val < vmin ? val : vmin;
+                    if (has) vmin = (val < vmin || val != val) ? val : vmin;      // NaN sticks (np.min)
                     if (CLOSEST) {
                         // arg-min over spheres of sdf - radius, first index wins ties (np.argmin)
                         if (has && val < best) {
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
                 if (prm.out_valid != nullptr) {
                     T m = vmin;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) { const T x = __shfl_xor_sync(0xffffffffu, m, o); m = x < m ? x : m; }
+                    for (int o = 16; o > 0; o >>= 1) { const T x = __shfl_xor_sync(0xffffffffu, m, o); m = (x < m || x != x) ? x : m; }
                     if (lane == 0) prm.out_valid[n] = m > T(0) ? 1 : 0;
                 }
                 if (CLOSEST) {

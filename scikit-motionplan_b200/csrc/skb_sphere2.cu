@@ -424,10 +424,10 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                     xi = cen[P.x & 0xffff];
                     const V4 xj = cen[(unsigned)P.x >> 16];
                     dx = xi.x - xj.x; dy = xi.y - xj.y; dz = xi.z - xj.z;
-                    const T thr = sizeof(T) == 4 ? (T)__int_as_float(P.y) : (row < R ? tabThr[row] : -Rl::inf());
+                    const T thr = sizeof(T) == 4 ? (T)__int_as_float(P.y) : (row < R ? tabThr[row] : -Rl::max());
                     return Rl::fma(dz, dz, Rl::fma(dy, dy, Rl::mul(dx, dx))) - thr;
                 };
-                T best = Rl::inf();
+                T best = Rl::inf(), poison = T(0);          // poison: NaN once any row's value is NaN (np.min semantics)
                 int bidx = 0x7fffffff;
                 for (int h = 0; h < n_hr; h += 4) {
                     T v[4];
@@ -438,8 +438,10 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                         v[k] = pair_value((h + k) * 32 + lane, xi, dx, dy, dz);
                     }
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
+                    for (int k = 0; k < 4; ++k) {
+                        poison = Rl::fma(v[k], T(0), poison);
                         if (v[k] < best) { best = v[k]; bidx = (h + k) * 32 + lane; }
+                    }
                     // validity only: one pair at or below zero decides the configuration
                     if (!JAC && prm.out_vals == nullptr && __any_sync(0xffffffffu, best <= T(0))) break;
                 }
@@ -450,6 +452,8 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                     const int xi = __shfl_xor_sync(0xffffffffu, mi, o);
                     if (x < m || (x == m && xi < mi)) { m = x; mi = xi; }
                 }
+                const bool nan_cfg = __any_sync(0xffffffffu, poison != poison);
+                if (nan_cfg) m = poison + Rl::inf() * T(0);        // NaN on every lane
                 if (lane == 0) {
                     if (prm.out_vals != nullptr) prm.out_vals[n] = m;
                     if (prm.out_valid != nullptr) prm.out_valid[n] = m > T(0) ? 1 : 0;
@@ -468,7 +472,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                         const T *t2 = tw + (col >> 1) * 12 + (col & 1);
                         T jv = dot6<T>(t2[0], t2[2], t2[4], t2[6], t2[8], t2[10], mx, my, mz, gx, gy, gz);
                         jv = ((pm >> col) & 1) ? jv : (((mm >> col) & 1) ? -jv : T(0));
-                        prm.out_jac[n * D + col] = jv;
+                        prm.out_jac[n * D + col] = nan_cfg ? m : jv;
                     }
                 }
             }
@@ -476,7 +480,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
             // ---- per-configuration reduction: closest row (value, Jacobian row) and / or validity byte
             for (int c = 0; c < g_live; ++c) {
                 const long long n = n0 + c;
-                T best = Rl::inf();
+                T best = Rl::inf(), poison = T(0);          // poison: NaN once any row's value is NaN (np.min semantics)
                 int bidx = 0x7fffffff;
                 RowState<T, MaskT> brs;
                 brs.gx = brs.gy = brs.gz = brs.mx = brs.my = brs.mz = T(0); brs.pm = 0; brs.mm = 0;
@@ -491,6 +495,8 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                     const T va = front(c, Aa, tabB[slot * 32 + lane], slot, rsa);
                     T vb = Rl::inf();
                     if (cntB > 0) vb = front(c, Ab, tabB[slot_b * 32 + lane], slot_b, rsb);
+                    if (lane < cntA) poison = Rl::fma(va, T(0), poison);
+                    if (lane < cntB) poison = Rl::fma(vb, T(0), poison);
                     if (lane < cntA && va < best) { best = va; bidx = s0 + lane; brs = rsa; }
                     if (lane < cntB && vb < best) { best = vb; bidx = s0 + 32 + lane; brs = rsb; }
                     slot = slot_b + 1;
@@ -505,6 +511,8 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                     const int xi = __shfl_xor_sync(0xffffffffu, mi, o);
                     if (x < m || (x == m && xi < mi)) { m = x; mi = xi; }
                 }
+                const bool nan_cfg = __any_sync(0xffffffffu, poison != poison);
+                if (nan_cfg) m = poison + Rl::inf() * T(0);        // NaN on every lane
                 if (lane == 0) {
                     if (prm.out_vals != nullptr) prm.out_vals[n] = m;
                     if (prm.out_valid != nullptr) prm.out_valid[n] = m > T(0) ? 1 : 0;
@@ -520,7 +528,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const
                         const T *t2 = tw + (col >> 1) * 12 + (col & 1);
                         T jv = dot6<T>(t2[0], t2[2], t2[4], t2[6], t2[8], t2[10], mx, my, mz, gx, gy, gz);
                         jv = ((pm >> col) & 1) ? jv : (((mm >> col) & 1) ? -jv : T(0));
-                        prm.out_jac[n * D + col] = jv;
+                        prm.out_jac[n * D + col] = nan_cfg ? m : jv;
                     }
                 }
             }

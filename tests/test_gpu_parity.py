@@ -271,6 +271,70 @@ def test_pairwise_jaxon_floating_base_wide_masks():
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_nan_configuration_is_never_valid(pr2, dtype):
+    """A NaN joint value poisons its configuration like numpy does (np.min -> NaN, all(values > 0) -> False): the
+    closest value and its Jacobian row are NaN, the validity byte is 0, the neighbouring configurations are untouched."""
+    from skmp_b200.constraint import CollFreeConst
+    from skmp_b200.robot.pr2 import PR2Config
+
+    torch = _torch()
+    colkin = PR2Config().get_collision_kin()
+    box = box_scene()
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    q = torch.randn(97, 7, device="cuda", generator=torch.Generator("cuda").manual_seed(4)).to(tdt) * 0.3
+    bad = q.clone()
+    bad[11, 6] = float("nan")                                  # the wrist: only the gripper spheres depend on it
+    for closest in (False, True):
+        const = CollFreeConst(colkin, box.sdf, pr2, only_closest_feature=closest)
+        v0, j0 = const.evaluate(q, True)
+        v1, j1 = const.evaluate(bad, True)
+        keep = torch.ones(len(q), dtype=torch.bool, device="cuda"); keep[11] = False
+        assert torch.equal(v0[keep], v1[keep]) and torch.equal(j0[keep], j1[keep])
+        assert torch.isnan(v1[11]).any() and (not closest or torch.isnan(j1[11]).all())
+        ok = const.is_valid_batch(bad)
+        assert not bool(ok[11]) and torch.equal(ok[keep], const.is_valid_batch(q)[keep])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n_pairs", [1, 31, 32, 33, 128, 129, 700])
+def test_pairwise_reducing_modes_any_pair_count(dtype, n_pairs):
+    """The closest row / validity byte of an explicit pair list (robot/pr2.py:338-350 passes one) for pair counts around
+    the scan's 32-lane and 4-half-round granularity: bit-identical to min / argmin over the all-pairs launch, shuffled
+    pair order included (np.argmin: the first minimal row wins), and a NaN configuration stays NaN / invalid."""
+    from skmp_b200.constraint import PairWiseSelfCollFreeConst
+    from skmp_b200.robot.fetch import FetchConfig
+    from skmp_b200.robot_model import Fetch
+
+    torch = _torch()
+    fetch = Fetch(); fetch.reset_pose()
+    colkin = FetchConfig().get_collision_kin()
+    every = PairWiseSelfCollFreeConst(colkin, fetch).check_sphere_id_pairs
+    rng = np.random.default_rng(100 + n_pairs)
+    pick = rng.permutation(len(every))[:n_pairs]
+    id_pairs = [every[i] for i in pick]
+    if n_pairs > 2:
+        id_pairs[1] = id_pairs[0]                              # a duplicated pair: an exact tie, the lower row must win
+    full = PairWiseSelfCollFreeConst(colkin, fetch, id_pairs=id_pairs)
+    closest = PairWiseSelfCollFreeConst(colkin, fetch, id_pairs=id_pairs, only_closest_feature=True)
+    qs = torch.as_tensor(sample_q(colkin, 257, rng).astype(dtype), device="cuda")
+    v, j = full.evaluate(qs, True)
+    vc, jc = closest.evaluate(qs, True)
+    idx = v.argmin(dim=1)
+    if n_pairs > 2:
+        assert not (idx == 1).any()
+    assert torch.equal(vc[:, 0], v.min(dim=1).values)
+    assert torch.equal(jc[:, 0], j[torch.arange(len(qs), device="cuda"), idx])
+    vc2, _ = closest.evaluate(qs, False)
+    assert torch.equal(vc2, vc)
+    assert torch.equal(closest.is_valid_batch(qs), vc[:, 0] > 0)
+    bad = qs.clone()
+    bad[3] = float("nan")
+    vb, jb = closest.evaluate(bad, True)
+    assert torch.isnan(vb[3]).all() and torch.equal(vb[:3], vc[:3]) and torch.equal(vb[4:], vc[4:])
+    assert not bool(closest.is_valid_batch(bad)[3])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("with_forces", [False, True])
 def test_com_stability_jaxon(dtype, with_forces):
     """COMStabilityConst (skmp/constraint.py:845-931) and solve_com_fk against the oracle: JAXON 37-DoF floating base,
