@@ -663,7 +663,7 @@ const skb_sphere_program *get_sphere_program(skb_plan *p) {
 // Rows (spheres or pairs) are cut into half-rounds of 32; adjacent half-rounds are fused into one two-rows-per-lane
 // step when that is cheaper under a simple issue-slot model (a fused step loads each twist pair once for both rows
 // but computes the union of the two halves' column sets).
-static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp) {
+static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp, bool allow_fuse = true) {
     sp->built = true;
     sp->supported = false;
     const int n_nodes = (int)p->nodes.size(), nf = p->F, D = p->D;
@@ -708,11 +708,12 @@ static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp) {
     for (int i = n_hr - 1; i >= 0; --i) {
         const double single = c_s0 + c_s1 * npairs(hcm[i]) + best[i + 1];
         best[i] = single; fuse[i] = 0;
-        if (i + 1 < n_hr) {
+        if (allow_fuse && i + 1 < n_hr) {
             const double both = c_f0 + c_f1 * npairs(hcm[i] | hcm[i + 1]) + best[i + 2];
             if (both < single) { best[i] = both; fuse[i] = 1; }
         }
     }
+    sp->phase2_slots = best[0];
     sp->steps.clear();
     for (int i = 0; i < n_hr;) {
         skb_s2_step st;
@@ -836,7 +837,25 @@ static void free_s2(skb_s2_program &sp) {
     if (sp.dF64) cudaFree(sp.dF64);
     if (sp.dI_lean) cudaFree(sp.dI_lean);
     if (sp.dMasks) cudaFree(sp.dMasks);
+    if (sp.unfused) { free_s2(*sp.unfused); delete sp.unfused; }
     sp = skb_s2_program();
+}
+
+static int upload_s2(skb_s2_program &sp) {
+    if (cudaMalloc(&sp.dI, sp.I.size() * sizeof(int32_t)) != cudaSuccess ||
+        cudaMemcpy(sp.dI, sp.I.data(), sp.I.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+        sp.dI = nullptr;
+        return set_error("step program upload failed (no CUDA device?)");
+    }
+    if (upload_reals<float>(sp.F, &sp.dF32) != 0 || upload_reals<double>(sp.F, &sp.dF64) != 0) return -1;
+    if (!sp.I_lean.empty()) {
+        if (cudaMalloc(&sp.dI_lean, sp.I_lean.size() * sizeof(int32_t)) != cudaSuccess ||
+            cudaMemcpy(sp.dI_lean, sp.I_lean.data(), sp.I_lean.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMalloc(&sp.dMasks, sp.masks.size() * sizeof(uint64_t)) != cudaSuccess ||
+            cudaMemcpy(sp.dMasks, sp.masks.data(), sp.masks.size() * sizeof(uint64_t), cudaMemcpyHostToDevice) != cudaSuccess)
+            return set_error("step program upload failed (lean pair tables)");
+    }
+    return 0;
 }
 
 const skb_s2_program *get_s2_program(skb_plan *p, int kind) {
@@ -846,20 +865,15 @@ const skb_s2_program *get_s2_program(skb_plan *p, int kind) {
     if (!sp.built && build_s2_program(p, kind, &sp) != 0) return nullptr;
     if (!sp.supported) return nullptr;
     if (!sp.dI) {
-        if (cudaMalloc(&sp.dI, sp.I.size() * sizeof(int32_t)) != cudaSuccess ||
-            cudaMemcpy(sp.dI, sp.I.data(), sp.I.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
-            set_error("step program upload failed (no CUDA device?)");
-            sp.dI = nullptr;
-            return nullptr;
-        }
-        if (upload_reals<float>(sp.F, &sp.dF32) != 0 || upload_reals<double>(sp.F, &sp.dF64) != 0) return nullptr;
-        if (!sp.I_lean.empty()) {
-            if (cudaMalloc(&sp.dI_lean, sp.I_lean.size() * sizeof(int32_t)) != cudaSuccess ||
-                cudaMemcpy(sp.dI_lean, sp.I_lean.data(), sp.I_lean.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
-                cudaMalloc(&sp.dMasks, sp.masks.size() * sizeof(uint64_t)) != cudaSuccess ||
-                cudaMemcpy(sp.dMasks, sp.masks.data(), sp.masks.size() * sizeof(uint64_t), cudaMemcpyHostToDevice) != cudaSuccess) {
-                set_error("step program upload failed (lean pair tables)");
-                return nullptr;
+        if (upload_s2(sp) != 0) return nullptr;
+        bool fused = false;
+        for (auto &st : sp.steps) fused = fused || st.cntB > 0;
+        if (fused && getenv("SKB_S2_NO_UNFUSED") == nullptr) {
+            sp.unfused = new skb_s2_program();
+            if (build_s2_program(p, kind, sp.unfused, false) != 0 || !sp.unfused->supported || upload_s2(*sp.unfused) != 0) {
+                free_s2(*sp.unfused);
+                delete sp.unfused;
+                sp.unfused = nullptr;
             }
         }
     }

@@ -187,6 +187,10 @@ struct skb_s2_program {
     void *dMasks = nullptr;
     int n_nodes = 0, n_levels = 0, rows = 0, n_cen = 0;
     int frame_stride = 0;            // floats per configuration
+    double phase2_slots = 0;         // issue-slot model of the steps of one configuration (the planner's cost)
+    // the same rows without fused steps: half the staging block per warp, i.e. more resident warps when shared memory
+    // limits the occupancy (wide rows, deep trees); the launcher scores both and takes the better one
+    skb_s2_program *unfused = nullptr;
     bool built = false, supported = false;
 };
 

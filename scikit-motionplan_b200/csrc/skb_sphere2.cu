@@ -19,6 +19,9 @@
 // Sphere centres, frames, twists and SDF gradients never touch HBM.
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -559,11 +562,21 @@ static int sm_count_cached() {
     return sms;
 }
 
-template <typename T, int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX = 1>
-static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const void *q, int64_t N, const void *dev_prims,
-                          const void *host_prims, int n_prims, double margin, void *out_vals, void *out_jac, uint8_t *out_valid,
-                          cudaStream_t stream) {
+// One candidate launch of a step program: kernel parameters, shared-memory layout, (G, warps per CTA, CTAs per SM) and the
+// score that picked them.
+template <typename T>
+struct S2Launch {
     S2Params<T> prm;
+    int G = 0, warps = 0, per_sm = 0;
+    size_t smem = 0;
+    double score = -1.0;
+};
+
+template <typename T, int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX>
+static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void *q, int64_t N, const void *dev_prims,
+                        const void *host_prims, int n_prims, double margin, void *out_vals, void *out_jac, uint8_t *out_valid,
+                        S2Launch<T> &L) {
+    S2Params<T> &prm = L.prm;
     memset(&prm, 0, sizeof(prm));
     const bool lean = KIND == KIND_PAIRWISE && RED;      // reducing modes of the pairwise constraint run the lean program
     prm.I = reinterpret_cast<const int32_t *>(lean ? sp->dI_lean : sp->dI);
@@ -596,6 +609,7 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
     prm.D = D; prm.NP = NP; prm.R = R; prm.n_steps = (int)sp->steps.size(); prm.n_levels = sp->n_levels; prm.n_cen = sp->n_cen;
     const int al = 16 / (int)sizeof(T);          // elements of T per 16 bytes
     prm.copy_vec = (((long long)R * D) % al == 0 && reinterpret_cast<uintptr_t>(out_jac) % 16 == 0) ? 1 : 0;
+    int stage_rows = 32;                         // a program without fused steps stages one half-round
     for (int s = 0; s < prm.n_steps; ++s) {
         prm.steps[s] = sp->steps[s];
         unsigned long long pact = 0;            // the kernel wants pair-activity bits, not column bits
@@ -603,6 +617,7 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
         prm.steps[s].cm = pact;
         const int len = (sp->steps[s].cntA + sp->steps[s].cntB) * D;
         if ((sp->steps[s].s0 * D) % al != 0 || len % al != 0) prm.copy_vec = 0;
+        if (sp->steps[s].cntB > 0) stage_rows = 64;
     }
     prm.off_F = align_up(prm.i_total * 4, 16);
     prm.off_prims = align_up(prm.off_F + prm.f_total * (int)sizeof(T), 16);
@@ -620,7 +635,7 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
         prm.woff_frames = e; e += g * prm.fstride;
         prm.woff_tw = e;     e += JAC ? g * prm.tstride : 0;
         prm.woff_cen = e;    e += g * prm.cstride;
-        prm.woff_stage = e;  e += (JAC && !RED) ? align_up(64 * D, al) : 0;
+        prm.woff_stage = e;  e += (JAC && !RED) ? align_up(stage_rows * D, al) : 0;
         prm.warp_elems = align_up(e, al);
         return (size_t)prm.off_warp + (size_t)warps * prm.warp_elems * sizeof(T);
     };
@@ -629,18 +644,17 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
     // candidate is scored with a small issue-slot model:  (resident warps)^0.75 / (FK slots + phase-2 slots per
     // configuration);  the occupancy comes from the runtime (registers and shared memory).
     auto kern = s2_kernel<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>;
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
     static const int cand[][2] = {{8, 8}, {8, 6}, {8, 4}, {4, 8}, {4, 7}, {4, 6}, {4, 4}, {2, 8}, {2, 6}, {2, 4}, {1, 8}, {1, 6}, {1, 4}, {1, 2}, {1, 1}};
     int halves = 0;
     for (auto &st : sp->steps) halves += st.cntB > 0 ? 2 : 1;
+    const double phase2 = (JAC && !RED) ? sp->phase2_slots : (RED ? 40.0 : 150.0) * halves;
     auto fk_slots = [&](int g) {
         const int s3 = 32 / (3 * g);
         double it = 0;
         for (int lv = 0; lv < sp->n_levels; ++lv) it += (sp->I[sp->I[Q_LEVEL_I] + 2 * lv + 1] + s3 - 1) / s3;
         return 90.0 * it / g;
     };
-    int G = 0, warps = 0, per_sm = 0;
-    double best_score = -1.0;
+    L.G = 0; L.score = -1.0;
     for (auto &c : cand) {
         if (p->tune_chunk > 0 && c[0] != p->tune_chunk) continue;
         if (p->tune_warps > 0 && c[1] != p->tune_warps) continue;
@@ -649,19 +663,46 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c[1] * 32, sm) != cudaSuccess || occ < 1) continue;
         if (p->tune_ctas > 0) occ = std::min(occ, p->tune_ctas);
-        const double score = std::pow((double)std::min(c[1] * occ, 48), 0.75) / (fk_slots(c[0]) + (RED ? 40.0 : 150.0) * halves);
-        if (score > best_score * 1.0001) { best_score = score; G = c[0]; warps = c[1]; per_sm = occ; }
+        const double score = std::pow((double)std::min(c[1] * occ, 48), 0.75) / (fk_slots(c[0]) + phase2);
+        if (score > L.score * 1.0001) { L.score = score; L.G = c[0]; L.warps = c[1]; L.per_sm = occ; }
     }
-    if (G == 0) return set_error("step kernel: shared-memory footprint exceeds 227 KB");
-    const size_t smem = layout(G, warps);
-    prm.G = G;
+    if (L.G == 0) return set_error("step kernel: shared-memory footprint exceeds 227 KB");
+    L.smem = layout(L.G, L.warps);
+    prm.G = L.G;
     prm.logG = 0;
-    while ((1 << prm.logG) < G) ++prm.logG;
-    prm.slots3 = 32 / (3 * G);
-    prm.n_tiles = (N + G - 1) / G;
-    const long long want = (prm.n_tiles + warps - 1) / warps;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count_cached() * per_sm));
-    kern<<<grid, warps * 32, smem, stream>>>(prm);
+    while ((1 << prm.logG) < L.G) ++prm.logG;
+    prm.slots3 = 32 / (3 * L.G);
+    prm.n_tiles = (N + L.G - 1) / L.G;
+    return 0;
+}
+
+template <typename T, int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX = 1>
+static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const void *q, int64_t N, const void *dev_prims,
+                          const void *host_prims, int n_prims, double margin, void *out_vals, void *out_jac, uint8_t *out_valid,
+                          cudaStream_t stream) {
+    auto kern = s2_kernel<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    S2Launch<T> L;
+    if (configure_s2<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>(p, sp, q, N, dev_prims, host_prims, n_prims, margin, out_vals, out_jac,
+                                                                out_valid, L) != 0) return -1;
+    // the full-output modes may run the same rows without fused steps: half the staging block, more resident warps
+    if (JAC && !RED && sp->unfused != nullptr) {
+        S2Launch<T> U;
+        if (configure_s2<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>(p, sp->unfused, q, N, dev_prims, host_prims, n_prims, margin, out_vals,
+                                                                    out_jac, out_valid, U) == 0) {
+            static const bool verbose = getenv("SKB_S2_VERBOSE") != nullptr;
+            if (verbose)
+                fprintf(stderr, "[skb] step kernel: fused G=%d warps=%d ctas=%d smem=%zu score=%.5f | unfused G=%d warps=%d ctas=%d smem=%zu score=%.5f\n",
+                        L.G, L.warps, L.per_sm, L.smem, L.score, U.G, U.warps, U.per_sm, U.smem, U.score);
+            // measured: going from 12 to 18-20 resident warps pays (JAXON env +20 %, PR2 dual arm fp64 +10 %), from 24 to 28
+            // it does not (PR2 dual arm fp32 -4 %: the unfused steps' extra twist loads outweigh it), which the score's
+            // warps^0.75 term overrates -- so the occupancy gain must be substantial
+            if (U.score > L.score && 4 * U.warps * U.per_sm >= 5 * L.warps * L.per_sm) L = U;
+        }
+    }
+    const long long want = (L.prm.n_tiles + L.warps - 1) / L.warps;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count_cached() * L.per_sm));
+    kern<<<grid, L.warps * 32, L.smem, stream>>>(L.prm);
     CUDA_OK(cudaGetLastError());
     ++g_launch_count;
     return 0;
