@@ -36,7 +36,8 @@ namespace skb {
 
 #ifndef SKB_S2_THREADS
 #define SKB_S2_THREADS 256      // max threads per CTA
-#define SKB_S2_BLOCKS 3         // min CTAs per SM (register cap = 65536 / product)
+#define SKB_S2_BLOCKS 3         // min CTAs per SM (register cap = 65536 / product); the fp32 grid all-mode kernels take 4:
+                                // they fit 64 registers without spilling and run 2 % faster for it, the others spill
 #endif
 
 // Launch-time constants of the fp32 corner-packed grid with identity rotation (the cfg3 hot path), folded on the host:
@@ -155,7 +156,7 @@ template <typename T, typename MaskT> struct RowState {   // what phase 2 keeps 
 // NPMAX: compile-time bound on the number of column pairs (the Jacobian loop is fully unrolled against it, so twist
 // addresses and column bits become immediates)
 template <typename T, int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX>
-__global__ void __launch_bounds__(SKB_S2_THREADS, SKB_S2_BLOCKS) s2_kernel(const __grid_constant__ S2Params<T> prm) {
+__global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIND_COLLFREE && SDFK == SDF_GRID_FAST && JAC && !RED) ? 4 : SKB_S2_BLOCKS) s2_kernel(const __grid_constant__ S2Params<T> prm) {
     using V4 = Vec4<T>;
     using Rl = Real<T>;
     using P2 = Pair2<T>;
