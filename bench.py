@@ -275,9 +275,11 @@ def run_b200(args):
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
     evs[0].record()
+    torch.cuda.nvtx.range_push("timed")          # lets `ncu --nvtx --nvtx-include "timed/"` pick the timed launches
     for i in range(args.steps):
         step()
         evs[i + 1].record()
+    torch.cuda.nvtx.range_pop()
     barrier()
     launches = L.skb_launch_count() - launches0
     per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]

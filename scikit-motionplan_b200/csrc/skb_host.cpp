@@ -832,6 +832,7 @@ static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp, bool allo
 }
 
 static void free_s2(skb_s2_program &sp) {
+    s2_forget_program(&sp);
     if (sp.dI) cudaFree(sp.dI);
     if (sp.dF32) cudaFree(sp.dF32);
     if (sp.dF64) cudaFree(sp.dF64);

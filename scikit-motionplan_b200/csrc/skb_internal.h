@@ -272,6 +272,7 @@ int set_error(const std::string &msg);           // returns -1
 const skb_schedule *get_schedule(skb_plan *p, int rows);   // builds + uploads lazily; nullptr on error
 const skb_pair_program *get_pair_program(skb_plan *p);
 const skb_sphere_program *get_sphere_program(skb_plan *p);   // nullptr when the plan is not eligible (not an error)
+void s2_forget_program(const skb_s2_program *sp);              // skb_sphere2.cu: drops the autotuner's entries of a freed program
 const skb_s2_program *get_s2_program(skb_plan *p, int kind);   // KIND_COLLFREE / KIND_PAIRWISE; nullptr when not eligible
 const void *get_dev_prims(skb_sdf *s, int dtype);
 const void *get_host_prims(const skb_sdf *s, int dtype);   // valid after get_dev_prims succeeded for that dtype

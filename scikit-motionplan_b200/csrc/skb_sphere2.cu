@@ -26,7 +26,11 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
+#include <map>
+#include <mutex>
 #include <string>
+#include <tuple>
 #include <type_traits>
 
 #include "skb_device.cuh"
@@ -187,11 +191,15 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
     int4 *lvrec = reinterpret_cast<int4 *>(smem + prm.off_lv);
     build_level_records(lvrec, sI + sI[Q_NODE_I], sI + sI[Q_LEVELNODE_I], prm.n_nodes);
     __syncthreads();
-    const int4 *tabB = reinterpret_cast<const int4 *>(sI + sI[Q_TABB_I]);
+    // The lane tables A / B are read once per (tile, step).  The full-output collfree kernels read them from global memory
+    // (L1-resident, a few KB) and keep only the tree description in shared memory: the 5 KB they would take per CTA decide
+    // between 3 and 4 resident CTAs for a 14-DoF arm pair.
+    constexpr bool TAB_GLOBAL = KIND == KIND_COLLFREE && !RED;
+    const int4 *tabB = TAB_GLOBAL ? reinterpret_cast<const int4 *>(prm.I + sI[Q_TABB_I]) : reinterpret_cast<const int4 *>(sI + sI[Q_TABB_I]);
     const int4 *tabC = reinterpret_cast<const int4 *>(sI + sI[Q_TABC_I]);
     const int32_t *cenNode = sI + sI[Q_CENNODE_I];
     const V4 *nodeF = reinterpret_cast<const V4 *>(sF + sI[Q_NODE_F]);
-    const V4 *tabA = reinterpret_cast<const V4 *>(sF + sI[Q_TABA_F]);
+    const V4 *tabA = TAB_GLOBAL ? reinterpret_cast<const V4 *>(prm.F + sI[Q_TABA_F]) : reinterpret_cast<const V4 *>(sF + sI[Q_TABA_F]);
     const V4 *cenA = reinterpret_cast<const V4 *>(sF + sI[Q_CENA_F]);
     const T *tabThr = sF + sI[Q_THR_F];               // pairwise, fp64 only: (r_i + r_j)^2 per (step, half, lane)
     const int G = prm.G, logG = prm.logG;
@@ -220,6 +228,9 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
     for (long long tile = (long long)blockIdx.x * n_warps + warp; tile < prm.n_tiles; tile += tile_step) {
         const long long n0 = tile * G;
         const int g_live = (int)min((long long)G, prm.N - n0);
+        // the staging block shares its shared memory with the q / sin-cos scratch of phase 1: the last bulk store of the
+        // previous tile must have finished reading it
+        if (JAC && !RED && lane == 0) bulk_wait_read<0>();
         __syncwarp();
         // q tile + one fully populated sin/cos pass over all G*D joint values
 #pragma unroll
@@ -576,7 +587,7 @@ struct S2Launch {
 template <typename T, int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX>
 static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void *q, int64_t N, const void *dev_prims,
                         const void *host_prims, int n_prims, double margin, void *out_vals, void *out_jac, uint8_t *out_valid,
-                        S2Launch<T> &L) {
+                        S2Launch<T> &L, int force_g = 0, int force_w = 0) {
     S2Params<T> &prm = L.prm;
     memset(&prm, 0, sizeof(prm));
     const bool lean = KIND == KIND_PAIRWISE && RED;      // reducing modes of the pairwise constraint run the lean program
@@ -593,6 +604,10 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
     prm.out_valid = out_valid;
     prm.i_total = (int)(lean ? sp->I_lean.size() : sp->I.size());
     prm.f_total = sizeof(T) == 4 ? sp->I[Q_THR_F] : (int)sp->F.size();     // the fp64-only threshold table is the tail of F
+    if (KIND == KIND_COLLFREE && !RED) {        // lane tables stay in global memory: stage the tree description only
+        prm.i_total = sp->I[Q_TABB_I];
+        prm.f_total = sp->I[Q_TABA_F];
+    }
     if (KIND == KIND_COLLFREE && host_prims) prm.prim0 = *reinterpret_cast<const DevPrim<T> *>(host_prims);
     if (KIND == KIND_COLLFREE && SDFK == SDF_GRID_FAST) {
         const DevPrim<T> &pr = prm.prim0;
@@ -633,10 +648,12 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
         int e = 0;
         prm.woff_q = e;      e += align_up(g * D, al);
         prm.woff_sc = e;     e += align_up(2 * g * D, al);
+        // q / sin-cos are dead after phase 1, the staging block is written in phase 2 only: they share the head of the slab
+        const int stage_elems = (JAC && !RED) ? align_up(stage_rows * D, al) : 0;
+        prm.woff_stage = 0;  e = std::max(e, stage_elems);
         prm.woff_frames = e; e += g * prm.fstride;
         prm.woff_tw = e;     e += JAC ? g * prm.tstride : 0;
         prm.woff_cen = e;    e += g * prm.cstride;
-        prm.woff_stage = e;  e += (JAC && !RED) ? align_up(stage_rows * D, al) : 0;
         prm.warp_elems = align_up(e, al);
         return (size_t)prm.off_warp + (size_t)warps * prm.warp_elems * sizeof(T);
     };
@@ -645,7 +662,8 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
     // candidate is scored with a small issue-slot model:  (resident warps)^0.75 / (FK slots + phase-2 slots per
     // configuration);  the occupancy comes from the runtime (registers and shared memory).
     auto kern = s2_kernel<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>;
-    static const int cand[][2] = {{8, 8}, {8, 6}, {8, 4}, {4, 8}, {4, 7}, {4, 6}, {4, 4}, {2, 8}, {2, 6}, {2, 4}, {1, 8}, {1, 6}, {1, 4}, {1, 2}, {1, 1}};
+    static const int cand[][2] = {{8, 8}, {8, 6}, {8, 5}, {8, 4}, {8, 3}, {8, 2}, {4, 8}, {4, 7}, {4, 6}, {4, 5}, {4, 4}, {4, 3}, {4, 2},
+                                  {2, 8}, {2, 6}, {2, 5}, {2, 4}, {2, 3}, {2, 2}, {1, 8}, {1, 6}, {1, 4}, {1, 2}, {1, 1}};
     int halves = 0;
     for (auto &st : sp->steps) halves += st.cntB > 0 ? 2 : 1;
     const double phase2 = (JAC && !RED) ? sp->phase2_slots : (RED ? 40.0 : 150.0) * halves;
@@ -656,9 +674,13 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
         return 90.0 * it / g;
     };
     L.G = 0; L.score = -1.0;
+    static const int env_g = getenv("SKB_S2_G") ? atoi(getenv("SKB_S2_G")) : 0, env_w = getenv("SKB_S2_WARPS") ? atoi(getenv("SKB_S2_WARPS")) : 0;
+    const int want_g = force_g > 0 ? force_g : (p->tune_chunk > 0 ? p->tune_chunk : env_g);      // tuning knobs
+    const int want_w = force_w > 0 ? force_w : (p->tune_warps > 0 ? p->tune_warps : env_w);
     for (auto &c : cand) {
-        if (p->tune_chunk > 0 && c[0] != p->tune_chunk) continue;
-        if (p->tune_warps > 0 && c[1] != p->tune_warps) continue;
+        if (want_g > 0 && c[0] != want_g) continue;
+        if (want_w > 0 && c[1] != want_w) continue;
+        if (want_w == 0 && c[1] > 1 && (c[1] & 1)) continue;           // odd CTAs load the four sub-partitions unevenly: autotuner only
         const size_t sm = layout(c[0], c[1]);
         if (sm > smem_limit) continue;
         int occ = 0;
@@ -667,7 +689,7 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
         const double score = std::pow((double)std::min(c[1] * occ, 48), 0.75) / (fk_slots(c[0]) + phase2);
         if (score > L.score * 1.0001) { L.score = score; L.G = c[0]; L.warps = c[1]; L.per_sm = occ; }
     }
-    if (L.G == 0) return set_error("step kernel: shared-memory footprint exceeds 227 KB");
+    if (L.G == 0) return force_g > 0 ? -1 : set_error("step kernel: shared-memory footprint exceeds 227 KB");
     L.smem = layout(L.G, L.warps);
     prm.G = L.G;
     prm.logG = 0;
@@ -677,35 +699,131 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
     return 0;
 }
 
+// Launch-configuration cache of the autotuner: (program, kernel instantiation, output alignment class) -> choice.
+struct S2Choice { int unfused, G, warps; };
+static std::mutex g_tune_mu;
+static std::map<std::tuple<const void *, const void *, size_t, int>, S2Choice> g_tune;
+
+// a program that is freed (plan destroyed, pair list replaced) takes its tuned choices with it: its address may be reused
+void s2_forget_program(const skb_s2_program *sp) {
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    for (auto it = g_tune.begin(); it != g_tune.end();) it = std::get<0>(it->first) == (const void *)sp ? g_tune.erase(it) : std::next(it);
+}
+
 template <typename T, int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX = 1>
 static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const void *q, int64_t N, const void *dev_prims,
                           const void *host_prims, int n_prims, double margin, void *out_vals, void *out_jac, uint8_t *out_valid,
                           cudaStream_t stream) {
     auto kern = s2_kernel<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    S2Launch<T> L;
-    if (configure_s2<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>(p, sp, q, N, dev_prims, host_prims, n_prims, margin, out_vals, out_jac,
-                                                                out_valid, L) != 0) return -1;
-    // the full-output modes may run the same rows without fused steps: half the staging block, more resident warps
-    if (JAC && !RED && sp->unfused != nullptr) {
-        S2Launch<T> U;
-        if (configure_s2<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>(p, sp->unfused, q, N, dev_prims, host_prims, n_prims, margin, out_vals,
-                                                                    out_jac, out_valid, U) == 0) {
-            static const bool verbose = getenv("SKB_S2_VERBOSE") != nullptr;
-            if (verbose)
-                fprintf(stderr, "[skb] step kernel: fused G=%d warps=%d ctas=%d smem=%zu score=%.5f | unfused G=%d warps=%d ctas=%d smem=%zu score=%.5f\n",
-                        L.G, L.warps, L.per_sm, L.smem, L.score, U.G, U.warps, U.per_sm, U.smem, U.score);
-            // measured: going from 12 to 18-20 resident warps pays (JAXON env +20 %, PR2 dual arm fp64 +10 %), from 24 to 28
-            // it does not (PR2 dual arm fp32 -4 %: the unfused steps' extra twist loads outweigh it), which the score's
-            // warps^0.75 term overrates -- so the occupancy gain must be substantial
-            if (U.score > L.score && 4 * U.warps * U.per_sm >= 5 * L.warps * L.per_sm) L = U;
+    static const bool verbose = getenv("SKB_S2_VERBOSE") != nullptr;
+    auto configure = [&](const skb_s2_program *prog, int64_t n, S2Launch<T> &out, int fg, int fw) {
+        return configure_s2<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>(p, prog, q, n, dev_prims, host_prims, n_prims, margin, out_vals,
+                                                                       out_jac, out_valid, out, fg, fw);
+    };
+    auto launch = [&](const S2Launch<T> &L) {
+        const long long want = (L.prm.n_tiles + L.warps - 1) / L.warps;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count_cached() * L.per_sm));
+        kern<<<grid, L.warps * 32, L.smem, stream>>>(L.prm);
+        ++g_launch_count;
+    };
+    const bool has_alt = JAC && !RED && sp->unfused != nullptr;      // the same rows without fused steps (half the staging block)
+    // the issue-slot model's choice: the fused program unless the unfused one raises the resident warps substantially
+    auto heuristic = [&](int64_t n, S2Launch<T> &L, bool &alt) {
+        alt = false;
+        if (configure(sp, n, L, 0, 0) != 0) return -1;
+        if (has_alt) {
+            S2Launch<T> U;
+            if (configure(sp->unfused, n, U, 0, 0) == 0) {
+                if (verbose)
+                    fprintf(stderr, "[skb] step kernel: fused G=%d warps=%d ctas=%d smem=%zu score=%.5f | unfused G=%d warps=%d ctas=%d smem=%zu score=%.5f\n",
+                            L.G, L.warps, L.per_sm, L.smem, L.score, U.G, U.warps, U.per_sm, U.smem, U.score);
+                // measured: going from 12 to 18-20 resident warps pays (JAXON env +20 %, PR2 dual arm fp64 +10 %), from 24 to 28
+                // it does not (the unfused steps' extra twist loads outweigh it), which the score's warps^0.75 term overrates
+                if (U.score > L.score && 4 * U.warps * U.per_sm >= 5 * L.warps * L.per_sm) { L = U; alt = true; }
+            }
+        }
+        return 0;
+    };
+
+    // ---- autotuned choice.  Which (program, G, warps per CTA) is fastest depends on how CTAs and warps land on the SM
+    // sub-partitions, the L1 carve-out and the DRAM access pattern -- PR2 dual arm: 4 CTAs of 6 warps run at 0.70 of the
+    // HBM roofline, 3 CTAs of 8 warps (the same 24 resident warps) at 0.67, 4 CTAs of 7 warps at 0.65 -- which no
+    // occupancy model predicts.  So the first large launch of a (plan, kernel) pair times every feasible candidate on a
+    // slice of its own batch (every candidate writes bit-identical results) and later launches reuse the winner.
+    static const int tune_min = getenv("SKB_S2_AUTOTUNE_MIN") ? atoi(getenv("SKB_S2_AUTOTUNE_MIN")) : 65536;
+    static const bool autotune = getenv("SKB_S2_AUTOTUNE") == nullptr || atoi(getenv("SKB_S2_AUTOTUNE")) != 0;
+    const bool forced = p->tune_chunk > 0 || p->tune_warps > 0 || p->tune_ctas > 0 || getenv("SKB_S2_G") || getenv("SKB_S2_WARPS");
+    if (autotune && !forced) {
+        const auto key = std::make_tuple((const void *)sp, (const void *)kern, sp->I.size() * 131 + (size_t)sp->rows,
+                                         (int)(reinterpret_cast<uintptr_t>(out_jac) % 16 == 0) | (out_vals != nullptr ? 2 : 0) | (out_valid != nullptr ? 4 : 0));
+        S2Choice ch{-1, 0, 0};
+        {
+            std::lock_guard<std::mutex> lk(g_tune_mu);
+            auto it = g_tune.find(key);
+            if (it != g_tune.end()) ch = it->second;
+        }
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (ch.unfused < 0 && N < tune_min) ch.unfused = -2;           // too small to time: heuristic (a tuned choice is reused, though)
+        if (ch.unfused < 0 && (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)) ch.unfused = -2;   // no timing inside a capture
+        if (ch.unfused == -1) {
+            const int64_t n_try = std::min<int64_t>(N, 262144);
+            cudaEvent_t e0, e1;
+            CUDA_OK(cudaEventCreate(&e0));
+            CUDA_OK(cudaEventCreate(&e1));
+            static const int gs[] = {8, 4, 2, 1}, ws[] = {8, 7, 6, 5, 4, 3, 2};
+            float best_ms = 1e30f, model_ms = 1e30f;
+            S2Choice model{-1, 0, 0};                                    // what the issue-slot model would launch
+            {
+                S2Launch<T> H;
+                bool alt = false;
+                if (heuristic(n_try, H, alt) == 0) model = S2Choice{alt ? 1 : 0, H.G, H.warps};
+            }
+            for (int alt = 0; alt < (has_alt ? 2 : 1); ++alt)
+                for (int g : gs)
+                    for (int w : ws) {
+                        S2Launch<T> C;
+                        if (configure(alt ? sp->unfused : sp, n_try, C, g, w) != 0) continue;
+                        float ms = 1e30f;
+                        for (int rep = 0; rep < 2; ++rep) {             // first run warms the instruction cache and L2
+                            cudaEventRecord(e0, stream);
+                            launch(C);
+                            cudaEventRecord(e1, stream);
+                            if (cudaEventSynchronize(e1) != cudaSuccess) break;
+                            float t = 0.f;
+                            if (cudaEventElapsedTime(&t, e0, e1) == cudaSuccess) ms = std::min(ms, t);
+                        }
+                        if (verbose) fprintf(stderr, "[skb] autotune %s G=%d warps=%d ctas=%d: %.3f ms\n", alt ? "unfused" : "fused", g, w, C.per_sm, ms);
+                        if (ms < best_ms) { best_ms = ms; ch = S2Choice{alt, g, w}; }
+                        if (alt == model.unfused && g == model.G && w == model.warps) model_ms = ms;
+                    }
+            // timings of a 0.2 - 1 ms slice scatter by a few per cent: the model's choice stands unless it is clearly beaten
+            if (model.unfused >= 0 && best_ms > 0.97f * model_ms) ch = model;
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+            CUDA_OK(cudaGetLastError());
+            if (ch.unfused >= 0) {
+                std::lock_guard<std::mutex> lk(g_tune_mu);
+                g_tune[key] = ch;
+                if (verbose) fprintf(stderr, "[skb] autotune picked %s G=%d warps=%d\n", ch.unfused ? "unfused" : "fused", ch.G, ch.warps);
+            }
+        }
+        if (ch.unfused >= 0) {
+            S2Launch<T> L;
+            if (configure((ch.unfused && has_alt) ? sp->unfused : sp, N, L, ch.G, ch.warps) == 0) {
+                launch(L);
+                CUDA_OK(cudaGetLastError());
+                return 0;
+            }
         }
     }
-    const long long want = (L.prm.n_tiles + L.warps - 1) / L.warps;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count_cached() * L.per_sm));
-    kern<<<grid, L.warps * 32, L.smem, stream>>>(L.prm);
+
+    // ---- heuristic choice (small batches, stream capture, autotuning switched off)
+    S2Launch<T> L;
+    bool alt_unused = false;
+    if (heuristic(N, L, alt_unused) != 0) return -1;
+    launch(L);
     CUDA_OK(cudaGetLastError());
-    ++g_launch_count;
     return 0;
 }
 

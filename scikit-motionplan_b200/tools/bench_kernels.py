@@ -36,9 +36,11 @@ def timed(fn, reps, warmup=3):
     torch.cuda.synchronize()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
     evs[0].record()
+    torch.cuda.nvtx.range_push("timed")          # lets `ncu --nvtx --nvtx-include "timed/"` pick the timed launches
     for i in range(reps):
         out = fn()
         evs[i + 1].record()
+    torch.cuda.nvtx.range_pop()
     torch.cuda.synchronize()
     ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(reps)]
     return float(np.mean(ms)), float(np.min(ms)), out
