@@ -413,7 +413,9 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
                     }
                 };
 
-                if (JAC) {
+                // (a step whose rows touch every column pair between them rewrites its whole block per configuration:
+                // nothing to fill)
+                if (JAC && pact != (NP >= 32 ? 0xffffffffu : (1u << NP) - 1u)) {
                     // zero fill of the step's staging block, once per (tile, step): the columns no row of the step needs
                     // keep their structural zeros while the configurations of the tile pass through
                     if (lane == 0) bulk_wait_read<0>();
@@ -576,10 +578,17 @@ static int sm_count_cached() {
 
 // One candidate launch of a step program: kernel parameters, shared-memory layout, (G, warps per CTA, CTAs per SM) and the
 // score that picked them.
+// shared-memory carve-out (KB) the unified L1 / shared array takes for `bytes_per_sm` of resident CTAs (1 KB reserved each)
+static int carve_kb(size_t bytes_per_sm) {
+    static const int steps[] = {8, 16, 32, 64, 100, 132, 164, 196, 228};
+    for (int kb : steps) if (bytes_per_sm <= (size_t)kb * 1024) return kb;
+    return 1 << 20;
+}
+
 template <typename T>
 struct S2Launch {
     S2Params<T> prm;
-    int G = 0, warps = 0, per_sm = 0;
+    int G = 0, warps = 0, per_sm = 0, fstride = 0;
     size_t smem = 0;
     double score = -1.0;
 };
@@ -674,6 +683,18 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
         return 90.0 * it / g;
     };
     L.G = 0; L.score = -1.0;
+    // Frame stride of the FK walk: lane -> (row = lane % 3, configuration = lane / 3 % G) reads / writes the 16-byte row
+    // `3 node + row` of its configuration's frame block.  Eight consecutive lanes (one pass of a 128-bit shared-memory
+    // access) cover configurations c, c+1, c+2: with a stride of 3 (mod 8) quads their rows fall into eight different
+    // 16-byte bank groups (PR2 dual arm with the minimal odd stride of 45 quads: 8 wavefronts per parent-row load against
+    // 4 ideal, 5.6 against 2.9 for the frame store).  The padding is taken only where it is free: the unified L1 /
+    // shared-memory array is carved in steps (... 132, 164, 196, 228 KB), and 3 CTAs of 66.9 instead of 63.9 KB move the
+    // SM from the 196 KB to the 228 KB carve-out -- 28 instead of 60 KB of L1 for the voxel-grid gathers cost the full-output
+    // PR2 launch 7 %, far more than the conflicts.
+    const int fs_min = sp->frame_stride;
+    int fs_pad = fs_min / 4;
+    while (fs_pad % 8 != 3) ++fs_pad;
+    fs_pad *= 4;
     static const int env_g = getenv("SKB_S2_G") ? atoi(getenv("SKB_S2_G")) : 0, env_w = getenv("SKB_S2_WARPS") ? atoi(getenv("SKB_S2_WARPS")) : 0;
     const int want_g = force_g > 0 ? force_g : (p->tune_chunk > 0 ? p->tune_chunk : env_g);      // tuning knobs
     const int want_w = force_w > 0 ? force_w : (p->tune_warps > 0 ? p->tune_warps : env_w);
@@ -681,15 +702,26 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
         if (want_g > 0 && c[0] != want_g) continue;
         if (want_w > 0 && c[1] != want_w) continue;
         if (want_w == 0 && c[1] > 1 && (c[1] & 1)) continue;           // odd CTAs load the four sub-partitions unevenly: autotuner only
+        prm.fstride = fs_min;
         const size_t sm = layout(c[0], c[1]);
         if (sm > smem_limit) continue;
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, c[1] * 32, sm) != cudaSuccess || occ < 1) continue;
+        int fs = fs_min;
+        if (fs_pad != fs_min) {                 // the padded stride, when it is free (see above)
+            prm.fstride = fs_pad;
+            const size_t sm2 = layout(c[0], c[1]);
+            int occ2 = 0;
+            if (sm2 <= smem_limit && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, kern, c[1] * 32, sm2) == cudaSuccess &&
+                occ2 == occ && carve_kb(occ2 * (sm2 + 1024)) == carve_kb(occ * (sm + 1024)))
+                fs = fs_pad;
+        }
         if (p->tune_ctas > 0) occ = std::min(occ, p->tune_ctas);
         const double score = std::pow((double)std::min(c[1] * occ, 48), 0.75) / (fk_slots(c[0]) + phase2);
-        if (score > L.score * 1.0001) { L.score = score; L.G = c[0]; L.warps = c[1]; L.per_sm = occ; }
+        if (score > L.score * 1.0001) { L.score = score; L.G = c[0]; L.warps = c[1]; L.per_sm = occ; L.fstride = fs; }
     }
     if (L.G == 0) return force_g > 0 ? -1 : set_error("step kernel: shared-memory footprint exceeds 227 KB");
+    prm.fstride = L.fstride;
     L.smem = layout(L.G, L.warps);
     prm.G = L.G;
     prm.logG = 0;
