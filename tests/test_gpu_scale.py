@@ -81,6 +81,38 @@ def test_cfg3_pr2_dual_grid_full_shard():
     assert ej.max() < 2e-4
 
 
+def test_launch_autotuner_is_result_neutral():
+    """The first launch of >= 65 536 configurations of a plan times every (program, G, warps per CTA) candidate on a slice
+    of the caller's own buffers (`launch_s2_inst`, csrc/skb_sphere2.cu).  Whatever the candidates left behind, and the
+    tuned launch itself, must equal -- bit for bit -- what a separate plan computes with the model's configuration on
+    pieces too small to be tuned, in every mode."""
+    import bench
+    from skmp_b200.constraint import CollFreeConst
+
+    torch = _torch()
+    pr2, colkin, grid = bench.make_problem()
+    n = 70_001
+    qs = _device_samples(colkin, n, 11)
+    tuned = CollFreeConst(colkin, grid, pr2)
+    vals, jac = tuned.evaluate(qs, True)            # tunes on the first 70 001 rows
+    vals_b, jac_b = tuned.evaluate(qs, True)        # reuses the choice
+    assert torch.equal(vals, vals_b) and torch.equal(jac, jac_b)
+    valid = tuned.is_valid_batch(qs)
+    closest = CollFreeConst(colkin, grid, pr2, only_closest_feature=True)
+    vc, jc = closest.evaluate(qs, True)
+    # a second solver: its plans carry no tuned entry, and 9 973 rows per call stay below the tuning threshold
+    pr2_f, colkin_f, grid_f = bench.make_problem()
+    fresh = CollFreeConst(colkin_f, grid_f, pr2_f)
+    fresh_closest = CollFreeConst(colkin_f, grid_f, pr2_f, only_closest_feature=True)
+    for a in range(0, n, 9_973):
+        b = min(n, a + 9_973)
+        v, j = fresh.evaluate(qs[a:b], True)
+        assert torch.equal(v, vals[a:b]) and torch.equal(j, jac[a:b])
+        assert torch.equal(fresh.is_valid_batch(qs[a:b]), valid[a:b])
+        v, j = fresh_closest.evaluate(qs[a:b], True)
+        assert torch.equal(v, vc[a:b]) and torch.equal(j, jc[a:b])
+
+
 def test_cfg2_fetch_pairwise_1m():
     """Fetch 8-DoF PairWiseSelfCollFreeConst, 1 M configurations (closest mode at full size, all-pairs on a slice)."""
     from skmp_b200.robot.fetch import FetchConfig
