@@ -323,7 +323,14 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
                 // register instead of being re-read from the constant bank inside the unrolled loop
                 unsigned pact = (unsigned)prm.steps[st].cm;
                 asm volatile("" : "+r"(pact));
-                const int s0 = prm.steps[st].s0, cntA = prm.steps[st].cntA, cntB = prm.steps[st].cntB;
+                const int s0 = prm.steps[st].s0;
+                int cntA = prm.steps[st].cntA, cntB = prm.steps[st].cntB;
+                // opaque: read from the constant bank once per (tile, step), not before every use inside the configuration loop
+                if (sizeof(T) == 4) asm volatile("" : "+r"(cntA), "+r"(cntB));
+                // output addresses of the step, formed once per (tile, step): configuration c adds c * R (* D) to them
+                T *step_vals = tile_vals + (unsigned)(s0 + lane);
+                T *step_jac = JAC ? tile_jac + (unsigned)(s0 * D) : nullptr;
+                if (sizeof(T) == 4) asm volatile("" : "+l"(step_vals), "+l"(step_jac));
                 const int4 B0 = tabB[slot * 32 + lane];
                 const int4 B1 = tabB[(slot + (cntB > 0 ? 1 : 0)) * 32 + lane];
                 const int slotA = slot, slotB = slot + (cntB > 0 ? 1 : 0);
@@ -361,7 +368,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
                     T vb = T(0);
                     if (HAS_B) vb = front(c, A1, B1, slotB, rb);
                     if (prm.out_vals != nullptr) {
-                        T *gv = tile_vals + (unsigned)(c * R + s0 + lane);
+                        T *gv = step_vals + (unsigned)(c * R);
                         if (lane < cntA) st_stream(gv, va);
                         if (HAS_B && lane < cntB) st_stream(gv + 32, vb);
                     }
@@ -397,7 +404,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
                     }
                     // ship: the dense [rows][D] block is contiguous in HBM
                     const int len = (cntA + (HAS_B ? cntB : 0)) * D;
-                    T *g = tile_jac + (unsigned)((c * R + s0) * D);
+                    T *g = step_jac + (unsigned)(c * R * D);
                     if (prm.copy_vec) {
                         fence_async_smem();
                         __syncwarp();
