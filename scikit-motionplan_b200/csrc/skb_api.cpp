@@ -18,6 +18,29 @@ using namespace skb;
 
 static size_t esize(int dtype) { return dtype == SKB_F64 ? 8 : 4; }
 
+// A plan's program tables and an SDF's grids / primitive tables live on ONE device.  Launching with another device current
+// would hand that device foreign pointers (an illegal address at best), so every compute entry point checks first.
+namespace skb {
+int check_plan_device(const skb_plan *p, const char *who) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return set_error(std::string(who) + ": no CUDA device (there is no CPU fallback)");
+    if (dev != p->device)
+        return set_error(std::string(who) + ": the plan was created on cuda:" + std::to_string(p->device) + " but cuda:" +
+                         std::to_string(dev) + " is current (create one plan per device)");
+    return 0;
+}
+int check_sdf_device(skb_sdf *s, const char *who) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return set_error(std::string(who) + ": no CUDA device (there is no CPU fallback)");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->device < 0) s->device = dev;
+    if (dev != s->device)
+        return set_error(std::string(who) + ": the SDF lives on cuda:" + std::to_string(s->device) + " but cuda:" +
+                         std::to_string(dev) + " is current (create one SDF handle per device)");
+    return 0;
+}
+}  // namespace skb
+
 // ------------------------------------------------------------------ host pipeline scratch
 struct skb_stream_ctx {
     static const int NS = 3;
@@ -45,7 +68,7 @@ static int ensure_ctx(skb_plan *p, size_t bq, size_t bv, size_t bj, size_t bvali
         cap = need;
         return 0;
     };
-    // every host call returns with its streams drained, so nothing is in flight here
+    // every host call returns with its streams drained (also on failure) and holds p->host_mu, so nothing is in flight here
     if (grow(c->dq, c->cap_q, bq)) return -1;
     if (grow(c->dv, c->cap_v, bv)) return -1;
     if (grow(c->dj, c->cap_j, bj)) return -1;
@@ -72,6 +95,9 @@ template <typename Launch>
 static int host_pipeline(skb_plan *p, int dtype, const void *q_host, int64_t N, size_t vals_per_cfg, size_t jac_per_cfg,
                          void *out_vals, void *out_jac, uint8_t *out_valid, Launch launch) {
     if (N <= 0) return 0;
+    // one host call at a time per plan: the streams and the device scratch below belong to the plan (ctypes releases the
+    // GIL, so two Python threads can be here at once)
+    std::lock_guard<std::mutex> host_lock(p->host_mu);
     const size_t es = esize(dtype);
     const size_t per_cfg = (out_vals ? vals_per_cfg : 0) + (out_jac ? jac_per_cfg : 0) + (size_t)p->D;
     int64_t chunk = (int64_t)std::max<size_t>(1024, (48u << 20) / std::max<size_t>(1, per_cfg * es));
@@ -81,22 +107,31 @@ static int host_pipeline(skb_plan *p, int dtype, const void *q_host, int64_t N, 
                    out_valid ? (size_t)chunk : 0))
         return -1;
     skb_stream_ctx *c = p->hostpipe;
-    int k = 0;
-    for (int64_t n0 = 0; n0 < N; n0 += chunk, k = (k + 1) % skb_stream_ctx::NS) {
-        const int64_t n = std::min<int64_t>(chunk, N - n0);
-        cudaStream_t st = c->st[k];
-        CUDA_OK(cudaMemcpyAsync(c->dq[k], (const char *)q_host + n0 * p->D * es, n * p->D * es, cudaMemcpyHostToDevice, st));
-        if (launch(c->dq[k], n, out_vals ? c->dv[k] : nullptr, out_jac ? c->dj[k] : nullptr, out_valid ? c->dvalid[k] : nullptr, st))
-            return -1;
-        if (out_vals)
-            CUDA_OK(cudaMemcpyAsync((char *)out_vals + n0 * vals_per_cfg * es, c->dv[k], n * vals_per_cfg * es, cudaMemcpyDeviceToHost, st));
-        if (out_jac)
-            CUDA_OK(cudaMemcpyAsync((char *)out_jac + n0 * jac_per_cfg * es, c->dj[k], n * jac_per_cfg * es, cudaMemcpyDeviceToHost, st));
-        if (out_valid) CUDA_OK(cudaMemcpyAsync(out_valid + n0, c->dvalid[k], n, cudaMemcpyDeviceToHost, st));
-    }
     const int used = (int)std::min<int64_t>(skb_stream_ctx::NS, (N + chunk - 1) / chunk);     // a small batch touched one stream
-    for (int i = 0; i < used; ++i) CUDA_OK(cudaStreamSynchronize(c->st[i]));
-    return 0;
+    auto enqueue = [&]() -> int {
+        int k = 0;
+        for (int64_t n0 = 0; n0 < N; n0 += chunk, k = (k + 1) % skb_stream_ctx::NS) {
+            const int64_t n = std::min<int64_t>(chunk, N - n0);
+            cudaStream_t st = c->st[k];
+            CUDA_OK(cudaMemcpyAsync(c->dq[k], (const char *)q_host + n0 * p->D * es, n * p->D * es, cudaMemcpyHostToDevice, st));
+            if (launch(c->dq[k], n, out_vals ? c->dv[k] : nullptr, out_jac ? c->dj[k] : nullptr, out_valid ? c->dvalid[k] : nullptr, st))
+                return -1;
+            if (out_vals)
+                CUDA_OK(cudaMemcpyAsync((char *)out_vals + n0 * vals_per_cfg * es, c->dv[k], n * vals_per_cfg * es, cudaMemcpyDeviceToHost, st));
+            if (out_jac)
+                CUDA_OK(cudaMemcpyAsync((char *)out_jac + n0 * jac_per_cfg * es, c->dj[k], n * jac_per_cfg * es, cudaMemcpyDeviceToHost, st));
+            if (out_valid) CUDA_OK(cudaMemcpyAsync(out_valid + n0, c->dvalid[k], n, cudaMemcpyDeviceToHost, st));
+        }
+        return 0;
+    };
+    const int rc = enqueue();
+    // drained on success AND on failure: the caller owns its buffers again when this returns, and the next call may regrow
+    // the scratch
+    int sync_rc = 0;
+    for (int i = 0; i < used; ++i)
+        if (cudaStreamSynchronize(c->st[i]) != cudaSuccess && rc == 0 && sync_rc == 0)
+            sync_rc = set_error("host pipeline: stream synchronisation failed");
+    return rc != 0 ? rc : sync_rc;
 }
 
 extern "C" {
@@ -105,6 +140,7 @@ int skb_sdf_eval(const skb_sdf *s, int32_t dtype, const void *pts_dev, int64_t M
                  void *stream) {
     if (!s || !pts_dev || !out_vals_dev) return set_error("sdf_eval: bad arguments");
     if (s->prims.empty()) return set_error("sdf_eval: the SDF has no primitive");
+    if (check_sdf_device(const_cast<skb_sdf *>(s), "sdf_eval") != 0) return -1;
     const void *dp = get_dev_prims(const_cast<skb_sdf *>(s), dtype);
     if (!dp) return -1;
     return launch_sdf_eval(dp, (int)s->prims.size(), dtype, pts_dev, M, out_vals_dev, out_grads_dev, stream);
@@ -114,6 +150,7 @@ int skb_fk(const skb_plan *p, int32_t dtype, const void *q_dev, int64_t N, int32
            void *out_jac_dev, void *stream) {
     if (!p || N < 0 || (N > 0 && (!q_dev || !out_pts_dev))) return set_error("fk: bad arguments");
     if (N > 0 && with_jacobian && !out_jac_dev) return set_error("fk: with_jacobian set but out_jac is NULL");
+    if (check_plan_device(p, "fk") != 0) return -1;
     if (p->rot_type == SKB_ROT_IGNORE) {   // point features: lane-per-feature kernel (skb_sphere.cu)
         const skb_sphere_program *sp = get_sphere_program(const_cast<skb_plan *>(p));
         if (sp) return launch_sphere(p, sp, KIND_MAP, dtype, q_dev, N, nullptr, nullptr, 0, 0.0, SKB_MODE_ALL, out_pts_dev,
@@ -134,6 +171,7 @@ int skb_collfree(const skb_plan *p, const skb_sdf *s, int32_t dtype, const void 
     if (s->prims.empty()) return set_error("collfree: the SDF has no primitive");
     if (p->rot_type != SKB_ROT_IGNORE) return set_error("collfree: the plan must be built with rot_type IGNORE");
     if (s->prims.size() > 64) return set_error("collfree: more than 64 SDF primitives");
+    if (check_plan_device(p, "collfree") != 0 || check_sdf_device(const_cast<skb_sdf *>(s), "collfree") != 0) return -1;
     const void *dp = get_dev_prims(const_cast<skb_sdf *>(s), dtype);
     if (!dp) return -1;
     // full-output fp32 mode: the two-rows-per-lane step kernel (skb_sphere2.cu)
@@ -156,6 +194,7 @@ int skb_pairwise(const skb_plan *p, int32_t dtype, const void *q_dev, int64_t N,
     if (!p || N < 0 || (N > 0 && !q_dev)) return set_error("pairwise: bad arguments");
     if (mode != SKB_MODE_ALL && mode != SKB_MODE_CLOSEST) return set_error("pairwise: bad mode");
     if (!p->pairs_set) return set_error("pairwise: skb_plan_set_pairs was not called");
+    if (check_plan_device(p, "pairwise") != 0) return -1;
     if (mode == SKB_MODE_CLOSEST || !out_valid_dev || (!out_vals_dev && !out_jac_dev))
         if (const skb_s2_program *s2 = get_s2_program(const_cast<skb_plan *>(p), KIND_PAIRWISE))
             return launch_s2(p, s2, KIND_PAIRWISE, dtype, q_dev, N, nullptr, nullptr, 0, 0.0, mode, out_vals_dev, out_jac_dev,
@@ -171,9 +210,11 @@ int skb_com(const skb_plan *p, const skb_sdf *s, int32_t dtype, const void *q_de
     if (what != SKB_COM_POINT && what != SKB_COM_STABILITY) return set_error("com: bad `what`");
     const void *dp = nullptr;
     int n_prims = 0;
+    if (check_plan_device(p, "com") != 0) return -1;
     if (what == SKB_COM_STABILITY) {
         if (!s || s->prims.empty()) return set_error("com: the stability constraint needs an SDF");
         if (s->prims.size() > 64) return set_error("com: more than 64 SDF primitives");
+        if (check_sdf_device(const_cast<skb_sdf *>(s), "com") != 0) return -1;
         dp = get_dev_prims(const_cast<skb_sdf *>(s), dtype);
         if (!dp) return -1;
         n_prims = (int)s->prims.size();

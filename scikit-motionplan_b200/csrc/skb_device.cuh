@@ -119,7 +119,7 @@ __device__ __forceinline__ T grid_fetch(const void *grid, bool f64, int64_t idx)
     return (T)__ldg(reinterpret_cast<const float *>(grid) + idx);
 }
 
-// 32-byte gather of one cell's corner pack (sm_100: LDG.E.256, one L1 wavefront per lane)
+// 32-byte gather of one cell's coefficient pack (sm_100: LDG.E.256, one L1 wavefront per lane)
 __device__ __forceinline__ void ldg_cell(const float *p, float c[8]) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3]), "=f"(c[4]), "=f"(c[5]), "=f"(c[6]), "=f"(c[7])
@@ -129,6 +129,36 @@ __device__ __forceinline__ void ldg_cell(const double *p, double c[8]) {
     const double2 *q = reinterpret_cast<const double2 *>(p);
     const double2 a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + 2), e = __ldg(q + 3);
     c[0] = a.x; c[1] = a.y; c[2] = b.x; c[3] = b.y; c[4] = d.x; c[5] = d.y; c[6] = e.x; c[7] = e.y;
+}
+
+// Trilinear interpolant of one voxel cell as a POLYNOMIAL in the in-cell coordinates (fx, fy, fz) in [0, 1]:
+//     f = a0 + a1 fx + a2 fy + a3 fz + a4 fx fy + a5 fx fz + a6 fy fz + a7 fx fy fz
+// with a1 = c100 - c000, a4 = c110 - c100 - c010 + c000, ... formed in fp64 when the cell packs are expanded
+// (expand_cells_kernel, skb_sphere.cu).  Value and gradient are Horner evaluations: no difference of two interpolated
+// O(1 m) numbers is ever taken, so the fp32 gradient carries the rounding of its own (centimetre-sized) coefficients
+// instead of 1 ulp of the distance divided by the voxel size (the corner-lerp form lost 1e-5 relative there).
+// Explicit fma / no contraction: every kernel instantiation returns the same bits for the same point.
+// Returns the value; (gx, gy, gz) = d f / d (fx, fy, fz) (per cell unit -- the caller scales by 1 / spacing).
+template <typename T>
+__device__ __forceinline__ T trilinear_poly(const T a[8], T fx, T fy, T fz, T &gx, T &gy, T &gz) {
+    using R = Real<T>;
+    const T p = R::fma(fz, a[7], a[4]);                 // d2f / dfx dfy
+    const T r = R::fma(fx, a[7], a[6]);                 // d2f / dfy dfz
+    gx = R::fma(fz, a[5], R::fma(fy, p, a[1]));
+    gy = R::fma(fz, r, R::fma(fx, a[4], a[2]));
+    gz = R::fma(fy, r, R::fma(fx, a[5], a[3]));
+    const T t = R::fma(fz, a[6], a[2]);
+    return R::fma(fx, gx, R::fma(fy, t, R::fma(fz, a[3], a[0])));
+}
+// the same coefficients from the eight corner values (grids without cell packs): differences of neighbouring samples
+template <typename T>
+__device__ __forceinline__ void trilinear_coeffs(T c000, T c001, T c010, T c011, T c100, T c101, T c110, T c111, T a[8]) {
+    a[0] = c000;
+    a[1] = c100 - c000; a[2] = c010 - c000; a[3] = c001 - c000;
+    a[4] = (c110 - c100) - a[2];
+    a[5] = (c101 - c100) - a[3];
+    a[6] = (c011 - c010) - a[3];
+    a[7] = ((c111 - c110) - (c101 - c100)) - ((c011 - c010) - a[3]);
 }
 
 // trilinear voxel grid: value + analytic gradient; `fill`, zero gradient outside the sample box
@@ -146,37 +176,31 @@ __device__ __forceinline__ T sdf_grid_local(const DevPrim<T> &pr, T x, T y, T z,
     int iz = min((int)R::floor(uz), pr.dims[2] - 2);
     const T fx = ux - T(ix), fy = uy - T(iy), fz = uz - T(iz);
     const bool f64 = (pr.flags & PF_GRID_F64) != 0;
-    T c000, c001, c010, c011, c100, c101, c110, c111;
+    T a[8];
     if (pr.flags & PF_GRID_CELLS) {
         const int64_t cell = ((int64_t)ix * (pr.dims[1] - 1) + iy) * (pr.dims[2] - 1) + iz;
         if (f64) {
             double c[8];
             ldg_cell(reinterpret_cast<const double *>(pr.cells) + cell * 8, c);
-            c000 = (T)c[0]; c001 = (T)c[1]; c010 = (T)c[2]; c011 = (T)c[3]; c100 = (T)c[4]; c101 = (T)c[5]; c110 = (T)c[6]; c111 = (T)c[7];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = (T)c[k];
         } else {
             float c[8];
             ldg_cell(reinterpret_cast<const float *>(pr.cells) + cell * 8, c);
-            c000 = (T)c[0]; c001 = (T)c[1]; c010 = (T)c[2]; c011 = (T)c[3]; c100 = (T)c[4]; c101 = (T)c[5]; c110 = (T)c[6]; c111 = (T)c[7];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = (T)c[k];
         }
     } else {
         const int64_t sy = pr.dims[2], sx = (int64_t)pr.dims[1] * pr.dims[2];
         const int64_t b = ix * sx + iy * sy + iz;
-        c000 = grid_fetch<T>(pr.grid, f64, b); c001 = grid_fetch<T>(pr.grid, f64, b + 1);
-        c010 = grid_fetch<T>(pr.grid, f64, b + sy); c011 = grid_fetch<T>(pr.grid, f64, b + sy + 1);
-        c100 = grid_fetch<T>(pr.grid, f64, b + sx); c101 = grid_fetch<T>(pr.grid, f64, b + sx + 1);
-        c110 = grid_fetch<T>(pr.grid, f64, b + sx + sy); c111 = grid_fetch<T>(pr.grid, f64, b + sx + sy + 1);
+        trilinear_coeffs<T>(grid_fetch<T>(pr.grid, f64, b), grid_fetch<T>(pr.grid, f64, b + 1),
+                            grid_fetch<T>(pr.grid, f64, b + sy), grid_fetch<T>(pr.grid, f64, b + sy + 1),
+                            grid_fetch<T>(pr.grid, f64, b + sx), grid_fetch<T>(pr.grid, f64, b + sx + 1),
+                            grid_fetch<T>(pr.grid, f64, b + sx + sy), grid_fetch<T>(pr.grid, f64, b + sx + sy + 1), a);
     }
-    // lerp along x, then y, then z (same association as the oracle)
-    const T c00 = c000 + fx * (c100 - c000), c01 = c001 + fx * (c101 - c001);
-    const T c10 = c010 + fx * (c110 - c010), c11 = c011 + fx * (c111 - c011);
-    const T c0 = c00 + fy * (c10 - c00), c1 = c01 + fy * (c11 - c01);
-    const T val = c0 + fz * (c1 - c0);
-    const T dx0 = (c100 - c000) + fy * ((c110 - c010) - (c100 - c000));
-    const T dx1 = (c101 - c001) + fy * ((c111 - c011) - (c101 - c001));
-    gx = (dx0 + fz * (dx1 - dx0)) * pr.par[3];
-    const T dy0 = c10 - c00, dy1 = c11 - c01;
-    gy = (dy0 + fz * (dy1 - dy0)) * pr.par[4];
-    gz = (c1 - c0) * pr.par[5];
+    T hx, hy, hz;
+    const T val = trilinear_poly<T>(a, fx, fy, fz, hx, hy, hz);
+    gx = hx * pr.par[3]; gy = hy * pr.par[4]; gz = hz * pr.par[5];
     return val;
 }
 

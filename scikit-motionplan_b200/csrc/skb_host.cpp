@@ -18,7 +18,7 @@
 namespace skb {
 
 static thread_local std::string g_err;
-int64_t g_launch_count = 0;
+std::atomic<int64_t> g_launch_count{0};
 
 int set_error(const std::string &msg) {
     g_err = msg;
@@ -1096,6 +1096,7 @@ static int upload_prims(skb_sdf *s, void **dst) {
 const void *get_host_prims(const skb_sdf *s, int dtype) { return dtype == SKB_F32 ? (const void *)s->host_f32.data() : (const void *)s->host_f64.data(); }
 
 const void *get_dev_prims(skb_sdf *s, int dtype) {
+    std::lock_guard<std::mutex> lk(s->mu);
     if (s->dev_count != (int)s->prims.size()) {
         if (s->dev_f32) cudaFree(s->dev_f32);
         if (s->dev_f64) cudaFree(s->dev_f64);
@@ -1119,7 +1120,7 @@ extern "C" {
 
 int skb_version(void) { return 100; }
 const char *skb_last_error(void) { return g_err.c_str(); }
-int64_t skb_launch_count(void) { return g_launch_count; }
+int64_t skb_launch_count(void) { return g_launch_count.load(); }
 
 int skb_device_count(int32_t *out_count) {
     int n = 0;
@@ -1250,6 +1251,7 @@ int skb_sdf_add_grid(skb_sdf *s, const double pos[3], const double rot[9], const
     h.grid_is_f64 = values_dtype == SKB_F64;
     size_t count = (size_t)dims[0] * dims[1] * dims[2];
     h.grid_bytes = count * (h.grid_is_f64 ? 8 : 4);
+    if (check_sdf_device(s, "sdf_add_grid") != 0) return -1;     // the grid lives on the current device
     CUDA_OK(cudaMalloc(&h.dev_grid, h.grid_bytes));
     CUDA_OK(cudaMemcpy(h.dev_grid, host_values, h.grid_bytes, cudaMemcpyHostToDevice));
     // corner-packed copy: one 32-byte (fp32) gather per trilinear lookup instead of eight 4-byte ones.

@@ -6,6 +6,7 @@
 #include <vector>
 #include <map>
 #include <mutex>
+#include <atomic>
 
 #include "../../include/skmp_b200.h"
 
@@ -62,8 +63,8 @@ struct DevPrim {
     T rot[9];
     T par[8];            // box: half[3]; cyl: radius, half height; sphere: radius; grid: lb[3], inv_spacing[3], fill
     const void *grid;    // device pointer (float or double values), C order [nx][ny][nz]
-    const void *cells;   // device pointer or NULL: per-cell corner packs [(nx-1)][(ny-1)][(nz-1)][8]
-                         // {c000,c001,c010,c011,c100,c101,c110,c111} (cXYZ), same value type as `grid`
+    const void *cells;   // device pointer or NULL: per-cell polynomial packs [(nx-1)][(ny-1)][(nz-1)][8]
+                         // {a0 .. a7} of trilinear_poly (skb_device.cuh), same value type as `grid`
 };
 enum { PRIM_BOX = 0, PRIM_CYLINDER = 1, PRIM_SPHERE = 2, PRIM_GRID = 3 };
 enum { PF_IDENTITY = 1, PF_GRID_F64 = 2, PF_GRID_CELLS = 4 };
@@ -89,14 +90,15 @@ struct skb_host_prim {
     int32_t dims[3];
     double pos[3], rot[9], par[8];
     void *dev_grid = nullptr;
-    void *dev_cells = nullptr;       // corner-packed copy (one 32/64-byte gather per lookup), may be NULL
+    void *dev_cells = nullptr;       // per-cell polynomial packs (one 32/64-byte gather per lookup), may be NULL
     int32_t grid_is_f64 = 0;
     size_t grid_bytes = 0;
 };
 
 struct skb_sdf {
     std::vector<skb_host_prim> prims;
-    int device = -1;
+    int device = -1;                 // device that holds the grids / primitive tables (-1: nothing uploaded yet)
+    std::mutex mu;                   // guards the lazy uploads
     // device copies of the primitive table, built lazily per dtype
     void *dev_f32 = nullptr;
     void *dev_f64 = nullptr;
@@ -263,7 +265,8 @@ struct skb_plan {
     std::vector<int32_t> pair_idx;
     std::vector<double> pair_thr;
     skb_stream_ctx *hostpipe = nullptr;
-    std::mutex mu;
+    std::mutex mu;                   // guards the lazily built / uploaded programs
+    std::mutex host_mu;              // serialises the *_host entry points of one plan (they share its streams and scratch)
 };
 
 namespace skb {
@@ -304,6 +307,9 @@ int launch_s2(const skb_plan *p, const skb_s2_program *sp, int kind, int dtype, 
               void *stream);
 enum { KIND_MAP = 0, KIND_COLLFREE = 1, KIND_PAIRWISE = 2 };
 
-extern int64_t g_launch_count;
+extern std::atomic<int64_t> g_launch_count;
+// every compute entry point runs on the device its handles were created on (one handle per device; skb_api.cpp)
+int check_plan_device(const skb_plan *p, const char *who);
+int check_sdf_device(skb_sdf *s, const char *who);     // binds an SDF without device resources to the current device
 
 }  // namespace skb

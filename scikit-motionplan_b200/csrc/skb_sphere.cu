@@ -93,7 +93,7 @@ enum { SDF_UNION = 0,       // any union of primitives, table staged in shared m
        SDF_SINGLE = 1,      // one primitive of any type, constants read from the kernel parameters
        SDF_GRID_FAST = 2 }; // one fp32 corner-packed voxel grid with identity rotation (the cfg3 hot path)
 
-// fp32 corner-packed grid, identity rotation: same arithmetic (and rounding) as sdf_prim_world -> sdf_grid_local,
+// fp32 cell-packed grid, identity rotation: same polynomial evaluation as sdf_prim_world -> sdf_grid_local,
 // minus the type dispatch, rotation, value-type and 64-bit index generality.
 __device__ __forceinline__ float sdf_grid_fast(const DevPrim<float> &pr, float px, float py, float pz, float &gx, float &gy, float &gz) {
     const float ux = ((px - pr.pos[0]) - pr.par[0]) * pr.par[3], uy = ((py - pr.pos[1]) - pr.par[1]) * pr.par[4],
@@ -104,18 +104,11 @@ __device__ __forceinline__ float sdf_grid_fast(const DevPrim<float> &pr, float p
     const int ix = min((int)floorf(ux), pr.dims[0] - 2), iy = min((int)floorf(uy), pr.dims[1] - 2), iz = min((int)floorf(uz), pr.dims[2] - 2);
     const float fx = ux - float(ix), fy = uy - float(iy), fz = uz - float(iz);
     const unsigned cell = ((unsigned)ix * (unsigned)(pr.dims[1] - 1) + (unsigned)iy) * (unsigned)(pr.dims[2] - 1) + (unsigned)iz;
-    float c[8];
-    ldg_cell(reinterpret_cast<const float *>(pr.cells) + (size_t)cell * 8, c);
-    const float d00 = c[4] - c[0], d01 = c[5] - c[1], d10 = c[6] - c[2], d11 = c[7] - c[3];
-    const float c00 = c[0] + fx * d00, c01 = c[1] + fx * d01, c10 = c[2] + fx * d10, c11 = c[3] + fx * d11;
-    const float e0 = c10 - c00, e1 = c11 - c01;
-    const float c0 = c00 + fy * e0, c1 = c01 + fy * e1;
-    const float h = c1 - c0;
-    const float dx0 = d00 + fy * (d10 - d00), dx1 = d01 + fy * (d11 - d01);
-    gx = (dx0 + fz * (dx1 - dx0)) * pr.par[3];
-    gy = (e0 + fz * (e1 - e0)) * pr.par[4];
-    gz = h * pr.par[5];
-    return c0 + fz * h;
+    float a[8], hx, hy, hz;
+    ldg_cell(reinterpret_cast<const float *>(pr.cells) + (size_t)cell * 8, a);
+    const float val = trilinear_poly<float>(a, fx, fy, fz, hx, hy, hz);
+    gx = hx * pr.par[3]; gy = hy * pr.par[4]; gz = hz * pr.par[5];
+    return val;
 }
 template <typename T>
 __device__ __forceinline__ T sdf_grid_fast(const DevPrim<T> &pr, T px, T py, T pz, T &gx, T &gy, T &gz) {
@@ -397,7 +390,9 @@ __global__ void __launch_bounds__(SKB_LB_THREADS, SKB_LB_BLOCKS) sphere_kernel(c
     if (WITH_JAC && !CLOSEST) bulk_wait_read<0>();   // shared memory must outlive the last bulk reads
 }
 
-// ------------------------------------------------------------------ corner-pack expansion of a voxel grid
+// ------------------------------------------------------------------ cell-pack expansion of a voxel grid
+// Per cell the eight coefficients of its trilinear polynomial (trilinear_poly, skb_device.cuh), formed in fp64 from the
+// corner samples and rounded once to the grid's value type: 32 B (fp32) per cell, one LDG.256 per lookup.
 template <typename V>
 __global__ void expand_cells_kernel(const V *grid, int nx, int ny, int nz, V *cells) {
     const long long total = (long long)(nx - 1) * (ny - 1) * (nz - 1);
@@ -406,11 +401,15 @@ __global__ void expand_cells_kernel(const V *grid, int nx, int ny, int nz, V *ce
         const long long t = i / (nz - 1);
         const int iy = (int)(t % (ny - 1)), ix = (int)(t / (ny - 1));
         const long long sy = nz, sx = (long long)ny * nz, b = ix * sx + iy * sy + iz;
+        const double c000 = grid[b], c001 = grid[b + 1], c010 = grid[b + sy], c011 = grid[b + sy + 1];
+        const double c100 = grid[b + sx], c101 = grid[b + sx + 1], c110 = grid[b + sx + sy], c111 = grid[b + sx + sy + 1];
         V *o = cells + i * 8;
-        o[0] = grid[b];           o[1] = grid[b + 1];
-        o[2] = grid[b + sy];      o[3] = grid[b + sy + 1];
-        o[4] = grid[b + sx];      o[5] = grid[b + sx + 1];
-        o[6] = grid[b + sx + sy]; o[7] = grid[b + sx + sy + 1];
+        o[0] = (V)c000;
+        o[1] = (V)(c100 - c000); o[2] = (V)(c010 - c000); o[3] = (V)(c001 - c000);
+        o[4] = (V)(c110 - c100 - c010 + c000);
+        o[5] = (V)(c101 - c100 - c001 + c000);
+        o[6] = (V)(c011 - c010 - c001 + c000);
+        o[7] = (V)(c111 - c110 - c101 - c011 + c100 + c010 + c001 - c000);
     }
 }
 

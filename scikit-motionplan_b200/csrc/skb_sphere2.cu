@@ -105,25 +105,20 @@ enum { SDF_UNION = 0, SDF_SINGLE = 1, SDF_GRID_FAST = 2 };
 
 // Branch-free: the cell index is clamped and the gather always issued, the fill value / zero gradient are selected
 // afterwards -- so the two gathers of a lane's two rows are in flight together instead of being serialised by a
-// divergent branch.  Trilinear value and gradient in the oracle's association order.
+// divergent branch.  Value and gradient are Horner evaluations of the cell's polynomial pack (trilinear_poly).
 __device__ __forceinline__ float s2_grid_fast(const GridFast &gr, float px, float py, float pz, float &gx, float &gy, float &gz) {
     const float ux = (px - gr.ox) * gr.ix_, uy = (py - gr.oy) * gr.iy_, uz = (pz - gr.oz) * gr.iz_;
     const bool inside = ux >= 0.f && ux <= gr.tx && uy >= 0.f && uy <= gr.ty && uz >= 0.f && uz <= gr.tz;
     const int ix = max(0, min((int)floorf(ux), gr.mx)), iy = max(0, min((int)floorf(uy), gr.my)), iz = max(0, min((int)floorf(uz), gr.mz));
     const float fx = ux - float(ix), fy = uy - float(iy), fz = uz - float(iz);
     const unsigned cell = ((unsigned)ix * gr.sy + (unsigned)iy) * gr.sz + (unsigned)iz;
-    float c[8];
-    ldg_cell(gr.cells + (size_t)cell * 8, c);
-    const float d00 = c[4] - c[0], d01 = c[5] - c[1], d10 = c[6] - c[2], d11 = c[7] - c[3];
-    const float c00 = c[0] + fx * d00, c01 = c[1] + fx * d01, c10 = c[2] + fx * d10, c11 = c[3] + fx * d11;
-    const float e0 = c10 - c00, e1 = c11 - c01;
-    const float c0 = c00 + fy * e0, c1 = c01 + fy * e1;
-    const float h = c1 - c0;
-    const float dx0 = d00 + fy * (d10 - d00), dx1 = d01 + fy * (d11 - d01);
-    gx = inside ? (dx0 + fz * (dx1 - dx0)) * gr.ix_ : 0.f;
-    gy = inside ? (e0 + fz * (e1 - e0)) * gr.iy_ : 0.f;
-    gz = inside ? h * gr.iz_ : 0.f;
-    return inside ? c0 + fz * h : gr.fill;
+    float a[8], hx, hy, hz;
+    ldg_cell(gr.cells + (size_t)cell * 8, a);
+    const float val = trilinear_poly<float>(a, fx, fy, fz, hx, hy, hz);
+    gx = inside ? hx * gr.ix_ : 0.f;
+    gy = inside ? hy * gr.iy_ : 0.f;
+    gz = inside ? hz * gr.iz_ : 0.f;
+    return inside ? val : gr.fill;
 }
 
 // two adjacent columns of a Jacobian row: packed f32x2 arithmetic for float, two scalar chains for double -- the same

@@ -28,6 +28,21 @@ def _is_torch(x) -> bool:
     return torch is not None and isinstance(x, torch.Tensor)
 
 
+def current_device_index() -> int:
+    """Index of the CUDA device a native call issued now would run on (0 without torch / without a device: the call then
+    fails loudly inside the library)."""
+    if torch is not None and torch.cuda.is_available():
+        return int(torch.cuda.current_device())
+    return 0
+
+
+def device_guard(index: int):
+    """Context manager making cuda:``index`` current (native handles are created on, and bound to, one device)."""
+    if torch is not None and torch.cuda.is_available():
+        return torch.cuda.device(index)
+    return contextlib.nullcontext()
+
+
 class Batch:
     """Normalises one (N, D) batch of configurations and allocates matching outputs."""
 
@@ -63,8 +78,10 @@ class Batch:
         if self.on_device:
             _lib.require_cuda()
             self.stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            self.device_index = int(self.device.index if self.device.index is not None else torch.cuda.current_device())
         else:
             self.stream = None
+            self.device_index = current_device_index()       # host path: the current device does the work
 
     def device_ctx(self):
         """Make the tensor's device current for the duration of a native call."""

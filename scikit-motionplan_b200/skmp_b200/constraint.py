@@ -28,7 +28,7 @@ from typing import Generic, List, Optional, Protocol, Sequence, Tuple, TypeVar, 
 import numpy as np
 
 from . import _lib
-from ._array import Batch, _is_torch, torch
+from ._array import Batch, _is_torch, current_device_index, torch
 from .kinematics import CollSpheresKinematicsMapBase, EndEffectorKinematicsMap
 from .rotmath import matrix2quaternion, rpy_angle, wxyz2xyzw
 from .sdf import SignedDistanceFunction, as_descriptor
@@ -280,33 +280,38 @@ class CollFreeConst(AbstractIneqConst):
         self.distance_margin = distance_margin
         self.assign_id_value()
 
-    def _plan(self):
-        # the plan is a snapshot of the solver's sticky state: rebuilt only after the solver changed (set_q / add_new_link)
+    def _plan(self, device_index: Optional[int] = None):
+        # the plan is a snapshot of the solver's sticky state: rebuilt only after the solver changed (set_q / add_new_link);
+        # one plan per device (its tables live in that device's memory)
         k = self.colkin
-        cached = self.__dict__.get("_plan_cache")
+        dev = current_device_index() if device_index is None else device_index
+        cache = self.__dict__.setdefault("_plan_cache", {})
+        cached = cache.get(dev)
         if cached is not None and cached[0] is k.fksolver and cached[1] == k.fksolver._version:
             return cached[2]
         plan = k.fksolver.get_plan(k.tinyfk_feature_ids, k.tinyfk_joint_ids, k.base_type, RotationType.IGNORE,
-                                   radii=k.get_radius_list())
-        self.__dict__["_plan_cache"] = (k.fksolver, k.fksolver._version, plan)
+                                   radii=k.get_radius_list(), device_index=dev)
+        cache[dev] = (k.fksolver, k.fksolver._version, plan)
         return plan
 
-    def _run(self, qs, want_vals: bool, with_jacobian: bool, want_valid: bool):
+    def _run(self, qs, want_vals: bool, with_jacobian: bool, want_valid: bool, only_closest: Optional[bool] = None):
         assert self.sdf is not None
-        plan = self._plan()
-        b = Batch(qs, plan.dim_cspace)
-        m = 1 if self.only_closest_feature else plan.n_feature
+        b = Batch(qs, self.colkin.dim_cspace)
+        plan = self._plan(b.device_index)
+        closest = self.only_closest_feature if only_closest is None else only_closest
+        m = 1 if closest else plan.n_feature
         vals = b.empty((b.n, m)) if want_vals else None
         jac = b.empty((b.n, m, plan.dim_cspace)) if with_jacobian else None
         valid = b.empty_bytes(b.n) if want_valid else None
-        mode = _lib.MODE_CLOSEST if self.only_closest_feature else _lib.MODE_ALL
+        mode = _lib.MODE_CLOSEST if closest else _lib.MODE_ALL
         L = _lib.lib()
+        sdf_h = self.sdf.native(b.device_index)
         with b.device_ctx():
             if b.on_device:
-                _lib.check(L.skb_collfree(plan.handle, self.sdf.native(), b.dtype_code, b.q_ptr, b.n,
+                _lib.check(L.skb_collfree(plan.handle, sdf_h, b.dtype_code, b.q_ptr, b.n,
                                           float(self.distance_margin), mode, b.ptr(vals), b.ptr(jac), b.ptr(valid), b.stream))
             else:
-                _lib.check(L.skb_collfree_host(plan.handle, self.sdf.native(), b.dtype_code, b.q_ptr, b.n,
+                _lib.check(L.skb_collfree_host(plan.handle, sdf_h, b.dtype_code, b.q_ptr, b.n,
                                                float(self.distance_margin), mode, b.ptr(vals), b.ptr(jac), b.ptr(valid)))
         return b, vals, jac, valid
 
@@ -318,11 +323,7 @@ class CollFreeConst(AbstractIneqConst):
         """Row minimum of the values, (N, 1): the closest-mode kernel without Jacobian (what a composite needs)."""
         if not self.reflect_robot_flag:
             raise RuntimeError("{}: you need to call reflect_skrobot_model beforehand".format(type(self).__name__))
-        saved, self.only_closest_feature = self.only_closest_feature, True
-        try:
-            b, vals, _, _ = self._run(qs, True, False, False)
-        finally:
-            self.only_closest_feature = saved
+        b, vals, _, _ = self._run(qs, True, False, False, only_closest=True)      # the mode is an argument: re-entrant
         return b.out(vals)
 
     def is_valid_batch(self, qs):
@@ -515,27 +516,30 @@ class PairWiseSelfCollFreeConst(AbstractIneqConst):
         self.only_closest_feature = only_closest_feature
         self.assign_id_value()
 
-    def _plan(self):
+    def _plan(self, device_index: Optional[int] = None):
         k = self.colkin
-        cached = self.__dict__.get("_plan_cache")
+        dev = current_device_index() if device_index is None else device_index
+        cache = self.__dict__.setdefault("_plan_cache", {})
+        cached = cache.get(dev)
         if (cached is not None and cached[0] is k.fksolver and cached[1] == k.fksolver._version
                 and cached[3] is self.check_sphere_id_pairs and cached[4] is self.check_sphere_pair_sqdists):
             return cached[2]
         local = {fid: i for i, fid in enumerate(k.tinyfk_feature_ids)}
         pairs = np.array([[local[a], local[b]] for a, b in self.check_sphere_id_pairs], dtype=np.int32)
         plan = k.fksolver.get_plan(k.tinyfk_feature_ids, k.tinyfk_joint_ids, k.base_type, RotationType.IGNORE,
-                                   radii=None, pairs=pairs, pair_sqdists=self.check_sphere_pair_sqdists)
-        self.__dict__["_plan_cache"] = (k.fksolver, k.fksolver._version, plan, self.check_sphere_id_pairs, self.check_sphere_pair_sqdists)
+                                   radii=None, pairs=pairs, pair_sqdists=self.check_sphere_pair_sqdists, device_index=dev)
+        cache[dev] = (k.fksolver, k.fksolver._version, plan, self.check_sphere_id_pairs, self.check_sphere_pair_sqdists)
         return plan
 
-    def _run(self, qs, want_vals: bool, with_jacobian: bool, want_valid: bool):
-        plan = self._plan()
-        b = Batch(qs, plan.dim_cspace)
-        m = 1 if self.only_closest_feature else len(self.check_sphere_id_pairs)
+    def _run(self, qs, want_vals: bool, with_jacobian: bool, want_valid: bool, only_closest: Optional[bool] = None):
+        b = Batch(qs, self.colkin.dim_cspace)
+        plan = self._plan(b.device_index)
+        closest = self.only_closest_feature if only_closest is None else only_closest
+        m = 1 if closest else len(self.check_sphere_id_pairs)
         vals = b.empty((b.n, m)) if want_vals else None
         jac = b.empty((b.n, m, plan.dim_cspace)) if with_jacobian else None
         valid = b.empty_bytes(b.n) if want_valid else None
-        mode = _lib.MODE_CLOSEST if self.only_closest_feature else _lib.MODE_ALL
+        mode = _lib.MODE_CLOSEST if closest else _lib.MODE_ALL
         L = _lib.lib()
         with b.device_ctx():
             if b.on_device:

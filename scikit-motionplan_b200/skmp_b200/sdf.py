@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._array import Batch, torch
+from ._array import Batch, current_device_index, device_guard, torch
 
 
 class SignedDistanceFunction:
@@ -30,45 +30,51 @@ class SignedDistanceFunction:
     def primitives(self) -> List[tuple]:
         raise NotImplementedError
 
-    def native(self) -> C.c_void_p:
+    def native(self, device_index: Optional[int] = None) -> C.c_void_p:
+        """The ``skb_sdf`` handle of this field on one device (default: the current one).  Grids and primitive tables live
+        in that device's memory, so there is one handle per device."""
+        dev = current_device_index() if device_index is None else int(device_index)
         if self._handle is None:
+            self._handle = {}
+        if dev not in self._handle:
             _lib.require_cuda()
             L = _lib.lib()
             h = C.c_void_p()
             _lib.check(L.skb_sdf_create(C.byref(h)))
             d = lambda a: _lib.dptr(np.ascontiguousarray(a, dtype=np.float64))
-            for prim in self.primitives():
-                kind = prim[0]
-                if kind == "box":
-                    _, pos, rot, half = prim
-                    _lib.check(L.skb_sdf_add_box(h, d(pos), d(rot), d(half)))
-                elif kind == "cylinder":
-                    _, pos, rot, radius, hh = prim
-                    _lib.check(L.skb_sdf_add_cylinder(h, d(pos), d(rot), float(radius), float(hh)))
-                elif kind == "sphere":
-                    _, pos, radius = prim
-                    _lib.check(L.skb_sdf_add_sphere(h, d(pos), float(radius)))
-                elif kind == "grid":
-                    _, pos, rot, lb, spacing, values, fill = prim
-                    vals = np.ascontiguousarray(values)
-                    if vals.dtype not in (np.float32, np.float64):
-                        vals = vals.astype(np.float64)
-                    dims = np.array(vals.shape, dtype=np.int32)
-                    code = _lib.F32 if vals.dtype == np.float32 else _lib.F64
-                    _lib.check(L.skb_sdf_add_grid(h, d(pos), d(rot), d(lb), d(spacing), _lib.dptr(dims, C.c_int32),
-                                                  float(fill), C.c_void_p(vals.ctypes.data), code))
-                else:
-                    raise ValueError(kind)
-            self._handle = h
-        return self._handle
+            with device_guard(dev):
+                for prim in self.primitives():
+                    kind = prim[0]
+                    if kind == "box":
+                        _, pos, rot, half = prim
+                        _lib.check(L.skb_sdf_add_box(h, d(pos), d(rot), d(half)))
+                    elif kind == "cylinder":
+                        _, pos, rot, radius, hh = prim
+                        _lib.check(L.skb_sdf_add_cylinder(h, d(pos), d(rot), float(radius), float(hh)))
+                    elif kind == "sphere":
+                        _, pos, radius = prim
+                        _lib.check(L.skb_sdf_add_sphere(h, d(pos), float(radius)))
+                    elif kind == "grid":
+                        _, pos, rot, lb, spacing, values, fill = prim
+                        vals = np.ascontiguousarray(values)
+                        if vals.dtype not in (np.float32, np.float64):
+                            vals = vals.astype(np.float64)
+                        dims = np.array(vals.shape, dtype=np.int32)
+                        code = _lib.F32 if vals.dtype == np.float32 else _lib.F64
+                        _lib.check(L.skb_sdf_add_grid(h, d(pos), d(rot), d(lb), d(spacing), _lib.dptr(dims, C.c_int32),
+                                                      float(fill), C.c_void_p(vals.ctypes.data), code))
+                    else:
+                        raise ValueError(kind)
+            self._handle[dev] = h
+        return self._handle[dev]
 
     def invalidate(self):
-        if self._handle is not None:
+        handles, self._handle = self._handle, None
+        for h in (handles or {}).values():
             try:
-                _lib.lib().skb_sdf_destroy(self._handle)
+                _lib.lib().skb_sdf_destroy(h)
             except Exception:
                 pass
-            self._handle = None
 
     def __del__(self):
         self.invalidate()
@@ -86,7 +92,7 @@ class SignedDistanceFunction:
         L = _lib.lib()
         if b.on_device:
             with b.device_ctx():
-                _lib.check(L.skb_sdf_eval(self.native(), b.dtype_code, b.q_ptr, b.n, b.ptr(vals), b.ptr(grads), b.stream))
+                _lib.check(L.skb_sdf_eval(self.native(b.device_index), b.dtype_code, b.q_ptr, b.n, b.ptr(vals), b.ptr(grads), b.stream))
         else:
             if torch is None:
                 raise _lib.SkbError("evaluating an SDF on host arrays needs torch for device staging")
@@ -94,7 +100,7 @@ class SignedDistanceFunction:
             dv = torch.empty((b.n,), dtype=dev.dtype, device=dev.device)
             dg = torch.empty((b.n, 3), dtype=dev.dtype, device=dev.device) if with_gradient else None
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _lib.check(L.skb_sdf_eval(self.native(), b.dtype_code, C.c_void_p(dev.data_ptr()), b.n, C.c_void_p(dv.data_ptr()),
+            _lib.check(L.skb_sdf_eval(self.native(b.device_index), b.dtype_code, C.c_void_p(dev.data_ptr()), b.n, C.c_void_p(dv.data_ptr()),
                                       C.c_void_p(dg.data_ptr()) if dg is not None else None, st))
             vals = dv.cpu() if b.is_torch else dv.cpu().numpy()
             grads = None if dg is None else (dg.cpu() if b.is_torch else dg.cpu().numpy())

@@ -15,7 +15,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._array import Batch
+from ._array import Batch, current_device_index, device_guard
 from .urdf import JT_FIXED, UrdfModel, parse_urdf
 
 
@@ -191,8 +191,11 @@ class KinematicModel:
     def get_plan(self, feature_ids: Sequence[int], joint_ids: Sequence[int], base_type: BaseType,
                  rot_type: RotationType, radii: Optional[Sequence[float]] = None,
                  pairs: Optional[np.ndarray] = None, pair_sqdists: Optional[np.ndarray] = None,
-                 weights: Optional[Sequence[float]] = None) -> Plan:
-        key = (tuple(feature_ids), tuple(joint_ids), base_type, rot_type,
+                 weights: Optional[Sequence[float]] = None, device_index: Optional[int] = None) -> Plan:
+        """Compiled plan for (features, joints, base, rotation type[, radii / pairs / weights]) on ONE device: the program
+        tables are uploaded to the device that is current when the plan is first used, so the cache is keyed by device."""
+        dev = current_device_index() if device_index is None else int(device_index)
+        key = (dev, tuple(feature_ids), tuple(joint_ids), base_type, rot_type,
                None if radii is None else tuple(float(r) for r in radii),
                None if pairs is None else (np.asarray(pairs).tobytes(), np.asarray(pair_sqdists).tobytes()),
                None if weights is None else tuple(float(w) for w in weights))
@@ -202,8 +205,9 @@ class KinematicModel:
             feats = np.asarray(feature_ids, dtype=np.int32)
             jl = self.joint_child_links(joint_ids)
             h = C.c_void_p()
-            _lib.check(L.skb_plan_create(self.native(), _lib.dptr(feats, C.c_int32), len(feats),
-                                         _lib.dptr(jl, C.c_int32), len(jl), base_type.value, rot_type.value, C.byref(h)))
+            with device_guard(dev):
+                _lib.check(L.skb_plan_create(self.native(), _lib.dptr(feats, C.c_int32), len(feats),
+                                             _lib.dptr(jl, C.c_int32), len(jl), base_type.value, rot_type.value, C.byref(h)))
             plan = Plan(h.value, len(jl) + base_dim(base_type), len(feats), tspace_dim(rot_type))
             if radii is not None:
                 r = np.ascontiguousarray(radii, dtype=np.float64)
@@ -224,8 +228,8 @@ class KinematicModel:
     def solve_fk(self, qs, feature_ids, joint_ids, base_type: BaseType = BaseType.FIXED,
                  with_jacobian: bool = False, rot_type: RotationType = RotationType.IGNORE):
         """-> points (N, F, T), jacobians (N, F, T, D) (``np.empty(0)``-like when not requested)."""
-        plan = self.get_plan(feature_ids, joint_ids, base_type, rot_type)
-        b = Batch(qs, plan.dim_cspace)
+        b = Batch(qs, len(joint_ids) + base_dim(base_type))
+        plan = self.get_plan(feature_ids, joint_ids, base_type, rot_type, device_index=b.device_index)
         pts = b.empty((b.n, plan.n_feature, plan.dim_tspace))
         jac = b.empty((b.n, plan.n_feature, plan.dim_tspace, plan.dim_cspace)) if with_jacobian else None
         L = _lib.lib()
@@ -243,8 +247,8 @@ class KinematicModel:
         feats = sorted({i for p in pairs for i in p})
         local = {f: k for k, f in enumerate(feats)}
         pr = np.array([[local[a], local[b]] for a, b in pairs], dtype=np.int32)
-        plan = self.get_plan(feats, joint_ids, base_type, RotationType.IGNORE, None, pr, np.zeros(len(pr)))
-        b = Batch(qs, plan.dim_cspace)
+        b = Batch(qs, len(joint_ids) + base_dim(base_type))
+        plan = self.get_plan(feats, joint_ids, base_type, RotationType.IGNORE, None, pr, np.zeros(len(pr)), device_index=b.device_index)
         P = len(pr)
         vals = b.empty((b.n, P))
         jac = b.empty((b.n, P, plan.dim_cspace)) if with_jacobian else None
@@ -282,13 +286,13 @@ class KinematicModel:
 
     def _com_call(self, qs, joint_ids, action_link_ids, action_forces, base_type, with_jacobian, what, sdf):
         feats, weights = self.com_points(action_link_ids, action_forces)
-        plan = self.get_plan(feats, joint_ids, base_type, RotationType.IGNORE, weights=weights)
-        b = Batch(qs, plan.dim_cspace)
+        b = Batch(qs, len(joint_ids) + base_dim(base_type))
+        plan = self.get_plan(feats, joint_ids, base_type, RotationType.IGNORE, weights=weights, device_index=b.device_index)
         m = 3 if what == _lib.COM_POINT else 1
         vals = b.empty((b.n, m))
         jac = b.empty((b.n, m, plan.dim_cspace)) if with_jacobian else None
         L = _lib.lib()
-        sdf_h = sdf.native() if sdf is not None else None
+        sdf_h = sdf.native(b.device_index) if sdf is not None else None
         with b.device_ctx():
             if b.on_device:
                 _lib.check(L.skb_com(plan.handle, sdf_h, b.dtype_code, b.q_ptr, b.n, what, b.ptr(vals), b.ptr(jac), b.stream))

@@ -1,0 +1,310 @@
+"""GPU tests of the classes and code paths that round 1 built but never exercised:
+
+  * AttachedObstacleCollPointsKinematicsMap               (skmp/kinematics.py:171-231; JAXON's 152-point cloud)
+  * RelativePoseConstraint / FixedZAxisConstraint         (skmp/constraint.py:508-607; tests/test_constraint.py:146-169)
+  * the standalone ``sdf(points)`` callable               (skmp/constraint.py:268,314,353,397,401)
+  * the fallback kernels: lane-per-configuration ``tree_kernel`` / ``pairwise_kernel`` (SKB_KERNEL=tree; what robots with
+    D > 64 or > 255 nodes get), the one-row-per-lane ``sphere_kernel`` for every collfree mode (SKB_KERNEL=sphere1) and voxel
+    grids without cell packs (SKB_GRID_CELLS=0; what grids too large for the packs get)
+  * the reference-held scene facts of tests/test_reference_pins.py, on the CUDA path.
+"""
+import copy
+
+import numpy as np
+import pytest
+
+from helpers import ROT, oracle_args, sample_q
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float32: 1e-5, np.float64: 1e-10}
+KINK_BAND = {np.float32: 2e-5, np.float64: 1e-9}
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((np.abs(a - b) / np.maximum(1.0, np.abs(b))).max()) if a.size else 0.0
+
+
+def dev(x, dtype):
+    return _torch().as_tensor(np.asarray(x).astype(dtype), device="cuda")
+
+
+# ------------------------------------------------------------------ AttachedObstacleCollPointsKinematicsMap
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_attached_obstacle_points_jaxon(dtype):
+    """A box held in JAXON's right hand: 6^3 lattice minus the 4^3 interior = 152 points (SURVEY 8 size table), radius =
+    margin; map() and CollFreeConst against the oracle, the point cloud against an independent numpy construction."""
+    from skmp_b200.constraint import CollFreeConst
+    from skmp_b200.robot.jaxon import JaxonConfig
+    from skmp_b200.robot_model import Jaxon
+    from skmp_b200.rotmath import rotation_matrix
+    from skmp_b200.sdf import Box, UnionSDF
+
+    jaxon = Jaxon(); jaxon.reset_manip_pose()
+    held = Box([0.2, 0.3, 0.25])
+    held.translate([0.4, -0.3, 1.0])
+    held.rotate_with_matrix(rotation_matrix(0.4, [0.3, 1.0, -0.2]))
+    rel = np.array([0.05, 0.0, -0.12])
+    kin = JaxonConfig().get_attached_obstacle_kin(rel, held)
+    assert kin.n_feature == 152 and len(kin.tinyfk_feature_ids) == 152 and kin.dim_cspace == 37 and kin.dim_tspace == 3
+    # the point cloud, restated: lattice in the box frame, rotated by the box, interior (deeper than 1 cm) dropped;
+    # numpy.meshgrid's default 'xy' indexing fixes the order (kinematics.py:195-204)
+    e = np.array([0.2, 0.3, 0.25])
+    gx, gy, gz = np.meshgrid(*[np.linspace(-0.5 * e[i], 0.5 * e[i], 6) for i in range(3)])
+    local = np.stack([gx.flatten(), gy.flatten(), gz.flatten()], axis=1)
+    depth = np.max(np.abs(local) - 0.5 * e, axis=1)            # box SDF inside the box
+    keep = depth > -1e-2
+    expect = local[keep] @ held.worldrot().T + rel
+    origins = kin.fksolver.origin[kin.tinyfk_feature_ids, :3]
+    assert np.abs(origins - expect).max() < 1e-12
+    attach = kin.fksolver.get_link_ids(["rarm_end_coords"])[0]
+    assert (kin.fksolver.parent[kin.tinyfk_feature_ids] == attach).all()
+
+    kin_m = copy.deepcopy(kin)
+    kin_m.radius_list = [0.03] * kin_m.n_feature                 # margin = 3 cm (kinematics.py:222)
+    env = UnionSDF([Box([4.0, 4.0, 0.2], pos=[0.0, 0.0, -0.1]), Box([0.6, 1.0, 0.8], pos=[0.9, 0.0, 0.4])])
+    rng = np.random.default_rng(31)
+    qs = sample_q(kin, 300, rng) * 0.5
+    qs[:, 33] += 1.0
+    qs = qs.astype(dtype).astype(np.float64)
+    kin.reflect_skrobot_model(jaxon)
+    pts, jac = kin.map(dev(qs, dtype))
+    tree, feat, jl, base = oracle_args(kin)
+    rp, rj = oracle.solve_fk(tree, qs, feat, jl, base)
+    assert err(pts.cpu().numpy(), rp) < TOL[dtype] and err(jac.cpu().numpy(), rj) < TOL[dtype]
+    for k, closest in ((kin, False), (kin_m, False), (kin_m, True)):
+        const = CollFreeConst(k, env, jaxon, only_closest_feature=closest)
+        v, j = const.evaluate(dev(qs, dtype), True)
+        tree, feat, jl, base = oracle_args(k)
+        rv, rjac, kink = oracle.collfree(tree, qs, feat, jl, oracle.Sdf(env.primitives()), k.get_radius_list(), base_type=base,
+                                         only_closest=closest, with_kink=True)
+        assert err(v.cpu().numpy(), rv) < TOL[dtype]
+        ok = kink > KINK_BAND[dtype]
+        assert ok.mean() > 0.99
+        assert err(j.cpu().numpy()[ok], rjac[ok]) < 2 * TOL[dtype]   # D = 37 chain: twice the value tolerance (measured 1.1e-5 in fp32)
+    # radius = margin shifts every value by exactly the margin
+    v0, _ = CollFreeConst(kin, env, jaxon).evaluate(dev(qs, np.float64), False)
+    v1, _ = CollFreeConst(kin_m, env, jaxon).evaluate(dev(qs, np.float64), False)
+    assert float((v0 - v1 - 0.03).abs().max()) < 1e-12
+
+
+# ------------------------------------------------------------------ derived pose constraints
+def _fd_jacobian(const, q, eps=1e-7):
+    """tests/test_constraint.py:26-38 (forward difference of evaluate_single), in fp64."""
+    f0, _ = const.evaluate_single(q, False)
+    f0 = np.asarray(f0.cpu() if hasattr(f0, "cpu") else f0)
+    jac = np.zeros((len(f0), len(q)))
+    for i in range(len(q)):
+        q1 = q.copy()
+        q1[i] += eps
+        f1, _ = const.evaluate_single(q1, False)
+        jac[:, i] = (np.asarray(f1.cpu() if hasattr(f1, "cpu") else f1) - f0) / eps
+    return jac
+
+
+@pytest.mark.parametrize("rot", ["RPY", "XYZW", "IGNORE"])
+def test_relative_pose_constraint(rot):
+    """tests/test_constraint.py:146-161: Jacobian = forward difference to 4 decimals, the caller's efkin is not modified;
+    plus values / Jacobians against the oracle's FK of the three features (xs[:,1] - xs[:,2], constraint.py:534-548)."""
+    from skmp_b200.constraint import RelativePoseConstraint
+    from skmp_b200.robot.pr2 import PR2Config
+    from skmp_b200.robot_model import PR2
+    from skmp_b200.tinyfk import RotationType
+
+    pr2 = PR2()
+    efkin = PR2Config(control_arm="dual").get_endeffector_kin(RotationType[rot])
+    const = RelativePoseConstraint(np.ones(3) * 0.1, efkin, pr2)
+    assert efkin.n_feature == 2 and len(efkin.tinyfk_feature_ids) == 2
+    assert const.efkin.n_feature == 3 and isinstance(const.id_value, str)
+    rng = np.random.default_rng(41)
+    for _ in range(3):
+        q = rng.standard_normal(14)
+        _, jac = const.evaluate_single(q, True)
+        np.testing.assert_almost_equal(np.asarray(jac), _fd_jacobian(const, q), decimal=4)
+    for dtype in (np.float32, np.float64):
+        qs = rng.standard_normal((200, 14)).astype(dtype).astype(np.float64)
+        v, j = const.evaluate(dev(qs, dtype), True)
+        tree, feat, jl, base = oracle_args(const.efkin)
+        xs, jacs = oracle.solve_fk(tree, qs, feat, jl, base, ROT[RotationType[rot]])
+        tol = TOL[dtype] * (3 if dtype == np.float32 else 1)       # atan2 / asin of fp32 rotation entries, as test_map_pose_features
+        assert err(v.cpu().numpy(), xs[:, 1, :] - xs[:, 2, :]) < tol
+        assert err(j.cpu().numpy(), jacs[:, 1] - jacs[:, 2]) < 3 * tol
+        v2, j2 = const.evaluate(qs.astype(dtype), False)            # host path, no Jacobian
+        assert err(v2, xs[:, 1, :] - xs[:, 2, :]) < tol and np.isnan(np.asarray(j2)).all()
+
+
+@pytest.mark.parametrize("rot", ["RPY", "IGNORE"])
+def test_fixed_zaxis_constraint(rot):
+    """tests/test_constraint.py:164-169 + the reference's own formula (constraint.py:582-603: reshape to
+    (n, 3, n_feature, T), z of (+x point - origin) then of (+y point - origin)) evaluated on the oracle's FK."""
+    from skmp_b200.constraint import FixedZAxisConstraint
+    from skmp_b200.robot.pr2 import PR2Config
+    from skmp_b200.robot_model import PR2
+    from skmp_b200.tinyfk import RotationType
+
+    pr2 = PR2()
+    efkin = PR2Config(control_arm="dual").get_endeffector_kin(RotationType[rot])
+    const = FixedZAxisConstraint(efkin, pr2)
+    assert efkin.n_feature == 2 and const.efkin.n_feature == 6 and const.n_feature == 2
+    rng = np.random.default_rng(43)
+    for _ in range(3):
+        q = rng.standard_normal(14)
+        val, jac = const.evaluate_single(q, True)
+        assert np.asarray(val).shape == (4,) and np.asarray(jac).shape == (4, 14)
+        np.testing.assert_almost_equal(np.asarray(jac), _fd_jacobian(const, q), decimal=4)
+    for dtype in (np.float32, np.float64):
+        qs = rng.standard_normal((200, 14)).astype(dtype).astype(np.float64)
+        v, j = const.evaluate(dev(qs, dtype), True)
+        tree, feat, jl, base = oracle_args(const.efkin)
+        xs, jacs = oracle.solve_fk(tree, qs, feat, jl, base, ROT[RotationType[rot]])
+        n, nf = len(qs), 2
+        tmp = xs.reshape(n, 3, nf, -1)
+        ref_v = np.concatenate([(tmp[:, 1] - tmp[:, 0])[:, :, 2], (tmp[:, 2] - tmp[:, 0])[:, :, 2]], axis=1).reshape(n, -1)
+        tj = jacs.reshape(n, 3, nf, -1, 14)
+        ref_j = np.concatenate([(tj[:, 1] - tj[:, 0])[:, :, 2, :], (tj[:, 2] - tj[:, 0])[:, :, 2, :]], axis=1).reshape(n, -1, 14)
+        assert err(v.cpu().numpy(), ref_v) < TOL[dtype] and err(j.cpu().numpy(), ref_j) < 2 * TOL[dtype]
+        # the unit offsets make the values the (3,1) / (3,2) entries of the end-effector rotation: |value| <= 1
+        assert float(v.abs().max()) <= 1.0 + 1e-5
+
+
+# ------------------------------------------------------------------ standalone sdf(points)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_sdf_callable_direct(dtype):
+    """sdf(points (M,3)) -> (M,) [+ analytic gradients (M,3)] for every descriptor, CUDA tensors and numpy, against the
+    oracle's primitives (``skb_sdf_eval``).  The reference calls it at skmp/constraint.py:314,329,353,368,397,401."""
+    from skmp_b200.rotmath import rotation_matrix
+    from skmp_b200.sdf import Box, Cylinder, GridSDF, Sphere, UnionSDF
+
+    rng = np.random.default_rng(51)
+    box = Box([0.7, 0.5, 1.2]); box.translate([0.85, -0.2, 0.9]); box.rotate_with_matrix(rotation_matrix(0.3, [0.1, 0.2, 1.0]))
+    cyl = Cylinder(0.15, 0.8); cyl.translate([0.4, -0.6, 1.0]); cyl.rotate_with_matrix(rotation_matrix(1.0, [1.0, 0.0, 0.0]))
+    sph = Sphere(0.2, pos=[0.6, 0.0, 1.6])
+    union = UnionSDF([box, cyl, sph])
+    lb, ub = np.array([-0.5, -1.5, 0.0]), np.array([1.5, 1.5, 2.0])
+    dims = np.array([40, 56, 48])
+    spacing = (ub - lb) / (dims - 1)
+    axes = [lb[i] + spacing[i] * np.arange(dims[i]) for i in range(3)]
+    lattice = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, 3)
+    grid_vals = oracle.Sdf(union.primitives())(lattice).reshape(tuple(dims)).astype(np.float32)   # sampled by the ORACLE, not by the engine
+    grid = GridSDF(grid_vals, lb, spacing, fill_value=7.5)
+    grid_rot = GridSDF(grid_vals.astype(np.float64), lb, spacing, fill_value=7.5, pos=[0.1, -0.05, 0.02], rot=rotation_matrix(0.2, [0.0, 0.0, 1.0]))
+    pts = rng.uniform([-0.8, -1.8, -0.3], [1.8, 1.8, 2.3], size=(6000, 3)).astype(dtype).astype(np.float64)   # some outside the grid
+    for sdf in (box, cyl, sph, union, grid, grid_rot):
+        rv, rg, kink = oracle.Sdf(sdf.primitives())(pts, with_grad=True, with_kink=True)
+        ok = kink > (1e-4 if dtype == np.float32 else 1e-9)
+        v, g = sdf(dev(pts, dtype), with_gradient=True)
+        assert err(v.cpu().numpy(), rv) < TOL[dtype]
+        assert err(g.cpu().numpy()[ok], rg[ok]) < 3 * TOL[dtype]       # unit-length gradients from rsqrt (2 ulp) in fp32
+        vh = sdf(pts.astype(dtype))                                        # numpy in -> numpy out, values only
+        assert isinstance(vh, np.ndarray) and err(vh, rv) < TOL[dtype]
+        vh2, gh2 = sdf(pts.astype(dtype), with_gradient=True)
+        assert np.array_equal(vh2, v.cpu().numpy()) and np.array_equal(gh2, g.cpu().numpy())
+    outside = ((pts < lb) | (pts > ub)).any(axis=1)
+    vg, gg = grid(dev(pts, dtype), with_gradient=True)
+    assert outside.sum() > 100 and (vg.cpu().numpy()[outside] == 7.5).all() and (gg.cpu().numpy()[outside] == 0).all()
+
+
+# ------------------------------------------------------------------ fallback kernels
+@pytest.mark.parametrize("env", [{"SKB_KERNEL": "tree"}, {"SKB_KERNEL": "sphere1"}, {"SKB_GRID_CELLS": "0"}],
+                         ids=["tree_kernels", "sphere1_kernel", "grid_without_cell_packs"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_fallback_kernels(monkeypatch, env, dtype):
+    """cfg1 (PR2 right arm vs box, all / closest / validity), a union + voxel-grid scene, cfg2 (Fetch pairwise, all / closest)
+    and pose rows, computed by the fallback code paths (selected when the plans / SDFs are created under the switch) and
+    compared with the oracle to the same tolerances as the default kernels."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    from skmp_b200.constraint import CollFreeConst, PoseConstraint
+    from skmp_b200.robot.fetch import FetchConfig
+    from skmp_b200.robot.pr2 import PR2Config
+    from skmp_b200.robot_model import PR2, Fetch
+    from skmp_b200.rotmath import rotation_matrix
+    from skmp_b200.sdf import Box, Cylinder, GridSDF, UnionSDF
+    from skmp_b200.tinyfk import RotationType
+
+    torch = _torch()
+    pr2 = PR2(); pr2.reset_manip_pose()
+    rng = np.random.default_rng(61)
+    box = Box([0.7, 0.5, 1.2], pos=[0.85, -0.2, 0.9])
+    cyl = Cylinder(0.15, 0.8); cyl.translate([0.4, -0.6, 1.0]); cyl.rotate_with_matrix(rotation_matrix(1.0, [1.0, 0.0, 0.0]))
+    union = UnionSDF([box, cyl])
+    lb, ub, dims = np.array([-0.5, -1.5, 0.0]), np.array([1.5, 1.5, 2.0]), np.array([48, 64, 48])
+    spacing = (ub - lb) / (dims - 1)
+    axes = [lb[i] + spacing[i] * np.arange(dims[i]) for i in range(3)]
+    lattice = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, 3)
+    grid = GridSDF(oracle.Sdf(union.primitives())(lattice).reshape(tuple(dims)).astype(np.float32), lb, spacing)
+    colkin = PR2Config().get_collision_kin()            # fresh solver: its plans are compiled under the switch
+    qs = sample_q(colkin, 500, rng).astype(dtype).astype(np.float64)
+    tree, feat, jl, base = oracle_args(colkin)
+    for sdf in (box, union, grid):
+        osdf = oracle.Sdf(sdf.primitives())
+        for closest in (False, True):
+            const = CollFreeConst(colkin, sdf, pr2, only_closest_feature=closest)
+            v, j = const.evaluate(dev(qs, dtype), True)
+            rv, rj, kink = oracle.collfree(tree, qs, feat, jl, osdf, colkin.get_radius_list(), only_closest=closest, with_kink=True)
+            assert err(v.cpu().numpy(), rv) < TOL[dtype]
+            ok = kink > KINK_BAND[dtype]
+            assert err(j.cpu().numpy()[ok], rj[ok]) < 2 * TOL[dtype]
+            v2, j2 = const.evaluate(dev(qs, dtype), False)
+            assert torch.equal(v2, v)
+        const = CollFreeConst(colkin, sdf, pr2)
+        valid = const.is_valid_batch(dev(qs, dtype)).cpu().numpy()
+        rv, _ = oracle.collfree(tree, qs, feat, jl, osdf, colkin.get_radius_list(), with_jacobian=False)
+        decisive = np.abs(rv).min(axis=1) > 1e-6
+        assert (valid == (rv > 0).all(axis=1))[decisive].all() and 0.02 < valid.mean() < 0.98
+    # Fetch pairwise
+    fetch = Fetch(); fetch.reset_pose()
+    for closest in (False, True):
+        pw = FetchConfig().get_pairwise_selcol_consts(fetch, only_closest_feature=closest)
+        q2 = sample_q(pw.colkin, 300, rng).astype(dtype).astype(np.float64)
+        v, j = pw.evaluate(dev(q2, dtype), True)
+        t2, _, jl2, b2 = oracle_args(pw.colkin)
+        sq, gr = oracle.inter_link_sqdists(t2, q2, np.array(pw.check_sphere_id_pairs), jl2, b2)
+        rv = sq - pw.check_sphere_pair_sqdists
+        if closest:
+            idx, n = rv.argmin(axis=1), np.arange(len(rv))
+            assert err(v.cpu().numpy()[:, 0], rv[n, idx]) < TOL[dtype] and err(j.cpu().numpy()[:, 0], gr[n, idx]) < 2 * TOL[dtype]
+        else:
+            assert err(v.cpu().numpy(), rv) < TOL[dtype] and err(j.cpu().numpy(), gr) < 2 * TOL[dtype]
+    # pose rows (the tree kernel's RPY / XYZW epilogue under SKB_KERNEL=tree)
+    for rt in (RotationType.RPY, RotationType.XYZW):
+        efkin = PR2Config(control_arm="dual").get_endeffector_kin(rt)
+        efkin.reflect_skrobot_model(pr2)
+        q3 = sample_q(efkin, 200, rng).astype(dtype).astype(np.float64)
+        pts, jac = efkin.map(dev(q3, dtype))
+        t3, f3, jl3, b3 = oracle_args(efkin)
+        rp, rjac = oracle.solve_fk(t3, q3, f3, jl3, b3, ROT[rt])
+        tol = TOL[dtype] * (3 if dtype == np.float32 else 1)
+        assert err(pts.cpu().numpy(), rp) < tol and err(jac.cpu().numpy(), rjac) < 3 * tol
+
+
+# ------------------------------------------------------------------ reference-held scene facts on the CUDA path
+def test_reference_pins_on_gpu():
+    """The facts of tests/test_reference_pins.py through the product API (numpy in, like the reference's callers)."""
+    from skmp_b200.constraint import CollFreeConst, PoseConstraint
+    from skmp_b200.robot.pr2 import PR2Config
+    from skmp_b200.robot_model import PR2, Coordinates, get_robot_state
+    from skmp_b200.sdf import Box
+
+    pr2 = PR2(); pr2.reset_manip_pose()
+    conf = PR2Config()
+    colkin, efkin = conf.get_collision_kin(), conf.get_endeffector_kin()
+    q_goal_cand = np.array([-0.78, 0.055, -1.37, -0.59, -0.494, -0.20, 1.87])
+    start = np.array([0.564, 0.35, -0.74, -0.7, -0.7, -0.17, -0.63])
+    pose = PoseConstraint.from_skrobot_coords([Coordinates(pos=[0.8, -0.6, 1.1])], efkin, pr2)
+    val, _ = pose.evaluate_single(q_goal_cand, False)
+    assert np.abs(np.asarray(val)[:3]).max() < 0.012 and np.abs(np.asarray(val)[3:]).max() < 0.015
+    q_now = get_robot_state(pr2, conf._get_control_joint_names())
+    near = CollFreeConst(colkin, Box([0.7, 0.5, 1.2], pos=[0.68, -0.3, 0.9]).sdf, pr2)
+    assert not near.is_valid(q_now)                                   # tests/test_satisfy.py:92-100
+    std = CollFreeConst(colkin, Box([0.7, 0.5, 1.2], pos=[0.85, -0.2, 0.9]).sdf, pr2)
+    assert std.is_valid(start) and std.is_valid(q_now)                # tests/solver_tests/utils.py:24-37
