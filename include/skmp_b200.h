@@ -121,6 +121,19 @@ SKB_API int skb_plan_set_weights(skb_plan *p, const double *weights /* n_feature
 /* tuning knobs (0 = auto): spheres per staged chunk, staging buffers per warp, warps per CTA */
 SKB_API int skb_plan_set_tuning(skb_plan *p, int32_t chunk_features, int32_t n_buffers, int32_t warps_per_cta,
                                 int32_t ctas_per_sm);
+/* Measures the launch configuration (configurations per warp tile, warps per CTA, fused / unfused row steps) of the step
+ * kernel that serves skb_collfree (pass the SDF) or skb_pairwise (s = NULL) for this plan, dtype, mode and output set
+ * (bit 0 values, bit 1 jacobians, bit 2 validity bytes), on up to 262 144 of the caller's sample configurations and on
+ * scratch outputs of its own; synchronous, 30-130 ms.  The choice is stored under a content key of the plan's structure:
+ * every later launch of a structurally equal plan (same robot / features / joints, any sticky state) reuses it, and
+ * SKB_TUNE_CACHE=<file> persists it across processes.  Without it, calls of fewer than 2^20 configurations use an
+ * issue-slot model; longer calls measure once themselves (SKB_S2_AUTOTUNE=0 disables that).  Results never depend on the
+ * choice (bit-identical).  out_choice (nullable): {unfused, G, warps}, out_choice[0] = -1 when nothing was tunable. */
+SKB_API int skb_plan_tune(const skb_plan *p, const skb_sdf *s /* NULL: pairwise */, int32_t dtype, const void *q_dev,
+                          int64_t N, double margin, int32_t mode, int32_t outputs, void *stream, int32_t *out_choice);
+/* the stored choice for (plan structure, dtype, mode, outputs): out_choice = {unfused, G, warps}, {-1, ..} when none */
+SKB_API int skb_plan_get_tuned(const skb_plan *p, const skb_sdf *s /* NULL: pairwise */, int32_t dtype, int32_t mode,
+                               int32_t outputs, int32_t *out_choice);
 SKB_API void skb_plan_destroy(skb_plan *p);
 
 /* ---------------------------------------------------------------- hot path (device pointers)
@@ -137,6 +150,13 @@ SKB_API int skb_fk(const skb_plan *p, int32_t dtype, const void *q_dev, int64_t 
 SKB_API int skb_collfree(const skb_plan *p, const skb_sdf *s, int32_t dtype, const void *q_dev, int64_t N,
                          double margin, int32_t mode, void *out_vals_dev, void *out_jac_dev,
                          uint8_t *out_valid_dev, void *stream);
+/* CollFreeConst rows of an SQP trajectory stack, written the way the solver consumes them
+ *        (skmp/solver/nlp_solver/trajectory_constraint.py:128-195: per waypoint evaluate_single, dense fill, conversion to
+ *        CSC with a cached pattern :34-47): out_data (N, D, S) is the Jacobian block of every configuration TRANSPOSED --
+ *        with the configurations of B trajectories laid out (B, n_wp, D) it IS the block-diagonal CSC `data` array of
+ *        each trajectory (column (waypoint, dof) holds that waypoint's S rows).  out_vals (N,S) nullable.  D <= 32. */
+SKB_API int skb_collfree_csc(const skb_plan *p, const skb_sdf *s, int32_t dtype, const void *q_dev, int64_t N,
+                             double margin, void *out_vals_dev, void *out_data_dev, void *stream);
 /* K3  PairWiseSelfCollFreeConst._evaluate = tinyfk.compute_inter_link_sqdists + threshold + row-min
  *        skmp/constraint.py:749-778.   values = |xi-xj|^2 - (ri+rj)^2
  *        SKB_MODE_ALL: (N,P), (N,P,D);  SKB_MODE_CLOSEST: (N,1), (N,1,D) */

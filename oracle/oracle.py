@@ -111,19 +111,23 @@ class Sdf:
             c.param[:] = list(param)
         self.arr, self.n = arr, len(prims)
 
-    def __call__(self, pts, with_grad=False, with_kink=False):
+    def __call__(self, pts, with_grad=False, with_kink=False, with_curv=False):
+        """values [, gradients] [, distance to the nearest gradient discontinuity] [, Lipschitz bound of the gradient (1/m)]"""
         pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
         m = len(pts)
         val = np.empty(m)
         grad = np.empty((m, 3))
         kink = np.empty(m)
+        curv = np.empty(m)
         lib().orc_sdf_eval(self.arr, self.n, _p(pts, C.c_double), C.c_int64(m), _p(val, C.c_double), _p(grad, C.c_double),
-                           _p(kink, C.c_double))
+                           _p(kink, C.c_double), _p(curv, C.c_double))
         out = (val,)
         if with_grad:
             out += (grad,)
         if with_kink:
             out += (kink,)
+        if with_curv:
+            out += (curv,)
         return out[0] if len(out) == 1 else out
 
 
@@ -165,8 +169,9 @@ def inter_link_sqdists(tree: Tree, qs, pairs, joint_links, base_type=BASE_FIXED,
 
 
 def collfree(tree: Tree, qs, feat_ids, joint_links, sdf: Sdf, radii, margin=0.0, base_type=BASE_FIXED, only_closest=False,
-             with_jacobian=True, grad_mode=GRAD_ANALYTIC, with_kink=False):
-    """CollFreeConst._evaluate restated (skmp/constraint.py:287-374)."""
+             with_jacobian=True, grad_mode=GRAD_ANALYTIC, with_kink=False, with_curv=False):
+    """CollFreeConst._evaluate restated (skmp/constraint.py:287-374).  with_kink / with_curv append, per output row, the
+    distance of the sphere centre to the nearest gradient discontinuity of the SDF and a Lipschitz bound of its gradient."""
     qs = np.ascontiguousarray(qs, dtype=np.float64)
     feat = np.ascontiguousarray(feat_ids, dtype=np.int32)
     jl = np.ascontiguousarray(joint_links, dtype=np.int32)
@@ -177,12 +182,18 @@ def collfree(tree: Tree, qs, feat_ids, joint_links, sdf: Sdf, radii, margin=0.0,
     vals = np.empty((n, m))
     jac = np.zeros((n, m, d)) if with_jacobian else np.empty(0)
     kink = np.empty((n, m))
+    curv = np.empty((n, m))
     rc = lib().orc_collfree(C.byref(tree.c), _p(qs, C.c_double), C.c_int64(n), _p(feat, C.c_int32), len(feat),
                             _p(jl, C.c_int32), len(jl), base_type, sdf.arr, sdf.n, _p(rad, C.c_double), C.c_double(margin),
                             int(only_closest), int(with_jacobian), grad_mode, _p(vals, C.c_double),
-                            _p(jac, C.c_double) if with_jacobian else None, _p(kink, C.c_double))
+                            _p(jac, C.c_double) if with_jacobian else None, _p(kink, C.c_double), _p(curv, C.c_double))
     assert rc == 0
-    return (vals, jac, kink) if with_kink else (vals, jac)
+    out = (vals, jac)
+    if with_kink:
+        out += (kink,)
+    if with_curv:
+        out += (curv,)
+    return out
 
 
 def collfree_threaded(n_threads: int, tree: Tree, qs, *args, keep: bool = True, block: int = 2048, **kw):

@@ -310,10 +310,19 @@ ORC_API int orc_inter_link_sqdists(const orc_tree *t, const double *qs, int64_t 
 /* ------------------------------------------------------------------ signed distance fields */
 static double sgn(double x) { return x >= 0.0 ? 1.0 : -1.0; }
 
-/* value, analytic gradient (local frame) and distance to the nearest gradient kink */
+/* Conditioning of the gradient at the last evaluated point: a Lipschitz bound (1/m) of the analytic gradient field
+ * around it.  A point that is off by dp (fp32 forward kinematics: up to 1e-6 m) sees a gradient that is off by up to
+ * curv * dp whatever the implementation -- 1/r at distance r from a box edge, a cylinder rim or axis, a sphere centre; the
+ * mixed second derivatives of the trilinear cell polynomial for a voxel grid.  The parity tests add that term to the
+ * Jacobian tolerance (tests/helpers.py::jac_tol) instead of a blanket slack factor. */
+static __thread double tl_curv = 0.0;
+
+/* value, analytic gradient (local frame) and distance to the nearest gradient DISCONTINUITY ("kink": medial axis inside a
+ * box / cylinder, edges and rims outside, voxel cell faces, the centre of a sphere) */
 static double prim_local(const orc_prim *pr, const double *pl, double *gl, double *kink) {
     gl[0] = gl[1] = gl[2] = 0.0;
     *kink = INFINITY;
+    tl_curv = 0.0;
     if (pr->type == SDF_BOX) {
         double s[3], qv[3], nq = 0.0; int outside = 0;
         for (int i = 0; i < 3; ++i) {
@@ -325,6 +334,13 @@ static double prim_local(const orc_prim *pr, const double *pl, double *gl, doubl
         if (outside) {
             double d = sqrt(nq);
             for (int i = 0; i < 3; ++i) gl[i] = sgn(pl[i]) * qv[i] / d;
+            /* nearest edge: at distance d in the edge / corner regions, sqrt(d^2 + (lateral distance to the face's border)^2)
+             * above a face (the gradient is constant there until the edge region begins) */
+            double a = fmax(s[0], fmax(s[1], s[2])), c = fmin(s[0], fmin(s[1], s[2]));
+            double second = s[0] + s[1] + s[2] - a - c;
+            double lat = second < 0.0 ? -second : 0.0;
+            *kink = sqrt(d*d + lat*lat);
+            tl_curv = 1.0 / *kink;
             return d;
         }
         int k = 0;
@@ -344,9 +360,11 @@ static double prim_local(const orc_prim *pr, const double *pl, double *gl, doubl
             double q0 = s0 > 0.0 ? s0 : 0.0, q1 = s1 > 0.0 ? s1 : 0.0;
             double d = sqrt(q0*q0 + q1*q1);
             gl[0] = ux*q0/d; gl[1] = uy*q0/d; gl[2] = sgn(pl[2])*q1/d;
+            *kink = sqrt(s0*s0 + s1*s1);                         /* the rim circle */
+            tl_curv = 1.0 / *kink + (s0 > 0.0 && rho > 0.0 ? 1.0 / rho : 0.0);
             return d;
         }
-        if (s0 >= s1) { gl[0] = ux; gl[1] = uy; *kink = fmin(s0 - s1, rho); return s0; }
+        if (s0 >= s1) { gl[0] = ux; gl[1] = uy; *kink = fmin(s0 - s1, rho); tl_curv = rho > 0.0 ? 1.0 / rho : INFINITY; return s0; }
         gl[2] = sgn(pl[2]); *kink = fmin(s1 - s0, fabs(pl[2]));
         return s1;
     }
@@ -354,6 +372,7 @@ static double prim_local(const orc_prim *pr, const double *pl, double *gl, doubl
         double n = sqrt(pl[0]*pl[0] + pl[1]*pl[1] + pl[2]*pl[2]);
         if (n > 0.0) { gl[0] = pl[0]/n; gl[1] = pl[1]/n; gl[2] = pl[2]/n; }
         *kink = n;
+        tl_curv = n > 0.0 ? 1.0 / n : INFINITY;
         return n - pr->param[0];
     }
     /* SDF_GRID: scipy RegularGridInterpolator(method="linear", bounds_error=False, fill_value) */
@@ -389,6 +408,12 @@ static double prim_local(const orc_prim *pr, const double *pl, double *gl, doubl
         double dy = (c10 - c00)*(1-fz) + (c11 - c01)*fz;
         double dz = c1 - c0;
         gl[0] = dx / h[0]; gl[1] = dy / h[1]; gl[2] = dz / h[2];
+        {   /* mixed second derivatives of the cell polynomial (the pure ones vanish) */
+            double a4 = c[6] - c[4] - c[2] + c[0], a5 = c[5] - c[4] - c[1] + c[0], a6 = c[3] - c[2] - c[1] + c[0];
+            double a7 = c[7] - c[6] - c[5] - c[3] + c[4] + c[2] + c[1] - c[0];
+            double fxy = (fabs(a4) + fabs(a7)) / (h[0]*h[1]), fxz = (fabs(a5) + fabs(a7)) / (h[0]*h[2]), fyz = (fabs(a6) + fabs(a7)) / (h[1]*h[2]);
+            tl_curv = fxy + fxz + fyz;
+        }
         return val;
     }
 }
@@ -404,25 +429,27 @@ static double prim_world(const orc_prim *pr, const double *p, double *g, double 
 
 /* UnionSDF: elementwise min over members (first index wins ties, like np.argmin) */
 static double union_eval(const orc_prim *prims, int np_, const double *p, double *g, double *kink) {
-    double best = INFINITY, second = INFINITY, bk = INFINITY, bg[3] = {0, 0, 0};
+    double best = INFINITY, second = INFINITY, bk = INFINITY, bc = 0.0, bg[3] = {0, 0, 0};
     for (int i = 0; i < np_; ++i) {
         double gi[3], ki;
         double v = prim_world(&prims[i], p, gi, &ki);
-        if (v < best) { second = best; best = v; bk = ki; bg[0] = gi[0]; bg[1] = gi[1]; bg[2] = gi[2]; }
+        if (v < best) { second = best; best = v; bk = ki; bc = tl_curv; bg[0] = gi[0]; bg[1] = gi[1]; bg[2] = gi[2]; }
         else if (v < second) second = v;
     }
     if (g) { g[0] = bg[0]; g[1] = bg[1]; g[2] = bg[2]; }
     if (kink) *kink = fmin(bk, second - best);
+    tl_curv = bc;
     return best;
 }
 
 ORC_API int orc_sdf_eval(const orc_prim *prims, int np_, const double *pts, int64_t M,
-                         double *out_val, double *out_grad, double *out_kink) {
+                         double *out_val, double *out_grad, double *out_kink, double *out_curv) {
     for (int64_t i = 0; i < M; ++i) {
         double g[3], k;
         out_val[i] = union_eval(prims, np_, pts + 3*i, g, &k);
         if (out_grad) { out_grad[3*i] = g[0]; out_grad[3*i+1] = g[1]; out_grad[3*i+2] = g[2]; }
         if (out_kink) out_kink[i] = k;
+        if (out_curv) out_curv[i] = tl_curv;
     }
     return 0;
 }
@@ -433,7 +460,7 @@ ORC_API int orc_collfree(const orc_tree *t, const double *qs, int64_t N,
                          const int32_t *feat_ids, int nf, const int32_t *joint_ids, int nj, int base_type,
                          const orc_prim *prims, int np_, const double *radii, double margin,
                          int only_closest, int with_jac, int grad_mode,
-                         double *out_vals, double *out_jac, double *out_kink) {
+                         double *out_vals, double *out_jac, double *out_kink, double *out_curv) {
     fkstate s;
     if (!fk_init(&s, t)) return -1;
     int D = nj + (base_type == BASE_PLANER ? 3 : (base_type == BASE_FLOATING ? 6 : 0));
@@ -458,6 +485,7 @@ ORC_API int orc_collfree(const orc_tree *t, const double *qs, int64_t N,
             union_eval(prims, np_, pts + 3*f, g, &kink);
             out_vals[row] = sd[f] - radii[f] - margin;
             if (out_kink) out_kink[row] = kink;
+            if (out_curv) out_curv[row] = tl_curv;
             if (!with_jac) continue;
             if (grad_mode == GRAD_FD) {
                 for (int i = 0; i < 3; ++i) {
@@ -476,4 +504,4 @@ ORC_API int orc_collfree(const orc_tree *t, const double *qs, int64_t N,
     return 0;
 }
 
-ORC_API int orc_version(void) { return 1; }
+ORC_API int orc_version(void) { return 2; }

@@ -189,6 +189,22 @@ int skb_collfree(const skb_plan *p, const skb_sdf *s, int32_t dtype, const void 
                        out_jac_dev, out_valid_dev, stream);
 }
 
+int skb_collfree_csc(const skb_plan *p, const skb_sdf *s, int32_t dtype, const void *q_dev, int64_t N, double margin,
+                     void *out_vals_dev, void *out_data_dev, void *stream) {
+    if (!p || !s || N < 0 || (N > 0 && (!q_dev || !out_data_dev))) return set_error("collfree_csc: bad arguments");
+    if (s->prims.empty()) return set_error("collfree_csc: the SDF has no primitive");
+    if (p->rot_type != SKB_ROT_IGNORE) return set_error("collfree_csc: the plan must be built with rot_type IGNORE");
+    if (s->prims.size() > 64) return set_error("collfree_csc: more than 64 SDF primitives");
+    if (p->D > 32) return set_error("collfree_csc: more than 32 columns (transpose the (N,S,D) blocks of skb_collfree instead)");
+    if (check_plan_device(p, "collfree_csc") != 0 || check_sdf_device(const_cast<skb_sdf *>(s), "collfree_csc") != 0) return -1;
+    const void *dp = get_dev_prims(const_cast<skb_sdf *>(s), dtype);
+    if (!dp) return -1;
+    const skb_s2_program *s2 = get_s2_program(const_cast<skb_plan *>(p), KIND_COLLFREE);
+    if (!s2) return set_error("collfree_csc: this plan is not served by the step kernel (D > 64, > 255 nodes, or SKB_KERNEL set)");
+    return launch_s2(p, s2, KIND_COLLFREE, dtype, q_dev, N, dp, get_host_prims(s, dtype), (int)s->prims.size(), margin, S2_MODE_ALL_CSC,
+                     out_vals_dev, out_data_dev, nullptr, stream);
+}
+
 int skb_pairwise(const skb_plan *p, int32_t dtype, const void *q_dev, int64_t N, int32_t mode, void *out_vals_dev,
                  void *out_jac_dev, uint8_t *out_valid_dev, void *stream) {
     if (!p || N < 0 || (N > 0 && !q_dev)) return set_error("pairwise: bad arguments");
@@ -222,6 +238,54 @@ int skb_com(const skb_plan *p, const skb_sdf *s, int32_t dtype, const void *q_de
     const skb_com_program *cp = get_com_program(const_cast<skb_plan *>(p));
     if (!cp) return -1;
     return launch_com(p, cp, dtype, q_dev, N, dp, n_prims, what, out_vals_dev, out_jac_dev, stream);
+}
+
+int skb_plan_tune(const skb_plan *p, const skb_sdf *s, int32_t dtype, const void *q_dev, int64_t N, double margin, int32_t mode,
+                  int32_t outputs, void *stream, int32_t *out_choice) {
+    if (!p || !q_dev || N <= 0) return set_error("plan_tune: bad arguments");
+    if (dtype != SKB_F32 && dtype != SKB_F64) return set_error("plan_tune: bad dtype");
+    if ((outputs & 7) == 0) return set_error("plan_tune: no output selected (1 values, 2 jacobians, 4 validity bytes)");
+    if (!s && !p->pairs_set) return set_error("plan_tune: pass an SDF (CollFreeConst) or set the plan's pairs (PairWiseSelfCollFreeConst)");
+    if (check_plan_device(p, "plan_tune") != 0) return -1;
+    const int64_t n = std::min<int64_t>(N, 262144);
+    const size_t es = esize(dtype);
+    const size_t M = mode == SKB_MODE_CLOSEST ? 1 : (s ? (size_t)p->F : p->pair_thr.size());
+    void *dv = nullptr, *dj = nullptr;
+    uint8_t *dvalid = nullptr;
+    int rc = 0;
+    if ((outputs & 1) && cudaMalloc(&dv, n * M * es) != cudaSuccess) rc = set_error("plan_tune: out of device memory");
+    if (rc == 0 && (outputs & 2) && cudaMalloc(&dj, n * M * p->D * es) != cudaSuccess) rc = set_error("plan_tune: out of device memory");
+    if (rc == 0 && (outputs & 4) && cudaMalloc(reinterpret_cast<void **>(&dvalid), n) != cudaSuccess) rc = set_error("plan_tune: out of device memory");
+    int made = 0;
+    if (rc == 0) {
+        s2_tune_begin(0);
+        rc = s ? skb_collfree(p, s, dtype, q_dev, n, margin, mode, dv, dj, dvalid, stream)
+               : skb_pairwise(p, dtype, q_dev, n, mode, dv, dj, dvalid, stream);
+        made = s2_tune_end(out_choice);
+        if (cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)) != cudaSuccess && rc == 0) rc = set_error("plan_tune: the timed launches failed");
+    }
+    if (dv) cudaFree(dv);
+    if (dj) cudaFree(dj);
+    if (dvalid) cudaFree(dvalid);
+    if (rc == 0 && !made && out_choice) out_choice[0] = -1;      // served by a kernel without launch candidates: nothing to tune
+    return rc;
+}
+
+int skb_plan_get_tuned(const skb_plan *p, const skb_sdf *s, int32_t dtype, int32_t mode, int32_t outputs, int32_t *out_choice) {
+    if (!p || !out_choice) return set_error("plan_get_tuned: bad arguments");
+    if ((outputs & 7) == 0) return set_error("plan_get_tuned: no output selected");
+    if (!s && !p->pairs_set) return set_error("plan_get_tuned: pass an SDF or set the plan's pairs");
+    // the launch path up to the kernel selection runs with placeholder (16-byte aligned, never dereferenced) buffers
+    void *fake = reinterpret_cast<void *>(uintptr_t(4096));
+    s2_tune_begin(1);
+    const int rc = s ? skb_collfree(p, s, dtype, fake, 1, 0.0, mode, (outputs & 1) ? fake : nullptr, (outputs & 2) ? fake : nullptr,
+                                    (outputs & 4) ? reinterpret_cast<uint8_t *>(fake) : nullptr, nullptr)
+                     : skb_pairwise(p, dtype, fake, 1, mode, (outputs & 1) ? fake : nullptr, (outputs & 2) ? fake : nullptr,
+                                    (outputs & 4) ? reinterpret_cast<uint8_t *>(fake) : nullptr, nullptr);
+    const int found = s2_tune_end(out_choice);
+    if (rc != 0) return rc;
+    if (!found) out_choice[0] = -1;
+    return 0;
 }
 
 int skb_com_host(const skb_plan *p_, const skb_sdf *s, int32_t dtype, const void *q_host, int64_t N, int32_t what,

@@ -177,7 +177,9 @@ __device__ __forceinline__ T sdf_grid_local(const DevPrim<T> &pr, T x, T y, T z,
     const T fx = ux - T(ix), fy = uy - T(iy), fz = uz - T(iz);
     const bool f64 = (pr.flags & PF_GRID_F64) != 0;
     T a[8];
-    if (pr.flags & PF_GRID_CELLS) {
+    // the packs are rounded to the grid's value type: fp64 arithmetic over an fp32 grid reads the corner samples instead
+    // (their differences are exact in fp64), so the fp64 build option keeps its 1e-10
+    if ((pr.flags & PF_GRID_CELLS) && (sizeof(T) == 4 || f64)) {
         const int64_t cell = ((int64_t)ix * (pr.dims[1] - 1) + iy) * (pr.dims[2] - 1) + iz;
         if (f64) {
             double c[8];

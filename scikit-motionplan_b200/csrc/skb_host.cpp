@@ -827,12 +827,24 @@ static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp, bool allo
     }
     sp->n_nodes = n_nodes; sp->n_levels = n_levels; sp->rows = rows; sp->n_cen = pairs ? nf : 0;
     sp->frame_stride = odd_quads(n_nodes * 12);
+    {   // structure hash (FNV-1a): tree, row tables, steps -- not the folded constants in F, which change with every
+        // reflect_skrobot_model while the best launch configuration does not
+        unsigned long long h = 1469598103934665603ull;
+        auto mix = [&](const void *data, size_t bytes) {
+            const unsigned char *b = reinterpret_cast<const unsigned char *>(data);
+            for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+        };
+        mix(I.data(), I.size() * sizeof(int32_t));
+        for (auto &st : sp->steps) { mix(&st.cm, sizeof(st.cm)); mix(&st.s0, sizeof(st.s0)); mix(&st.cntA, sizeof(st.cntA)); mix(&st.cntB, sizeof(st.cntB)); }
+        const int meta[4] = {rows, D, kind, allow_fuse ? 1 : 0};
+        mix(meta, sizeof(meta));
+        sp->hash = h;
+    }
     sp->supported = true;
     return 0;
 }
 
 static void free_s2(skb_s2_program &sp) {
-    s2_forget_program(&sp);
     if (sp.dI) cudaFree(sp.dI);
     if (sp.dF32) cudaFree(sp.dF32);
     if (sp.dF64) cudaFree(sp.dF64);

@@ -189,6 +189,7 @@ struct skb_s2_program {
     void *dMasks = nullptr;
     int n_nodes = 0, n_levels = 0, rows = 0, n_cen = 0;
     int frame_stride = 0;            // floats per configuration
+    unsigned long long hash = 0;     // FNV-1a of the program's STRUCTURE (I, step list, rows, D): the autotuner's cache key
     double phase2_slots = 0;         // issue-slot model of the steps of one configuration (the planner's cost)
     // the same rows without fused steps: half the staging block per warp, i.e. more resident warps when shared memory
     // limits the occupancy (wide rows, deep trees); the launcher scores both and takes the better one
@@ -275,7 +276,8 @@ int set_error(const std::string &msg);           // returns -1
 const skb_schedule *get_schedule(skb_plan *p, int rows);   // builds + uploads lazily; nullptr on error
 const skb_pair_program *get_pair_program(skb_plan *p);
 const skb_sphere_program *get_sphere_program(skb_plan *p);   // nullptr when the plan is not eligible (not an error)
-void s2_forget_program(const skb_s2_program *sp);              // skb_sphere2.cu: drops the autotuner's entries of a freed program
+void s2_tune_begin(int query_only);                                       // skb_sphere2.cu: brackets of skb_plan_tune (thread local)
+int s2_tune_end(int32_t out_choice[3]);                       // 1 when a choice was measured and stored
 const skb_s2_program *get_s2_program(skb_plan *p, int kind);   // KIND_COLLFREE / KIND_PAIRWISE; nullptr when not eligible
 const void *get_dev_prims(skb_sdf *s, int dtype);
 const void *get_host_prims(const skb_sdf *s, int dtype);   // valid after get_dev_prims succeeded for that dtype
@@ -306,6 +308,7 @@ int launch_s2(const skb_plan *p, const skb_s2_program *sp, int kind, int dtype, 
               const void *host_prims, int n_prims, double margin, int mode, void *out_vals, void *out_jac, uint8_t *out_valid,
               void *stream);
 enum { KIND_MAP = 0, KIND_COLLFREE = 1, KIND_PAIRWISE = 2 };
+enum { S2_MODE_ALL_CSC = 100 };      // internal launch_s2 mode: SKB_MODE_ALL with transposed Jacobian blocks (skb_collfree_csc)
 
 extern std::atomic<int64_t> g_launch_count;
 // every compute entry point runs on the device its handles were created on (one handle per device; skb_api.cpp)

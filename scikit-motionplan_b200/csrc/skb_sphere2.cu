@@ -154,7 +154,12 @@ template <typename T, typename MaskT> struct RowState {   // what phase 2 keeps 
 // RED = true : per-configuration reduction -- closest row (np.argmin: first index wins ties) and / or validity byte
 // NPMAX: compile-time bound on the number of column pairs (the Jacobian loop is fully unrolled against it, so twist
 // addresses and column bits become immediates)
-template <typename T, int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX>
+// CSC = true (full-output mode with Jacobians only): the Jacobian block of a configuration is written TRANSPOSED, [D][R] -- the
+// order of the block-diagonal CSC `data` array of the SQP solver's stacked constraint Jacobian (one column per (waypoint,
+// dof), rows of the waypoint's constraint inside it: skmp/solver/nlp_solver/trajectory_constraint.py:157-194).  In that
+// layout the rows of a step are consecutive addresses of ONE column, i.e. lane-per-row stores are coalesced as they are:
+// no staging block, no bulk store, one 128-byte store per (column, half).
+template <typename T, int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX, bool CSC = false>
 __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIND_COLLFREE && SDFK == SDF_GRID_FAST && JAC && !RED) ? 4 : SKB_S2_BLOCKS) s2_kernel(const __grid_constant__ S2Params<T> prm) {
     using V4 = Vec4<T>;
     using Rl = Real<T>;
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
         const int g_live = (int)min((long long)G, prm.N - n0);
         // the staging block shares its shared memory with the q / sin-cos scratch of phase 1: the last bulk store of the
         // previous tile must have finished reading it
-        if (JAC && !RED && lane == 0) bulk_wait_read<0>();
+        if (JAC && !RED && !CSC && lane == 0) bulk_wait_read<0>();
         __syncwarp();
         // q tile + one fully populated sin/cos pass over all G*D joint values
 #pragma unroll
@@ -324,7 +329,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
                 if (sizeof(T) == 4) asm volatile("" : "+r"(cntA), "+r"(cntB));
                 // output addresses of the step, formed once per (tile, step): configuration c adds c * R (* D) to them
                 T *step_vals = tile_vals + (unsigned)(s0 + lane);
-                T *step_jac = JAC ? tile_jac + (unsigned)(s0 * D) : nullptr;
+                T *step_jac = JAC ? (CSC ? tile_jac + (unsigned)(s0 + lane) : tile_jac + (unsigned)(s0 * D)) : nullptr;
                 if (sizeof(T) == 4) asm volatile("" : "+l"(step_vals), "+l"(step_jac));
                 const int4 B0 = tabB[slot * 32 + lane];
                 const int4 B1 = tabB[(slot + (cntB > 0 ? 1 : 0)) * 32 + lane];
@@ -368,6 +373,32 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
                         if (HAS_B && lane < cntB) st_stream(gv + 32, vb);
                     }
                     if (!JAC) return;
+                    if (CSC) {
+                        // transposed block: element (row, col) of configuration c at  c R D + col R + row
+                        T *gA = step_jac + (unsigned)(c * R * D);          // step_jac already points at row s0 + lane of column 0
+                        const V4 *t4 = reinterpret_cast<const V4 *>(tw);
+                        const bool inA = lane < cntA, inB = HAS_B && lane < cntB;
+#pragma unroll
+                        for (int jp = 0; jp < NPMAX; ++jp) {
+                            const int col = 2 * jp;
+                            if (col < D) {
+                                V2 a = P2::make(T(0), T(0)), b = a;
+                                if (pact & (1u << jp)) {
+                                    const V4 t0 = t4[3 * jp], t1 = t4[3 * jp + 1], t2 = t4[3 * jp + 2];
+                                    a = contract(t0, t1, t2, ra, col);
+                                    if (HAS_B) b = contract(t0, t1, t2, rb, col);
+                                }
+                                T *g0 = gA + (unsigned)(col * R);
+                                if (inA) st_stream(g0, a.x);
+                                if (inB) st_stream(g0 + 32, b.x);
+                                if (col + 1 < D) {
+                                    if (inA) st_stream(g0 + R, a.y);
+                                    if (inB) st_stream(g0 + R + 32, b.y);
+                                }
+                            }
+                        }
+                        return;
+                    }
                     T *rowA = wstage + row_off;
                     T *rowB = rowA + 32 * D;
                     // the bulk store of the previous step must have finished reading the staging block
@@ -417,7 +448,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
 
                 // (a step whose rows touch every column pair between them rewrites its whole block per configuration:
                 // nothing to fill)
-                if (JAC && pact != (NP >= 32 ? 0xffffffffu : (1u << NP) - 1u)) {
+                if (JAC && !CSC && pact != (NP >= 32 ? 0xffffffffu : (1u << NP) - 1u)) {
                     // zero fill of the step's staging block, once per (tile, step): the columns no row of the step needs
                     // keep their structural zeros while the configurations of the tile pass through
                     if (lane == 0) bulk_wait_read<0>();
@@ -553,7 +584,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
             }
         }
     }       // tiles
-    if (JAC && !RED) bulk_wait_read<0>();   // shared memory must outlive the last bulk reads
+    if (JAC && !RED && !CSC) bulk_wait_read<0>();   // shared memory must outlive the last bulk reads
 }
 
 // ------------------------------------------------------------------ launcher
@@ -595,7 +626,7 @@ struct S2Launch {
     double score = -1.0;
 };
 
-template <typename T, int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX>
+template <typename T, int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX, bool CSC = false>
 static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void *q, int64_t N, const void *dev_prims,
                         const void *host_prims, int n_prims, double margin, void *out_vals, void *out_jac, uint8_t *out_valid,
                         S2Launch<T> &L, int force_g = 0, int force_w = 0) {
@@ -660,7 +691,7 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
         prm.woff_q = e;      e += align_up(g * D, al);
         prm.woff_sc = e;     e += align_up(2 * g * D, al);
         // q / sin-cos are dead after phase 1, the staging block is written in phase 2 only: they share the head of the slab
-        const int stage_elems = (JAC && !RED) ? align_up(stage_rows * D, al) : 0;
+        const int stage_elems = (JAC && !RED && !CSC) ? align_up(stage_rows * D, al) : 0;
         prm.woff_stage = 0;  e = std::max(e, stage_elems);
         prm.woff_frames = e; e += g * prm.fstride;
         prm.woff_tw = e;     e += JAC ? g * prm.tstride : 0;
@@ -672,7 +703,7 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
     // (three lanes per node, `slots3` nodes of a level at once) but costs shared memory, i.e. resident warps.  Every
     // candidate is scored with a small issue-slot model:  (resident warps)^0.75 / (FK slots + phase-2 slots per
     // configuration);  the occupancy comes from the runtime (registers and shared memory).
-    auto kern = s2_kernel<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>;
+    auto kern = s2_kernel<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX, CSC>;
     static const int cand[][2] = {{8, 8}, {8, 6}, {8, 5}, {8, 4}, {8, 3}, {8, 2}, {4, 8}, {4, 7}, {4, 6}, {4, 5}, {4, 4}, {4, 3}, {4, 2},
                                   {2, 8}, {2, 6}, {2, 5}, {2, 4}, {2, 3}, {2, 2}, {1, 8}, {1, 6}, {1, 4}, {1, 2}, {1, 1}};
     int halves = 0;
@@ -733,27 +764,69 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
     return 0;
 }
 
-// Launch-configuration cache of the autotuner: (program, kernel instantiation, output alignment class) -> choice.
+// Launch-configuration cache of the autotuner: (structure hash of the program, kernel instantiation, output class) -> choice.
+// The key is CONTENT based (skb_s2_program::hash covers the tree, the row tables and the step list, not the folded
+// constants), so a choice survives every plan rebuild after set_q / reflect_skrobot_model and can be persisted:
+// SKB_TUNE_CACHE=<file> is read once and appended to whenever a new choice is made.
 struct S2Choice { int unfused, G, warps; };
+typedef std::tuple<unsigned long long, unsigned, unsigned> S2Key;
 static std::mutex g_tune_mu;
-static std::map<std::tuple<const void *, const void *, size_t, int>, S2Choice> g_tune;
+static std::map<S2Key, S2Choice> g_tune;
+static bool g_tune_loaded = false;
+static thread_local int tl_tune_request = 0;        // 1: skb_plan_tune is running on this thread; 2: ... and a choice was made;
+                                                    // 3: skb_plan_get_tuned (look the stored choice up, launch nothing)
+static thread_local S2Choice tl_tune_result = {-1, 0, 0};
 
-// a program that is freed (plan destroyed, pair list replaced) takes its tuned choices with it: its address may be reused
-void s2_forget_program(const skb_s2_program *sp) {
+static void tune_cache_load_locked() {
+    if (g_tune_loaded) return;
+    g_tune_loaded = true;
+    const char *path = getenv("SKB_TUNE_CACHE");
+    if (!path) return;
+    if (FILE *f = fopen(path, "r")) {
+        unsigned long long h; unsigned inst, flags; int u, g, w;
+        while (fscanf(f, "%llx %x %x %d %d %d", &h, &inst, &flags, &u, &g, &w) == 6)
+            if (u >= 0 && u <= 1 && g >= 1 && g <= 8 && w >= 1 && w <= 8) g_tune[S2Key(h, inst, flags)] = S2Choice{u, g, w};
+        fclose(f);
+    }
+}
+static bool tune_lookup(const S2Key &key, S2Choice &ch) {
     std::lock_guard<std::mutex> lk(g_tune_mu);
-    for (auto it = g_tune.begin(); it != g_tune.end();) it = std::get<0>(it->first) == (const void *)sp ? g_tune.erase(it) : std::next(it);
+    tune_cache_load_locked();
+    auto it = g_tune.find(key);
+    if (it == g_tune.end()) return false;
+    ch = it->second;
+    return true;
+}
+static void tune_store(const S2Key &key, const S2Choice &ch) {
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    tune_cache_load_locked();
+    g_tune[key] = ch;
+    if (const char *path = getenv("SKB_TUNE_CACHE"))
+        if (FILE *f = fopen(path, "a")) {
+            fprintf(f, "%llx %x %x %d %d %d\n", std::get<0>(key), std::get<1>(key), std::get<2>(key), ch.unfused, ch.G, ch.warps);
+            fclose(f);
+        }
+}
+// skb_plan_tune (skb_api.cpp) brackets one compute call with these: the step-kernel launch inside it times its candidates
+// whatever the batch size and reports the choice
+void s2_tune_begin(int query_only) { tl_tune_request = query_only ? 3 : 1; tl_tune_result = S2Choice{-1, 0, 0}; }
+int s2_tune_end(int32_t out_choice[3]) {
+    const int made = tl_tune_request == 2 ? 1 : 0;
+    tl_tune_request = 0;
+    if (out_choice) { out_choice[0] = tl_tune_result.unfused; out_choice[1] = tl_tune_result.G; out_choice[2] = tl_tune_result.warps; }
+    return made;
 }
 
-template <typename T, int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX = 1>
+template <typename T, int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX = 1, bool CSC = false>
 static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const void *q, int64_t N, const void *dev_prims,
                           const void *host_prims, int n_prims, double margin, void *out_vals, void *out_jac, uint8_t *out_valid,
                           cudaStream_t stream) {
-    auto kern = s2_kernel<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>;
+    auto kern = s2_kernel<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX, CSC>;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     static const bool verbose = getenv("SKB_S2_VERBOSE") != nullptr;
     auto configure = [&](const skb_s2_program *prog, int64_t n, S2Launch<T> &out, int fg, int fw) {
-        return configure_s2<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX>(p, prog, q, n, dev_prims, host_prims, n_prims, margin, out_vals,
-                                                                       out_jac, out_valid, out, fg, fw);
+        return configure_s2<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX, CSC>(p, prog, q, n, dev_prims, host_prims, n_prims, margin, out_vals,
+                                                                            out_jac, out_valid, out, fg, fw);
     };
     auto launch = [&](const S2Launch<T> &L) {
         const long long want = (L.prm.n_tiles + L.warps - 1) / L.warps;
@@ -780,31 +853,38 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
         return 0;
     };
 
-    // ---- autotuned choice.  Which (program, G, warps per CTA) is fastest depends on how CTAs and warps land on the SM
+    // ---- measured choice.  Which (program, G, warps per CTA) is fastest depends on how CTAs and warps land on the SM
     // sub-partitions, the L1 carve-out and the DRAM access pattern -- PR2 dual arm: 4 CTAs of 6 warps run at 0.70 of the
     // HBM roofline, 3 CTAs of 8 warps (the same 24 resident warps) at 0.67, 4 CTAs of 7 warps at 0.65 -- which no
-    // occupancy model predicts.  So the first large launch of a (plan, kernel) pair times every feasible candidate on a
-    // slice of its own batch (every candidate writes bit-identical results) and later launches reuse the winner.
-    static const int tune_min = getenv("SKB_S2_AUTOTUNE_MIN") ? atoi(getenv("SKB_S2_AUTOTUNE_MIN")) : 65536;
+    // occupancy model predicts.  Candidates are timed (every one writes bit-identical results)
+    //   * by skb_plan_tune(): explicitly, on scratch outputs of its own, for any batch size, or
+    //   * inside a user call only when the batch has at least SKB_S2_AUTOTUNE_MIN configurations (default 2^20: a call
+    //     that long does not notice the 30-130 ms) and SKB_S2_AUTOTUNE is not 0;
+    // the choice is kept under a content key (see above), reused by every later launch of a structurally equal program and
+    // optionally persisted (SKB_TUNE_CACHE).  Smaller batches without a stored choice, launches inside a stream capture and
+    // forced configurations use the issue-slot model.
+    static const int tune_min = getenv("SKB_S2_AUTOTUNE_MIN") ? atoi(getenv("SKB_S2_AUTOTUNE_MIN")) : (1 << 20);
     static const bool autotune = getenv("SKB_S2_AUTOTUNE") == nullptr || atoi(getenv("SKB_S2_AUTOTUNE")) != 0;
     const bool forced = p->tune_chunk > 0 || p->tune_warps > 0 || p->tune_ctas > 0 || getenv("SKB_S2_G") || getenv("SKB_S2_WARPS");
-    if (autotune && !forced) {
-        const auto key = std::make_tuple((const void *)sp, (const void *)kern, sp->I.size() * 131 + (size_t)sp->rows,
-                                         (int)(reinterpret_cast<uintptr_t>(out_jac) % 16 == 0) | (out_vals != nullptr ? 2 : 0) | (out_valid != nullptr ? 4 : 0));
+    const bool explicit_tune = tl_tune_request != 0;
+    if ((autotune || explicit_tune) && !forced) {
+        constexpr unsigned inst = (unsigned)sizeof(T) | (unsigned)KIND << 4 | (unsigned)SDFK << 8 | (unsigned)VW << 12 |
+                                  (unsigned)sizeof(MaskT) << 16 | (RED ? 1u << 20 : 0u) | (JAC ? 1u << 21 : 0u) | (CSC ? 1u << 22 : 0u) | (unsigned)NPMAX << 24;
+        const S2Key key(sp->hash, inst, (unsigned)((reinterpret_cast<uintptr_t>(out_jac) % 16 == 0) | (out_vals != nullptr ? 2 : 0) | (out_valid != nullptr ? 4 : 0)));
         S2Choice ch{-1, 0, 0};
-        {
-            std::lock_guard<std::mutex> lk(g_tune_mu);
-            auto it = g_tune.find(key);
-            if (it != g_tune.end()) ch = it->second;
+        if (tl_tune_request == 3) {                 // query: report the stored choice, launch nothing
+            if (tune_lookup(key, ch)) { tl_tune_result = ch; tl_tune_request = 2; }
+            return 0;
         }
+        const bool known = !explicit_tune && tune_lookup(key, ch);
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        if (ch.unfused < 0 && N < tune_min) ch.unfused = -2;           // too small to time: heuristic (a tuned choice is reused, though)
-        if (ch.unfused < 0 && (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)) ch.unfused = -2;   // no timing inside a capture
-        if (ch.unfused == -1) {
+        if (!known && !explicit_tune && N < tune_min) ch.unfused = -2;           // too small to time inside a user call: model
+        if (!known && ch.unfused == -1 && (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)) ch.unfused = -2;   // no timing inside a capture
+        if (!known && ch.unfused == -1) {
             const int64_t n_try = std::min<int64_t>(N, 262144);
-            cudaEvent_t e0, e1;
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
             CUDA_OK(cudaEventCreate(&e0));
-            CUDA_OK(cudaEventCreate(&e1));
+            if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); return set_error("step kernel autotuner: cudaEventCreate failed"); }
             static const int gs[] = {8, 4, 2, 1}, ws[] = {8, 7, 6, 5, 4, 3, 2};
             float best_ms = 1e30f, model_ms = 1e30f;
             S2Choice model{-1, 0, 0};                                    // what the issue-slot model would launch
@@ -837,8 +917,8 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
             cudaEventDestroy(e1);
             CUDA_OK(cudaGetLastError());
             if (ch.unfused >= 0) {
-                std::lock_guard<std::mutex> lk(g_tune_mu);
-                g_tune[key] = ch;
+                tune_store(key, ch);
+                if (explicit_tune) { tl_tune_request = 2; tl_tune_result = ch; }
                 if (verbose) fprintf(stderr, "[skb] autotune picked %s G=%d warps=%d\n", ch.unfused ? "unfused" : "fused", ch.G, ch.warps);
             }
         }
@@ -878,6 +958,14 @@ static int launch_s2_mode(S2_SIG, int mode) {
     }
     if (!jac) return launch_s2_inst<T, KIND, SDFK, 1, unsigned, false, false>(S2_ARGS);
     const int NP = (p->D + 1) / 2;
+    if (mode == S2_MODE_ALL_CSC) {              // transposed Jacobian blocks (CollFreeConst rows of an SQP trajectory stack)
+        if (KIND != KIND_COLLFREE || NP > 16) return set_error("csc output: CollFreeConst with at most 32 columns");
+#define S2_CSC(NPM) launch_s2_inst<T, KIND_COLLFREE, (KIND == KIND_COLLFREE ? SDFK : SDF_SINGLE), 1, unsigned, false, true, NPM, true>(S2_ARGS)
+        if (NP <= 4) return S2_CSC(4);
+        if (NP <= 8) return S2_CSC(8);
+        return S2_CSC(16);
+#undef S2_CSC
+    }
 #define S2_FULL(VWv, MT, NPM) launch_s2_inst<T, KIND, SDFK, VWv, MT, false, true, NPM>(S2_ARGS)
     if (NP <= 4) return even ? S2_FULL(2, unsigned, 4) : S2_FULL(1, unsigned, 4);
     if (NP <= 8) return even ? S2_FULL(2, unsigned, 8) : S2_FULL(1, unsigned, 8);

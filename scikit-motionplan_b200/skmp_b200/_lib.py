@@ -51,9 +51,12 @@ def _declare(lib):
         "skb_plan_set_pairs": ([vp, pi32, i32, pdbl], C.c_int),
         "skb_plan_set_weights": ([vp, pdbl], C.c_int),
         "skb_plan_set_tuning": ([vp, i32, i32, i32, i32], C.c_int),
+        "skb_plan_tune": ([vp, vp, i32, vp, i64, dbl, i32, i32, vp, pi32], C.c_int),
+        "skb_plan_get_tuned": ([vp, vp, i32, i32, i32, pi32], C.c_int),
         "skb_plan_destroy": ([vp], None),
         "skb_fk": ([vp, i32, vp, i64, i32, vp, vp, vp], C.c_int),
         "skb_collfree": ([vp, vp, i32, vp, i64, dbl, i32, vp, vp, vp, vp], C.c_int),
+        "skb_collfree_csc": ([vp, vp, i32, vp, i64, dbl, vp, vp, vp], C.c_int),
         "skb_pairwise": ([vp, i32, vp, i64, i32, vp, vp, vp, vp], C.c_int),
         "skb_com": ([vp, vp, i32, vp, i64, i32, vp, vp, vp], C.c_int),
         "skb_com_host": ([vp, vp, i32, vp, i64, i32, vp, vp], C.c_int),

@@ -144,6 +144,143 @@ def is_valid_motion_step_batch(motion_step_box, q1s, q2s, ineq_const, dtype=np.f
 
 
 # ------------------------------------------------------------------ trajectory-constraint stacking for SQP
+class TrajectoryBatchStack:
+    """Batched ``TrajectoryConstraint.evaluate`` (skmp/solver/nlp_solver/trajectory_constraint.py:128-195) for the
+    local-constraint table, for B trajectories at once, entirely on the GPU.
+
+    ``local_constraint_table`` maps waypoint index -> constraint (insertion order = row order, like the reference's
+    ``local_table.keys()`` loop).  The stacked Jacobian of one trajectory is block diagonal, (M_total, n_wp * n_dof): the
+    block of waypoint i sits in rows ``head_i .. head_i + M_i`` and columns ``i * n_dof .. (i + 1) * n_dof``.  Its CSC
+    pattern is fixed by the table (the reference's ``determine_sparse_pattern``, :34-47): ``indices`` / ``indptr`` are built
+    once; ``evaluate_batch_csc`` returns ``values (B, M_total)`` and ``data (B, nnz)`` with ``data[b]`` the CSC ``data``
+    array of trajectory b -- for waypoints in ascending order the (n_dof, M_i) transpose of the waypoint's Jacobian.
+
+    One launch per distinct constraint over all B x (its waypoints) rows.  A ``CollFreeConst`` writes its transposed blocks
+    straight into ``data`` (``evaluate_csc``); when one constraint covers every waypoint -- the SQP solver's global
+    inequality constraint -- nothing is gathered, copied or transposed at all."""
+
+    def __init__(self, n_dof: int, n_wp: int, local_constraint_table: Dict[int, object]):
+        self.n_dof, self.n_wp = n_dof, n_wp
+        self.table = dict(local_constraint_table)
+        for i in self.table:
+            if not (0 <= i < n_wp):
+                raise ValueError("index {} exceeds the waypoint number {}".format(i, n_wp))
+        self._layout = None
+        self._dev_index = {}
+
+    # groups: constraint object -> waypoint indices, in table order
+    def _groups(self):
+        groups: Dict[int, Tuple[object, List[int]]] = {}
+        for i, const in self.table.items():
+            groups.setdefault(id(const), (const, []))[1].append(i)
+        return list(groups.values())
+
+    @staticmethod
+    def _rows_of(const, n_dof: int) -> int:
+        if hasattr(const, "colkin") and hasattr(const, "sdf"):                    # CollFreeConst
+            return 1 if const.only_closest_feature else const.colkin.n_feature
+        if hasattr(const, "check_sphere_id_pairs"):                               # PairWiseSelfCollFreeConst
+            return 1 if const.only_closest_feature else len(const.check_sphere_id_pairs)
+        if hasattr(const, "efkin") and hasattr(const, "desired_poses"):           # PoseConstraint
+            return const.efkin.n_feature * const.efkin.dim_tspace
+        v, _ = const.evaluate(np.zeros((1, n_dof)), False)                       # anything else: ask it once
+        return int(v.shape[1])
+
+    def layout(self):
+        """(heads {waypoint: first row}, m_total, indices (nnz,), indptr (n_wp * n_dof + 1,), data offsets {waypoint: offset})."""
+        if self._layout is None:
+            dims = {i: self._rows_of(c, self.n_dof) for i, c in self.table.items()}
+            heads, head = {}, 0
+            for i in self.table:                       # row order = table order
+                heads[i] = head
+                head += dims[i]
+            indptr = np.zeros(self.n_dof * self.n_wp + 1, dtype=np.int64)
+            indices, doff, off = [], {}, 0
+            for i in range(self.n_wp):                 # column order = waypoint order
+                m = dims.get(i, 0)
+                if m:
+                    doff[i] = off
+                    off += m * self.n_dof
+                for d in range(self.n_dof):
+                    indptr[i * self.n_dof + d + 1] = indptr[i * self.n_dof + d] + m
+                    if m:
+                        indices.append(heads[i] + np.arange(m))
+            self._layout = (heads, head, np.concatenate(indices) if indices else np.zeros(0, dtype=np.int64), indptr, doff, dims)
+        return self._layout
+
+    @property
+    def indices(self) -> np.ndarray:
+        return self.layout()[2]
+
+    @property
+    def indptr(self) -> np.ndarray:
+        return self.layout()[3]
+
+    @property
+    def shape(self) -> Tuple[int, int]:
+        return self.layout()[1], self.n_dof * self.n_wp
+
+    def evaluate_batch_csc(self, traj_vectors):
+        """``traj_vectors`` (B, n_wp * n_dof), numpy or CUDA torch (fp32 / fp64) -> (values (B, M_total), data (B, nnz)) of the
+        same array kind; with ``indices`` / ``indptr`` each row is one trajectory's CSC Jacobian."""
+        if torch is None or not torch.cuda.is_available():
+            raise RuntimeError("TrajectoryBatchStack needs a CUDA device (no CPU fallback)")
+        is_np = not _is_torch(traj_vectors)
+        t = torch.as_tensor(np.ascontiguousarray(traj_vectors)) if is_np else traj_vectors
+        if t.dtype not in (torch.float32, torch.float64):
+            t = t.to(torch.float64)
+        if not t.is_cuda:
+            t = t.cuda()
+        B = t.shape[0]
+        trajs = t.reshape(B, self.n_wp, self.n_dof)
+        heads, m_total, indices, _, doff, dims = self.layout()
+        nnz = len(indices)
+        groups = self._groups()
+        values = data = None
+        if len(groups) == 1 and list(self.table) == list(range(self.n_wp)):
+            # one constraint on every waypoint in order: its outputs ARE the stacked arrays
+            const = groups[0][0]
+            v, d = self._block(const, trajs.reshape(B * self.n_wp, self.n_dof))
+            values, data = v.reshape(B, m_total), d.reshape(B, nnz)
+        else:
+            values = torch.empty((B, m_total), dtype=t.dtype, device=t.device)
+            data = torch.empty((B, nnz), dtype=t.dtype, device=t.device)
+            for const, idxs in groups:
+                order = sorted(idxs)
+                rows = trajs[:, order, :].reshape(B * len(order), self.n_dof)
+                v, d = self._block(const, rows)
+                m = dims[order[0]]
+                vcols, dcols = self._positions(const, order, heads, doff, m, t.device)
+                values.index_copy_(1, vcols, v.reshape(B, len(order) * m))
+                data.index_copy_(1, dcols, d.reshape(B, len(order) * m * self.n_dof))
+        if is_np:
+            return values.cpu().numpy(), data.cpu().numpy()
+        return values, data
+
+    def _block(self, const, rows):
+        """values (n, M), transposed Jacobian blocks (n, n_dof, M)."""
+        if hasattr(const, "evaluate_csc"):
+            return const.evaluate_csc(rows)
+        v, j = const.evaluate(rows, True)
+        return v, j.transpose(1, 2).contiguous()
+
+    def _positions(self, const, order, heads, doff, m, device):
+        key = (id(const), str(device))
+        pos = self._dev_index.get(key)
+        if pos is None:
+            vcols = np.concatenate([heads[i] + np.arange(m) for i in order])
+            dcols = np.concatenate([doff[i] + np.arange(m * self.n_dof) for i in order])
+            pos = self._dev_index[key] = (torch.as_tensor(vcols, device=device), torch.as_tensor(dcols, device=device))
+        return pos
+
+    def csc_matrix(self, data_row):
+        """scipy CSC matrix of one trajectory from its ``data`` row (host side, for a QP solver that wants scipy)."""
+        from scipy.sparse import csc_matrix
+
+        d = data_row.cpu().numpy() if _is_torch(data_row) else np.asarray(data_row)
+        return csc_matrix((d.astype(np.float64), self.indices, self.indptr), shape=self.shape)
+
+
 class TrajectoryConstraintStack:
     """Batched ``TrajectoryConstraint.evaluate`` (trajectory_constraint.py:128-195) for the local-constraint table.
 
@@ -160,6 +297,7 @@ class TrajectoryConstraintStack:
             if not (0 <= i < n_wp):
                 raise ValueError("index {} exceeds the waypoint number {}".format(i, n_wp))
         self._pattern = None
+        self._gpu_stack = None
 
     # groups: constraint object -> waypoint indices, in table order
     def _groups(self):
@@ -195,11 +333,19 @@ class TrajectoryConstraintStack:
         self._pattern = (heads, head, np.concatenate(indices) if indices else np.zeros(0, dtype=np.int64), indptr, dict(dims))
 
     def evaluate(self, traj_vector: np.ndarray):
-        """-> (values (M_total,), scipy.sparse.csc_matrix (M_total, n_wp * n_dof)), equal to the reference's."""
+        """-> (values (M_total,), scipy.sparse.csc_matrix (M_total, n_wp * n_dof)), equal to the reference's.  With a CUDA
+        device the blocks and the CSC ``data`` array come from ``TrajectoryBatchStack`` (B = 1): one launch per distinct
+        constraint, nothing is looped over or transposed on the host."""
         from scipy.sparse import csc_matrix
 
-        traj = np.asarray(traj_vector).reshape(-1, self.n_dof)
+        traj = np.asarray(traj_vector, dtype=np.float64).reshape(-1, self.n_dof)
         assert len(traj) == self.n_wp
+        if torch is not None and torch.cuda.is_available():
+            if self._gpu_stack is None:
+                self._gpu_stack = TrajectoryBatchStack(self.n_dof, self.n_wp, self.table)
+            st = self._gpu_stack
+            values, data = st.evaluate_batch_csc(traj.reshape(1, -1))
+            return values[0], csc_matrix((data[0], st.indices, st.indptr), shape=st.shape)
         blocks = self._blocks(traj)
         dims = {i: len(blocks[i][0]) for i in self.table}
         if self._pattern is None or self._pattern[4] != dims:

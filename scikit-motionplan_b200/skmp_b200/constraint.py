@@ -319,6 +319,27 @@ class CollFreeConst(AbstractIneqConst):
         b, vals, jac, _ = self._run(qs, True, with_jacobian, False)
         return b.out(vals), (b.out(jac) if with_jacobian else self.dummy_jacobian())
 
+    def evaluate_csc(self, qs):
+        """values (N, M) and the Jacobian block of every configuration TRANSPOSED, (N, D, M): the order in which the SQP
+        solver's stacked, block-diagonal CSC Jacobian stores a waypoint's rows (one column per (waypoint, dof);
+        skmp/solver/nlp_solver/trajectory_constraint.py:157-194).  For CUDA tensors in all-spheres mode with D <= 32 the
+        kernel writes that layout directly (``skb_collfree_csc``: lane-per-row stores are coalesced in it, no staging);
+        otherwise the (N, M, D) blocks are transposed afterwards.  Same numbers as ``evaluate`` bit for bit."""
+        if not self.reflect_robot_flag:
+            raise RuntimeError("{}: you need to call reflect_skrobot_model beforehand".format(type(self).__name__))
+        b = Batch(qs, self.colkin.dim_cspace)
+        plan = self._plan(b.device_index)
+        if not b.on_device or self.only_closest_feature or plan.dim_cspace > 32:
+            v, j = self._evaluate(qs, True)
+            jt = j.transpose(1, 2).contiguous() if _is_torch(j) else np.ascontiguousarray(np.swapaxes(j, 1, 2))
+            return v, jt
+        vals = b.empty((b.n, plan.n_feature))
+        data = b.empty((b.n, plan.dim_cspace, plan.n_feature))
+        with b.device_ctx():
+            _lib.check(_lib.lib().skb_collfree_csc(plan.handle, self.sdf.native(b.device_index), b.dtype_code, b.q_ptr, b.n,
+                                                   float(self.distance_margin), b.ptr(vals), b.ptr(data), b.stream))
+        return vals, data
+
     def _min_values(self, qs):
         """Row minimum of the values, (N, 1): the closest-mode kernel without Jacobian (what a composite needs)."""
         if not self.reflect_robot_flag:
@@ -333,6 +354,46 @@ class CollFreeConst(AbstractIneqConst):
         b, _, _, valid = self._run(qs, False, False, True)
         out = b.out(valid)
         return out.bool() if _is_torch(out) else out.astype(bool)
+
+    def tune(self, qs, with_jacobian: bool = True, values: bool = True, validity: bool = False):
+        """Measure the kernel launch configuration for this constraint's (mode, dtype, outputs) once, explicitly, on up to
+        262 144 of the sample configurations ``qs`` (a CUDA tensor) and on scratch outputs of the library's own
+        (``skb_plan_tune``).  The choice is keyed by the plan's structure: it survives ``reflect_skrobot_model`` and is
+        shared by every structurally equal constraint; ``SKB_TUNE_CACHE=<file>`` persists it.  Calls of fewer than 2^20
+        configurations never tune on their own.  Results do not depend on the choice.
+        -> (unfused, G, warps) or None when the serving kernel has no launch candidates."""
+        import ctypes as C
+
+        if not self.reflect_robot_flag:
+            raise RuntimeError("{}: you need to call reflect_skrobot_model beforehand".format(type(self).__name__))
+        b = Batch(qs, self.colkin.dim_cspace)
+        if not b.on_device:
+            raise ValueError("tune() needs sample configurations on the GPU (a CUDA tensor)")
+        plan = self._plan(b.device_index)
+        outputs = (1 if values else 0) | (2 if with_jacobian else 0) | (4 if validity else 0)
+        mode = _lib.MODE_CLOSEST if self.only_closest_feature else _lib.MODE_ALL
+        choice = (C.c_int32 * 3)()
+        sdf = getattr(self, "sdf", None)
+        with b.device_ctx():
+            _lib.check(_lib.lib().skb_plan_tune(plan.handle, sdf.native(b.device_index) if sdf is not None else None, b.dtype_code,
+                                                b.q_ptr, b.n, float(getattr(self, "distance_margin", 0.0)), mode, outputs, b.stream, choice))
+        return None if choice[0] < 0 else (int(choice[0]), int(choice[1]), int(choice[2]))
+
+    def tuned(self, dtype=np.float32, with_jacobian: bool = True, values: bool = True, validity: bool = False, device_index=None):
+        """The stored launch choice for (mode, dtype, outputs), or None (``skb_plan_get_tuned``)."""
+        import ctypes as C
+
+        dev = current_device_index() if device_index is None else device_index
+        plan = self._plan(dev)
+        outputs = (1 if values else 0) | (2 if with_jacobian else 0) | (4 if validity else 0)
+        mode = _lib.MODE_CLOSEST if self.only_closest_feature else _lib.MODE_ALL
+        choice = (C.c_int32 * 3)()
+        sdf = getattr(self, "sdf", None)
+        from ._array import device_guard
+        with device_guard(dev):
+            _lib.check(_lib.lib().skb_plan_get_tuned(plan.handle, sdf.native(dev) if sdf is not None else None,
+                                                     _lib.F32 if np.dtype(dtype) == np.float32 else _lib.F64, mode, outputs, choice))
+        return None if choice[0] < 0 else (int(choice[0]), int(choice[1]), int(choice[2]))
 
     def _reflect_skrobot_model(self, robot_model) -> None:
         assert robot_model, "robot_model must not be None"
@@ -553,6 +614,8 @@ class PairWiseSelfCollFreeConst(AbstractIneqConst):
         return b.out(vals), (b.out(jac) if with_jacobian else self.dummy_jacobian())
 
     _min_values = CollFreeConst._min_values
+    tune = CollFreeConst.tune
+    tuned = CollFreeConst.tuned
 
     def is_valid_batch(self, qs):
         if not self.reflect_robot_flag:

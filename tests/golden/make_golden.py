@@ -70,10 +70,10 @@ def cfg1():
     qs = sample_q(kin, 32, rng).astype(np.float32).astype(np.float64)
     qs[0] = np.float32([0.564, 0.35, -0.74, -0.7, -0.7, -0.17, -0.63])
     sdf = oracle.Sdf(box_scene().primitives())
-    v, j, kink = oracle.collfree(tree, qs, feat, jl, sdf, kin.get_radius_list(), margin=0.05, with_kink=True)
+    v, j, kink, curv = oracle.collfree(tree, qs, feat, jl, sdf, kin.get_radius_list(), margin=0.05, with_kink=True, with_curv=True)
     vc, jc = oracle.collfree(tree, qs, feat, jl, sdf, kin.get_radius_list(), margin=0.05, only_closest=True)
     pts, pj = oracle.solve_fk(tree, qs[:8], feat, jl, base)
-    return {"qs": qs, "values": v, "jac": j, "kink": kink, "closest_values": vc, "closest_jac": jc, "points": pts, "points_jac": pj}
+    return {"qs": qs, "values": v, "jac": j, "kink": kink, "curv": curv, "closest_values": vc, "closest_jac": jc, "points": pts, "points_jac": pj}
 
 
 def cfg2():
@@ -111,8 +111,8 @@ def cfg3():
     grid = grid_scene()
     rng = np.random.default_rng(102)
     qs = sample_q(kin, 16, rng).astype(np.float32).astype(np.float64)
-    v, j, kink = oracle.collfree(tree, qs, feat, jl, oracle.Sdf(grid.primitives()), kin.get_radius_list(), with_kink=True)
-    return {"qs": qs, "values": v, "jac": j, "kink": kink}
+    v, j, kink, curv = oracle.collfree(tree, qs, feat, jl, oracle.Sdf(grid.primitives()), kin.get_radius_list(), with_kink=True, with_curv=True)
+    return {"qs": qs, "values": v, "jac": j, "kink": kink, "curv": curv}
 
 
 def cfg5():

@@ -81,3 +81,67 @@ def random_urdf(rng, n_links: int, path) -> str:
     lines.append('</robot>')
     path.write_text("\n".join(lines))
     return str(path)
+
+
+# ------------------------------------------------------------------ parity tolerances (BASELINE.json north_star)
+# fp32 within 1e-5, fp64 within 1e-10, error measure |got - ref| / max(1, |ref|).  Two conditioning terms are added where
+# the REFERENCE FUNCTION itself amplifies input rounding -- they are properties of the function, not of an implementation:
+#   * SDF gradients: forward kinematics in fp32 places a sphere centre with an error of up to FK_POS_ERR (measured: 7e-7 m at
+#     2.5 m from the origin, profiles/parity_r2.json); the analytic gradient field moves by curv * error, where `curv` is the
+#     oracle's Lipschitz bound of the gradient at that point (1/r at distance r from a box edge, cylinder rim / axis, sphere
+#     centre; the mixed second derivatives of a voxel cell).  In smooth regions (curv << 1/m) the term vanishes.
+#   * RPY rows: roll-pitch-yaw angles and their rate map are singular at pitch = +-pi/2; an fp32 rotation matrix (entries good
+#     to RPY_ROT_ERR) yields angles good to err / cos(pitch) and Jacobian rows good to err / cos(pitch)^2.
+# Rows closer than KINK_BAND to a gradient DISCONTINUITY (where fp32 and fp64 may legitimately take different sides) are
+# excluded from the Jacobian comparison and counted.
+TOL = {np.float32: 1e-5, np.float64: 1e-10}
+KINK_BAND = {np.float32: 2e-5, np.float64: 1e-9}
+FK_POS_ERR = {np.float32: 1e-6, np.float64: 2e-15}      # metres (x lever arm of the Jacobian column, <= 2.5 m)
+RPY_ROT_ERR = {np.float32: 4e-7, np.float64: 1e-15}
+
+
+def _dt(dtype):
+    return np.dtype(dtype).type
+
+
+def scaled_err(got, ref):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    return np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
+
+
+def max_err(got, ref) -> float:
+    e = scaled_err(got, ref)
+    return float(e.max()) if e.size else 0.0
+
+
+def collfree_jac_excess(jac, ref_jac, kink, curv, dtype, fd_eps=0.0):
+    """max over the compared entries of error / tolerance for CollFreeConst Jacobians (N, M, D) against the oracle's, with
+    the per-row tolerance TOL + (FK_POS_ERR + fd_eps) * curv; rows within KINK_BAND of a discontinuity are excluded.
+    ``fd_eps``: when the oracle differentiates by forward differences like the reference (eps = 1e-7), ITS truncation
+    error eps / 2 * |second derivative| <= eps * curv belongs to the tolerance as well.
+    -> (excess (<= 1 passes), fraction of rows excluded)."""
+    dtype = _dt(dtype)
+    e = scaled_err(jac, ref_jac)
+    tol = TOL[dtype] + (FK_POS_ERR[dtype] + fd_eps) * np.minimum(curv, 1e12)
+    ok = kink > KINK_BAND[dtype]
+    ratio = (e / tol[..., None])[ok]
+    return (float(ratio.max()) if ratio.size else 0.0), float(1.0 - ok.mean())
+
+
+def pose_excess(vals, jac, ref_pts, ref_jac, rot_type, dtype):
+    """error / tolerance of pose rows: ``vals`` (N, F, T) or (N, F*T) features and ``jac`` (N, F, T, D) against the
+    oracle's, TOL for positions, quaternions and IGNORE features; for RPY rows TOL + RPY_ROT_ERR / cos(pitch) (angles) and
+    TOL + RPY_ROT_ERR / cos(pitch)^2 (their Jacobian rows).  -> (value excess, Jacobian excess)."""
+    dtype = _dt(dtype)
+    ref_pts = np.asarray(ref_pts, dtype=np.float64)
+    n, f, t = ref_pts.shape
+    ev = scaled_err(np.asarray(vals).reshape(n, f, t), ref_pts)
+    ej = scaled_err(np.asarray(jac).reshape(n, f, t, -1), ref_jac)
+    tv = np.full((n, f, t), TOL[dtype])
+    tj = np.full((n, f, t), TOL[dtype])
+    if t == 6:      # [x y z roll pitch yaw]: skmp/kinematics.py:153-162
+        cp = np.maximum(np.abs(np.cos(ref_pts[:, :, 4])), 1e-12)[:, :, None]
+        tv[:, :, 3:] += RPY_ROT_ERR[dtype] / cp
+        tj[:, :, 3:] += RPY_ROT_ERR[dtype] / cp ** 2
+    return float((ev / tv).max()), float((ej / tj[..., None]).max())

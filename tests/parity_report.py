@@ -28,11 +28,11 @@ for p in (ROOT, ROOT / "scikit-motionplan_b200", ROOT / "tests"):
     if str(p) not in sys.path:
         sys.path.insert(0, str(p))
 
-from helpers import ROT, oracle_args, sample_q  # noqa: E402
+from helpers import FK_POS_ERR, KINK_BAND, ROT, RPY_ROT_ERR, TOL, collfree_jac_excess, oracle_args, pose_excess, sample_q  # noqa: E402
 from oracle import oracle  # noqa: E402
 
-KINK_BAND = {"float32": 2e-5, "float64": 1e-9}      # metres, analytic mode
 KINK_BAND_FD = 4e-7                                 # FD mode: the forward step (1e-7) must not straddle a kink either
+SMOOTH_CURV = 1.0                                   # 1/m: rows whose gradient-conditioning term is below 2e-6 ("smooth")
 
 
 def _err(got, ref):
@@ -61,13 +61,22 @@ def collfree_entry(const, colkin, sdf, qs, dtype, margin=0.0):
     v, j = _gpu(const, qs, dtype)
     tree, feat, jl, base = oracle_args(colkin)
     osdf = oracle.Sdf(sdf.primitives())
+    dt = np.dtype(dtype).type
     out = {}
     for mode, name in ((oracle.GRAD_ANALYTIC, "analytic"), (oracle.GRAD_FD, "fd")):
-        rv, rj, kink = oracle.collfree(tree, qs, feat, jl, osdf, colkin.get_radius_list(), margin=margin, base_type=base,
-                                       grad_mode=mode, with_kink=True)
-        band = max(KINK_BAND[np.dtype(dtype).name], KINK_BAND_FD if mode == oracle.GRAD_FD else 0.0)
+        rv, rj, kink, curv = oracle.collfree(tree, qs, feat, jl, osdf, colkin.get_radius_list(), margin=margin, base_type=base,
+                                             grad_mode=mode, with_kink=True, with_curv=True)
+        band = max(KINK_BAND[dt], KINK_BAND_FD if mode == oracle.GRAD_FD else 0.0)
         ok = kink > band
+        smooth = ok & (curv <= SMOOTH_CURV)
+        # FD mode: the reference's own truncation error (eps / 2 x second derivative) is part of what is compared; fp64 rows
+        # also carry the FD's round-off 2^-52 |sdf| / eps ~ 5e-9
+        excess, _ = collfree_jac_excess(j, rj, np.where(ok, kink, 0.0), curv, dt, fd_eps=1e-7 if mode == oracle.GRAD_FD else 0.0)
+        if mode == oracle.GRAD_FD and dt == np.float64:
+            excess = float(np.max((_err(j, rj) / (1e-8 + (2e-15 + 1e-7) * np.minimum(curv, 1e12))[..., None])[ok])) if ok.any() else 0.0
         out[name] = {"values": _stats(_err(v, rv)), "jacobians": _stats(_err(j[ok], rj[ok])),
+                     "jacobians_smooth_rows": _stats(_err(j[smooth], rj[smooth])), "smooth_row_frac": float(smooth.mean()),
+                     "jacobian_err_over_tol_max": excess,
                      "kink_band_m": band, "kink_excluded_frac": float(1.0 - ok.mean())}
     out["validity_mismatch_outside_1e-6_band"] = int((((v > 0) != (rv > 0)) & (np.abs(rv) > 1e-6)).sum())
     return out
@@ -96,8 +105,17 @@ def pose_entry(const, qs, dtype):
     tree, feat, jl, base = oracle_args(kin)
     rp, rj = oracle.solve_fk(tree, qs, feat, jl, base, ROT[kin.rot_type])
     n = len(qs)
-    rv = rp.reshape(n, -1) - np.hstack(const.desired_poses)
-    return {"values": _stats(_err(v, rv)), "jacobians": _stats(_err(j, rj.reshape(n, rv.shape[1], -1)))}
+    target = np.hstack(const.desired_poses)
+    rv = rp.reshape(n, -1) - target
+    ev, ej = pose_excess(v + target, j, rp, rj, kin.rot_type, np.dtype(dtype).type)
+    out = {"values": _stats(_err(v, rv)), "jacobians": _stats(_err(j, rj.reshape(n, rv.shape[1], -1))),
+           "value_err_over_tol_max": ev, "jacobian_err_over_tol_max": ej}
+    if rp.shape[2] == 6:       # RPY: the rate map is singular at pitch = +-pi/2; report the well-conditioned part separately
+        good = (np.abs(np.cos(rp[:, :, 4])) > 0.3).all(axis=1)
+        out["jacobians_cos_pitch_gt_0.3"] = _stats(_err(j[good], rj.reshape(n, rv.shape[1], -1)[good]))
+        out["cos_pitch_gt_0.3_frac"] = float(good.mean())
+        out["min_cos_pitch"] = float(np.abs(np.cos(rp[:, :, 4])).min())
+    return out
 
 
 def measure(n_scale: float = 1.0, dtypes=(np.float32, np.float64)):
@@ -114,6 +132,11 @@ def measure(n_scale: float = 1.0, dtypes=(np.float32, np.float64)):
         return max(32, int(n * n_scale))
 
     report = {"error_measure": "|got - ref| / max(1, |ref|), maximum over all entries",
+              "tolerance_model": {"values": "TOL", "collfree_jacobian_row": "TOL + FK_POS_ERR * curv (curv = the oracle's Lipschitz bound of the SDF gradient at the sphere centre, 1/m)",
+                                  "rpy_rows": "angles TOL + RPY_ROT_ERR / cos(pitch), their Jacobian rows TOL + RPY_ROT_ERR / cos(pitch)^2",
+                                  "TOL": {k.__name__: v for k, v in TOL.items()}, "FK_POS_ERR_m": {k.__name__: v for k, v in FK_POS_ERR.items()},
+                                  "RPY_ROT_ERR": {k.__name__: v for k, v in RPY_ROT_ERR.items()},
+                                  "err_over_tol_max": "<= 1 passes; tests/helpers.py"},
               "reference_gradient": "fd = forward difference eps 1e-7 in fp64 (skmp/constraint.py:320-331,362-369), analytic = exact",
               "north_star_tolerance": {"float32": 1e-5, "float64": 1e-10}, "configs": {}}
     pr2 = PR2(); pr2.reset_manip_pose()
@@ -190,6 +213,9 @@ if __name__ == "__main__":
         for dt, e in entry.items():
             if "analytic" in e:
                 print(f"{cfg:75s} {dt}: val {e['analytic']['values']['max']:.2e}  jac(analytic) {e['analytic']['jacobians']['max']:.2e} "
-                      f"jac(fd) {e['fd']['jacobians']['max']:.2e}  kink-excluded {e['analytic']['kink_excluded_frac']:.4f}/{e['fd']['kink_excluded_frac']:.4f}")
+                      f"[smooth rows {e['analytic']['jacobians_smooth_rows']['max']:.2e}, err/tol {e['analytic']['jacobian_err_over_tol_max']:.2f}] "
+                      f"jac(fd) {e['fd']['jacobians']['max']:.2e} [smooth {e['fd']['jacobians_smooth_rows']['max']:.2e}, err/tol {e['fd']['jacobian_err_over_tol_max']:.2f}]  "
+                      f"kink-excluded {e['analytic']['kink_excluded_frac']:.4f}/{e['fd']['kink_excluded_frac']:.4f}")
             else:
-                print(f"{cfg:75s} {dt}: val {e['values']['max']:.2e}  jac {e['jacobians']['max']:.2e}")
+                extra = f" [err/tol val {e['value_err_over_tol_max']:.2f} jac {e['jacobian_err_over_tol_max']:.2f}]" if "jacobian_err_over_tol_max" in e else ""
+                print(f"{cfg:75s} {dt}: val {e['values']['max']:.2e}  jac {e['jacobians']['max']:.2e}{extra}")

@@ -129,3 +129,84 @@ def test_edge_validity_cuda_inputs_return_cuda_bools():
     b = is_valid_motion_step_batch(step_box, torch.as_tensor(q1s, device="cuda"), torch.as_tensor(q2s, device="cuda"), const)
     assert isinstance(a, np.ndarray) and b.is_cuda and b.dtype == torch.bool
     assert np.array_equal(a, b.cpu().numpy())
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_collfree_csc_blocks_are_the_transposed_jacobians(dtype):
+    """``skb_collfree_csc`` / ``CollFreeConst.evaluate_csc``: the transposed (N, D, S) blocks written by the kernel equal the
+    (N, S, D) Jacobians of ``evaluate`` bit for bit -- box, union and voxel grid SDFs, D = 7 (odd), D = 14, ragged batch
+    sizes; D = 37 (JAXON) goes through the transpose fallback."""
+    import torch
+
+    import bench
+    from skmp_b200.constraint import CollFreeConst
+    from skmp_b200.robot.jaxon import JaxonConfig
+    from skmp_b200.robot.pr2 import PR2Config
+    from skmp_b200.robot_model import Jaxon
+    from skmp_b200.sdf import Box, Cylinder, UnionSDF
+
+    pr2, conf, colkin, box, const = _scene()
+    pr2_d, colkin_d, grid = bench.make_problem()
+    union = UnionSDF([box, Cylinder(0.15, 0.8, pos=[0.4, -0.6, 1.0])])
+    jaxon = Jaxon(); jaxon.reset_manip_pose()
+    jkin = JaxonConfig().get_collision_kin()
+    cases = [(const, colkin), (CollFreeConst(colkin, union, pr2, distance_margin=0.02), colkin),
+             (CollFreeConst(colkin_d, grid, pr2_d), colkin_d), (CollFreeConst(colkin_d, union, pr2_d), colkin_d),
+             (CollFreeConst(jkin, UnionSDF([Box([4.0, 4.0, 0.2], pos=[0.0, 0.0, -0.1])]), jaxon), jkin)]
+    rng = np.random.default_rng(70)
+    for c, kin in cases:
+        for n in (1, 31, 1003):
+            q = torch.as_tensor(sample_q(kin, n, rng).astype(dtype), device="cuda")
+            v, j = c.evaluate(q, True)
+            vc, d = c.evaluate_csc(q)
+            assert d.shape == (n, kin.dim_cspace, kin.n_feature) and d.is_contiguous()
+            assert torch.equal(vc, v) and torch.equal(d, j.transpose(1, 2))
+    # numpy in -> numpy out (host path: transpose of the host result)
+    qn = sample_q(colkin, 17, rng).astype(dtype)
+    vn, dn = const.evaluate_csc(qn)
+    v, j = const.evaluate(qn, True)
+    assert isinstance(dn, np.ndarray) and np.array_equal(dn, np.swapaxes(np.asarray(j), 1, 2)) and np.array_equal(vn, v)
+
+
+def test_trajectory_batch_stack_csc_equals_reference_dense_assembly():
+    """``TrajectoryBatchStack.evaluate_batch_csc``: for every trajectory of the batch, (data, indices, indptr) is the CSC
+    form of the dense matrix the reference assembles waypoint by waypoint (trajectory_constraint.py:128-195, restated in
+    tests/test_batched_host.py::ref_trajectory_evaluate) -- homogeneous collision table (the zero-copy path), and a mixed
+    table in non-monotone insertion order (pose goal, collision on some waypoints, a configuration point)."""
+    import torch
+    from scipy.sparse import csc_matrix
+
+    from skmp_b200.batched import TrajectoryBatchStack, TrajectoryConstraintStack
+    from skmp_b200.constraint import ConfigPointConst, PoseConstraint
+    from skmp_b200.tinyfk import RotationType
+    from test_batched_host import ref_trajectory_evaluate
+
+    pr2, conf, colkin, box, ineq = _scene()
+    eq = PoseConstraint([np.array([0.7, -0.6, 1.0, 0.0, 0.0, 0.0])], conf.get_endeffector_kin(RotationType.RPY), pr2)
+    cp = ConfigPointConst(np.linspace(-0.3, 0.3, 7))
+    n_dof, n_wp, B = 7, 6, 5
+    rng = np.random.default_rng(71)
+    trajs = sample_q(colkin, B * n_wp, rng).reshape(B, n_wp * n_dof)
+    tables = [{i: ineq for i in range(n_wp)}, {n_wp - 1: eq, 0: cp, 2: ineq, 4: ineq, 1: eq}]
+    for table in tables:
+        stack = TrajectoryBatchStack(n_dof, n_wp, table)
+        values, data = stack.evaluate_batch_csc(torch.as_tensor(trajs, device="cuda"))
+        assert values.shape == (B, stack.shape[0]) and data.shape == (B, len(stack.indices))
+        vh, dh = stack.evaluate_batch_csc(trajs)                                 # numpy in -> numpy out
+        assert np.array_equal(vh, values.cpu().numpy()) and np.array_equal(dh, data.cpu().numpy())
+        for b in range(B):
+            rv, rJ, dense = ref_trajectory_evaluate(n_dof, n_wp, table, trajs[b])
+            J = csc_matrix((dh[b], stack.indices, stack.indptr), shape=stack.shape)
+            assert J.shape == dense.shape
+            assert np.abs(vh[b] - rv).max() < 1e-12 and np.abs(J.toarray() - dense).max() < 1e-12
+            assert np.array_equal(stack.csc_matrix(data[b]).toarray(), J.toarray())
+        # the single-trajectory front end (the reference's call shape) rides on the same path
+        v1, J1 = TrajectoryConstraintStack(n_dof, n_wp, table).evaluate(trajs[0])
+        rv, rJ, dense = ref_trajectory_evaluate(n_dof, n_wp, table, trajs[0])
+        assert np.abs(v1 - rv).max() < 1e-12 and np.abs(J1.toarray() - dense).max() < 1e-12
+        assert np.array_equal(J1.indices, rJ.indices) or J1.nnz >= rJ.nnz       # structural zeros are stored, like determine_sparse_pattern's fill
+    # fp32 batch: same layout, values within fp32 of the fp64 run
+    stack = TrajectoryBatchStack(n_dof, n_wp, tables[0])
+    v32, d32 = stack.evaluate_batch_csc(torch.as_tensor(trajs.astype(np.float32), device="cuda"))
+    v64, d64 = stack.evaluate_batch_csc(torch.as_tensor(trajs.astype(np.float32).astype(np.float64), device="cuda"))
+    assert v32.dtype == torch.float32 and float((v32.double() - v64).abs().max()) < 1e-5

@@ -13,13 +13,10 @@ import copy
 import numpy as np
 import pytest
 
-from helpers import ROT, oracle_args, sample_q
+from helpers import ROT, RPY_ROT_ERR, TOL, collfree_jac_excess, oracle_args, pose_excess, sample_q, scaled_err
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
-
-TOL = {np.float32: 1e-5, np.float64: 1e-10}
-KINK_BAND = {np.float32: 2e-5, np.float64: 1e-9}
 
 
 def _torch():
@@ -85,12 +82,13 @@ def test_attached_obstacle_points_jaxon(dtype):
         const = CollFreeConst(k, env, jaxon, only_closest_feature=closest)
         v, j = const.evaluate(dev(qs, dtype), True)
         tree, feat, jl, base = oracle_args(k)
-        rv, rjac, kink = oracle.collfree(tree, qs, feat, jl, oracle.Sdf(env.primitives()), k.get_radius_list(), base_type=base,
-                                         only_closest=closest, with_kink=True)
+        rv, rjac, kink, curv = oracle.collfree(tree, qs, feat, jl, oracle.Sdf(env.primitives()), k.get_radius_list(), base_type=base,
+                                               only_closest=closest, with_kink=True, with_curv=True)
         assert err(v.cpu().numpy(), rv) < TOL[dtype]
-        ok = kink > KINK_BAND[dtype]
-        assert ok.mean() > 0.99
-        assert err(j.cpu().numpy()[ok], rjac[ok]) < 2 * TOL[dtype]   # D = 37 chain: twice the value tolerance (measured 1.1e-5 in fp32)
+        # the held box's surface points graze the table's edges: within a millimetre of an edge the gradient turns by
+        # 1 / distance per metre, which the per-row tolerance accounts for (helpers.collfree_jac_excess)
+        excess, excluded = collfree_jac_excess(j.cpu().numpy(), rjac, kink, curv, dtype)
+        assert excess <= 1.0 and excluded < 0.01
     # radius = margin shifts every value by exactly the margin
     v0, _ = CollFreeConst(kin, env, jaxon).evaluate(dev(qs, np.float64), False)
     v1, _ = CollFreeConst(kin_m, env, jaxon).evaluate(dev(qs, np.float64), False)
@@ -135,11 +133,18 @@ def test_relative_pose_constraint(rot):
         v, j = const.evaluate(dev(qs, dtype), True)
         tree, feat, jl, base = oracle_args(const.efkin)
         xs, jacs = oracle.solve_fk(tree, qs, feat, jl, base, ROT[RotationType[rot]])
-        tol = TOL[dtype] * (3 if dtype == np.float32 else 1)       # atan2 / asin of fp32 rotation entries, as test_map_pose_features
-        assert err(v.cpu().numpy(), xs[:, 1, :] - xs[:, 2, :]) < tol
-        assert err(j.cpu().numpy(), jacs[:, 1] - jacs[:, 2]) < 3 * tol
+        # the rotational rows are differences of two RPY angle sets / their rate maps: tolerance of the worse-conditioned one
+        # (helpers.pose_excess: TOL + RPY_ROT_ERR / cos(pitch)^k), twice for the difference
+        cp = np.minimum(np.abs(np.cos(xs[:, 1, 4])), np.abs(np.cos(xs[:, 2, 4]))) if xs.shape[2] == 6 else np.ones(len(qs))
+        tv = np.full(xs.shape[2], TOL[dtype])[None, :].repeat(len(qs), 0)
+        tj = tv.copy()
+        if xs.shape[2] == 6:
+            tv[:, 3:] += 2 * RPY_ROT_ERR[dtype] / cp[:, None]
+            tj[:, 3:] += 2 * RPY_ROT_ERR[dtype] / cp[:, None] ** 2
+        assert (scaled_err(v.cpu().numpy(), xs[:, 1, :] - xs[:, 2, :]) / tv).max() <= 1.0
+        assert (scaled_err(j.cpu().numpy(), jacs[:, 1] - jacs[:, 2]) / tj[:, :, None]).max() <= 1.0
         v2, j2 = const.evaluate(qs.astype(dtype), False)            # host path, no Jacobian
-        assert err(v2, xs[:, 1, :] - xs[:, 2, :]) < tol and np.isnan(np.asarray(j2)).all()
+        assert (scaled_err(v2, xs[:, 1, :] - xs[:, 2, :]) / tv).max() <= 1.0 and np.isnan(np.asarray(j2)).all()
 
 
 @pytest.mark.parametrize("rot", ["RPY", "IGNORE"])
@@ -171,7 +176,7 @@ def test_fixed_zaxis_constraint(rot):
         ref_v = np.concatenate([(tmp[:, 1] - tmp[:, 0])[:, :, 2], (tmp[:, 2] - tmp[:, 0])[:, :, 2]], axis=1).reshape(n, -1)
         tj = jacs.reshape(n, 3, nf, -1, 14)
         ref_j = np.concatenate([(tj[:, 1] - tj[:, 0])[:, :, 2, :], (tj[:, 2] - tj[:, 0])[:, :, 2, :]], axis=1).reshape(n, -1, 14)
-        assert err(v.cpu().numpy(), ref_v) < TOL[dtype] and err(j.cpu().numpy(), ref_j) < 2 * TOL[dtype]
+        assert err(v.cpu().numpy(), ref_v) < TOL[dtype] and err(j.cpu().numpy(), ref_j) < TOL[dtype]      # z rows only: no RPY term
         # the unit offsets make the values the (3,1) / (3,2) entries of the end-effector rotation: |value| <= 1
         assert float(v.abs().max()) <= 1.0 + 1e-5
 
@@ -250,12 +255,13 @@ def test_fallback_kernels(monkeypatch, env, dtype):
         for closest in (False, True):
             const = CollFreeConst(colkin, sdf, pr2, only_closest_feature=closest)
             v, j = const.evaluate(dev(qs, dtype), True)
-            rv, rj, kink = oracle.collfree(tree, qs, feat, jl, osdf, colkin.get_radius_list(), only_closest=closest, with_kink=True)
+            rv, rj, kink, curv = oracle.collfree(tree, qs, feat, jl, osdf, colkin.get_radius_list(), only_closest=closest,
+                                                 with_kink=True, with_curv=True)
             assert err(v.cpu().numpy(), rv) < TOL[dtype]
-            ok = kink > KINK_BAND[dtype]
-            assert err(j.cpu().numpy()[ok], rj[ok]) < 2 * TOL[dtype]
-            v2, j2 = const.evaluate(dev(qs, dtype), False)
-            assert torch.equal(v2, v)
+            excess, excluded = collfree_jac_excess(j.cpu().numpy(), rj, kink, curv, dtype)
+            assert excess <= 1.0 and excluded < 0.02
+            v2, j2 = const.evaluate(dev(qs, dtype), False)        # another kernel instantiation: same values to rounding
+            assert err(v2.cpu().numpy(), v.cpu().numpy()) < TOL[dtype] * 0.1 and np.isnan(np.asarray(j2)).all()
         const = CollFreeConst(colkin, sdf, pr2)
         valid = const.is_valid_batch(dev(qs, dtype)).cpu().numpy()
         rv, _ = oracle.collfree(tree, qs, feat, jl, osdf, colkin.get_radius_list(), with_jacobian=False)
@@ -272,9 +278,9 @@ def test_fallback_kernels(monkeypatch, env, dtype):
         rv = sq - pw.check_sphere_pair_sqdists
         if closest:
             idx, n = rv.argmin(axis=1), np.arange(len(rv))
-            assert err(v.cpu().numpy()[:, 0], rv[n, idx]) < TOL[dtype] and err(j.cpu().numpy()[:, 0], gr[n, idx]) < 2 * TOL[dtype]
+            assert err(v.cpu().numpy()[:, 0], rv[n, idx]) < TOL[dtype] and err(j.cpu().numpy()[:, 0], gr[n, idx]) < TOL[dtype]
         else:
-            assert err(v.cpu().numpy(), rv) < TOL[dtype] and err(j.cpu().numpy(), gr) < 2 * TOL[dtype]
+            assert err(v.cpu().numpy(), rv) < TOL[dtype] and err(j.cpu().numpy(), gr) < TOL[dtype]
     # pose rows (the tree kernel's RPY / XYZW epilogue under SKB_KERNEL=tree)
     for rt in (RotationType.RPY, RotationType.XYZW):
         efkin = PR2Config(control_arm="dual").get_endeffector_kin(rt)
@@ -283,8 +289,8 @@ def test_fallback_kernels(monkeypatch, env, dtype):
         pts, jac = efkin.map(dev(q3, dtype))
         t3, f3, jl3, b3 = oracle_args(efkin)
         rp, rjac = oracle.solve_fk(t3, q3, f3, jl3, b3, ROT[rt])
-        tol = TOL[dtype] * (3 if dtype == np.float32 else 1)
-        assert err(pts.cpu().numpy(), rp) < tol and err(jac.cpu().numpy(), rjac) < 3 * tol
+        ev, ej = pose_excess(pts.cpu().numpy(), jac.cpu().numpy(), rp, rjac, rt, dtype)
+        assert ev <= 1.0 and ej <= 1.0
 
 
 # ------------------------------------------------------------------ reference-held scene facts on the CUDA path

@@ -8,8 +8,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 GOLDEN = Path(__file__).resolve().parent / "golden"
-TOL = {np.float32: 1e-5, np.float64: 1e-10}
-KINK_BAND = {np.float32: 2e-5, np.float64: 1e-9}
+from helpers import KINK_BAND, TOL, collfree_jac_excess  # noqa: E402
 
 
 def relerr(a, b):
@@ -34,12 +33,13 @@ def test_cfg1_golden(dtype):
     tol = TOL[dtype]
     v, j = CollFreeConst(kin, box_scene().sdf, pr2, distance_margin=0.05).evaluate(dev(g["qs"], dtype), True)
     ok = g["kink"] > KINK_BAND[dtype]
-    assert relerr(v.cpu(), g["values"]) < tol and relerr(j.cpu().numpy()[ok], g["jac"][ok]) < 4 * tol
+    assert relerr(v.cpu(), g["values"]) < tol and collfree_jac_excess(j.cpu().numpy(), g["jac"], g["kink"], g["curv"], dtype)[0] <= 1.0
     vc, jc = CollFreeConst(kin, box_scene().sdf, pr2, only_closest_feature=True, distance_margin=0.05).evaluate(dev(g["qs"], dtype), True)
     assert relerr(vc.cpu(), g["closest_values"]) < tol
     idx = g["values"].argmin(axis=1)
     okc = ok[np.arange(len(idx)), idx] & (np.diff(np.sort(g["values"], axis=1)[:, :2], axis=1)[:, 0] > 1e-4)
-    assert relerr(jc.cpu().numpy()[okc], g["closest_jac"][okc]) < 4 * tol
+    n = np.arange(len(idx))
+    assert collfree_jac_excess(jc.cpu().numpy()[okc], g["closest_jac"][okc], g["kink"][n, idx][okc, None], g["curv"][n, idx][okc, None], dtype)[0] <= 1.0
     pts, pj = kin.map(dev(g["qs"][:8], dtype))
     assert relerr(pts.cpu(), g["points"]) < tol and relerr(pj.cpu(), g["points_jac"]) < tol
 
@@ -57,7 +57,7 @@ def test_cfg2_golden(dtype):
     const = PairWiseSelfCollFreeConst(kin, fetch, id_pairs=ids)
     assert np.allclose(const.check_sphere_pair_sqdists, g["thresholds"], atol=1e-15)
     v, j = const.evaluate(dev(g["qs"], dtype), True)
-    assert relerr(v.cpu(), g["values"]) < TOL[dtype] and relerr(j.cpu(), g["jac"]) < 2 * TOL[dtype]
+    assert relerr(v.cpu(), g["values"]) < TOL[dtype] and relerr(j.cpu(), g["jac"]) < TOL[dtype]
     # the constructor's own q = 0 filter yields the same pair list (itertools.combinations order)
     auto = PairWiseSelfCollFreeConst(kin, fetch)
     assert auto.check_sphere_id_pairs == ids
@@ -72,11 +72,8 @@ def test_cfg3_golden(dtype):
     g = np.load(GOLDEN / "cfg3_pr2_dual_grid.npz")
     const = CollFreeConst(PR2Config(control_arm="dual").get_collision_kin(), grid_scene(), _pr2())
     v, j = const.evaluate(dev(g["qs"], dtype), True)
-    vtol = TOL[dtype] * (4 if dtype == np.float32 else 1)
-    assert relerr(v.cpu(), g["values"]) < vtol
-    ok = g["kink"] > KINK_BAND[dtype]
-    jtol = 2e-4 if dtype == np.float32 else 4 * TOL[dtype]     # differences of fp32 corner values over 5 cm voxels
-    assert relerr(j.cpu().numpy()[ok], g["jac"][ok]) < jtol
+    assert relerr(v.cpu(), g["values"]) < TOL[dtype]
+    assert collfree_jac_excess(j.cpu().numpy(), g["jac"], g["kink"], g["curv"], dtype)[0] <= 1.0
     valid = const.is_valid_batch(dev(g["qs"], dtype)).cpu().numpy()
     decisive = np.abs(g["values"]).min(axis=1) > 1e-6
     assert (valid == (g["values"] > 0).all(axis=1))[decisive].all()
@@ -93,5 +90,4 @@ def test_cfg5_pose_golden(dtype):
     kin = JaxonConfig().get_endeffector_kin(rot_type=RotationType.XYZW)
     kin.reflect_skrobot_model(jaxon)
     pts, jac = kin.map(dev(g["qs"], dtype))
-    tol = TOL[dtype] * (3 if dtype == np.float32 else 1)
-    assert relerr(pts.cpu(), g["points"]) < tol and relerr(jac.cpu(), g["jac"]) < 3 * tol
+    assert relerr(pts.cpu(), g["points"]) < TOL[dtype] and relerr(jac.cpu(), g["jac"]) < TOL[dtype]      # XYZW rows: no singularity

@@ -9,13 +9,11 @@ KINK_BAND are excluded from the *Jacobian* comparison only.
 import numpy as np
 import pytest
 
-from helpers import BASE, ROT, oracle_args, sample_q
+from helpers import BASE, KINK_BAND, ROT, TOL, collfree_jac_excess, oracle_args, pose_excess, sample_q
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
 
-KINK_BAND = {np.float32: 2e-5, np.float64: 1e-9}   # metres
-TOL = {np.float32: 1e-5, np.float64: 1e-10}
 VALID_BAND = 1e-6
 
 
@@ -75,13 +73,12 @@ def test_collfree_box_config1(pr2, dtype, device, margin):
         const = CollFreeConst(colkin, box.sdf, pr2, only_closest_feature=closest, distance_margin=margin)
         v, j = run_collfree(const, qs, dtype, device)
         tree, feat, jl, base = oracle_args(colkin)
-        rv, rj, kink = oracle.collfree(tree, qs, feat, jl, oracle.Sdf(box.primitives()), colkin.get_radius_list(),
-                                       margin=margin, only_closest=closest, with_kink=True)
+        rv, rj, kink, curv = oracle.collfree(tree, qs, feat, jl, oracle.Sdf(box.primitives()), colkin.get_radius_list(),
+                                             margin=margin, only_closest=closest, with_kink=True, with_curv=True)
         assert v.shape == rv.shape and j.shape == rj.shape
         assert close(v, rv, TOL[dtype]) < TOL[dtype]
-        ok = kink > KINK_BAND[dtype]
-        assert ok.mean() > 0.999
-        assert close(j[ok], rj[ok], TOL[dtype]) < TOL[dtype] * 4
+        excess, excluded = collfree_jac_excess(j, rj, kink, curv, dtype)
+        assert excluded < 0.001 and excess <= 1.0
         band = np.abs(rv) > VALID_BAND
         assert ((v > 0) == (rv > 0))[band].all()
 
@@ -152,9 +149,8 @@ def test_map_pose_features(pr2, dtype, rot):
         pts, jac = kin.map(torch.as_tensor(qs.astype(dtype), device="cuda"))
         tree, feat, jl, base = oracle_args(kin)
         rp, rj = oracle.solve_fk(tree, qs, feat, jl, base, ROT[rt])
-        tol = TOL[dtype] * (3 if dtype == np.float32 else 1)   # atan2/asin of fp32 rotation entries
-        assert close(pts.cpu().numpy(), rp, tol) < tol
-        assert close(jac.cpu().numpy(), rj, tol) < tol * 3
+        ev, ej = pose_excess(pts.cpu().numpy(), jac.cpu().numpy(), rp, rj, rt, dtype)    # RPY rows: + err / cos(pitch)^k
+        assert ev <= 1.0 and ej <= 1.0
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -178,15 +174,13 @@ def test_collfree_union_and_grid(pr2, dtype):
     for sdf in (union, grid):
         const = CollFreeConst(colkin, sdf, pr2)
         v, j = run_collfree(const, qs, dtype, True)
-        rv, rj, kink = oracle.collfree(tree, qs, feat, jl, oracle.Sdf(sdf.primitives()), colkin.get_radius_list(), with_kink=True)
-        tol = TOL[dtype] * (4 if (sdf is grid and dtype == np.float32) else 1)
-        assert close(v, rv, tol) < tol
-        band = KINK_BAND[dtype]
-        ok = kink > band
-        assert ok.mean() > 0.99
-        # trilinear gradient = differences of fp32-interpolated corner values / 3 cm voxels
-        jtol = 2e-4 if (sdf is grid and dtype == np.float32) else tol * 4
-        assert close(j[ok], rj[ok], jtol) < jtol
+        rv, rj, kink, curv = oracle.collfree(tree, qs, feat, jl, oracle.Sdf(sdf.primitives()), colkin.get_radius_list(),
+                                             with_kink=True, with_curv=True)
+        assert close(v, rv, TOL[dtype]) < TOL[dtype]
+        # voxel grid: value and gradient are Horner evaluations of the cell polynomial (no cancellation), so the grid
+        # meets the same per-row tolerance as the analytic primitives
+        excess, excluded = collfree_jac_excess(j, rj, kink, curv, dtype)
+        assert excluded < 0.01 and excess <= 1.0
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -212,14 +206,14 @@ def test_pairwise_fetch_config2(dtype):
     sq, gr = oracle.inter_link_sqdists(tree, qs, np.array(const.check_sphere_id_pairs), jl, base)
     rv = sq - const.check_sphere_pair_sqdists
     assert close(v.cpu().numpy(), rv, TOL[dtype]) < TOL[dtype]
-    assert close(j.cpu().numpy(), gr, TOL[dtype]) < TOL[dtype] * 2
+    assert close(j.cpu().numpy(), gr, TOL[dtype]) < TOL[dtype]
     closest = conf.get_pairwise_selcol_consts(fetch, only_closest_feature=True)
     closest.check_sphere_id_pairs, closest.check_sphere_pair_sqdists = const.check_sphere_id_pairs, const.check_sphere_pair_sqdists
     vc, jc = closest.evaluate(qs.astype(dtype), True)
     idx = rv.argmin(axis=1)
     assert close(np.asarray(vc)[:, 0], rv.min(axis=1), TOL[dtype]) < TOL[dtype]
     decided = np.sort(rv, axis=1)[:, 1] - np.sort(rv, axis=1)[:, 0] > 1e-4
-    assert close(np.asarray(jc)[decided, 0], gr[np.arange(len(qs)), idx][decided], TOL[dtype]) < TOL[dtype] * 2
+    assert close(np.asarray(jc)[decided, 0], gr[np.arange(len(qs)), idx][decided], TOL[dtype]) < TOL[dtype]
 
 
 def test_min_all_equals_closest(pr2):
@@ -260,7 +254,7 @@ def test_pairwise_jaxon_floating_base_wide_masks():
     rv = sq - full.check_sphere_pair_sqdists
     tol = TOL[np.float32]
     assert close(v.cpu().numpy(), rv, tol) < tol
-    assert close(j.cpu().numpy(), gr, tol) < tol * 4
+    assert close(j.cpu().numpy(), gr, tol) < tol
     vc, jc = closest.evaluate(q_dev, True)
     assert torch.equal(vc[:, 0], v.min(dim=1).values)                      # same arithmetic in both modes
     idx = v.argmin(dim=1)
@@ -361,18 +355,18 @@ def test_com_stability_jaxon(dtype, with_forces):
     com, jc = const.com(q_dev, True)
     rcom, rjc = oracle.com_fk(tree, qs, feats, np.array(w), jl, oracle.BASE_FLOATING)
     assert com.shape == (1000, 3) and jc.shape == (1000, 3, 37)
-    assert close(com.cpu().numpy(), rcom, tol) < tol and close(jc.cpu().numpy(), rjc, tol) < tol * 2
+    assert close(com.cpu().numpy(), rcom, tol) < tol and close(jc.cpu().numpy(), rjc, tol) < tol
     xs, jt = s.solve_com_fk(qs.astype(dtype), const.tinyfk_joint_ids, const.action_link_ids, const.action_forces,
                             BaseType.FLOATING, True)                  # numpy in -> numpy out, the reference's call shape
     assert isinstance(xs, np.ndarray) and xs.shape == (1000, 3) and jt.shape == (3000, 37)
-    assert close(xs, rcom, tol) < tol and close(jt.reshape(1000, 3, 37), rjc, tol) < tol * 2
+    assert close(xs, rcom, tol) < tol and close(jt.reshape(1000, 3, 37), rjc, tol) < tol
     v, j = const.evaluate(q_dev, True)
     rv, rj, kink = oracle.com_stability(tree, qs, feats, np.array(w), jl, oracle.Sdf(box.primitives()), oracle.BASE_FLOATING,
                                         with_kink=True)
     assert v.shape == (1000, 1) and j.shape == (1000, 1, 37)
     assert close(v.cpu().numpy(), rv, tol) < tol
     ok = kink > (2e-5 if dtype == np.float32 else 1e-9)
-    assert ok.mean() > 0.95 and close(j.cpu().numpy()[ok], rj[ok], tol) < tol * 4
+    assert ok.mean() > 0.95 and close(j.cpu().numpy()[ok], rj[ok], tol) < tol
     v2, j2 = const.evaluate(q_dev, False)
     assert torch.equal(v2, v) and np.isnan(np.asarray(j2)).all()
     assert const.is_valid(qs[0].astype(dtype)) == bool(rv[0, 0] > 0)

@@ -5,7 +5,7 @@ sub-sample against the CPU oracle."""
 import numpy as np
 import pytest
 
-from helpers import ROT, oracle_args, sample_q
+from helpers import ROT, TOL, collfree_jac_excess, oracle_args, pose_excess, sample_q
 from oracle import oracle
 
 pytestmark = pytest.mark.gpu
@@ -73,44 +73,96 @@ def test_cfg3_pr2_dual_grid_full_shard():
     pick = np.arange(0, n, n // 300)[:300]
     q64 = qs[pick].cpu().numpy().astype(np.float64)
     tree, feat, jl, base = oracle_args(colkin)
-    rv, rj, kink = oracle.collfree(tree, q64, feat, jl, oracle.Sdf(grid.primitives()), colkin.get_radius_list(), with_kink=True)
+    rv, rj, kink, curv = oracle.collfree(tree, q64, feat, jl, oracle.Sdf(grid.primitives()), colkin.get_radius_list(),
+                                         with_kink=True, with_curv=True)
     ev = np.abs(vals[pick].cpu().numpy() - rv) / np.maximum(1, np.abs(rv))
-    assert ev.max() < 4e-5
-    ok = kink > 2e-5
-    ej = (np.abs(jac[pick].cpu().numpy() - rj) / np.maximum(1, np.abs(rj)))[ok]
-    assert ej.max() < 2e-4
+    assert ev.max() < TOL[np.float32]
+    assert collfree_jac_excess(jac[pick].cpu().numpy(), rj, kink, curv, np.float32)[0] <= 1.0
 
 
-def test_launch_autotuner_is_result_neutral():
-    """The first launch of >= 65 536 configurations of a plan times every (program, G, warps per CTA) candidate on a slice
-    of the caller's own buffers (`launch_s2_inst`, csrc/skb_sphere2.cu).  Whatever the candidates left behind, and the
-    tuned launch itself, must equal -- bit for bit -- what a separate plan computes with the model's configuration on
-    pieces too small to be tuned, in every mode."""
+def test_launch_tuning_is_explicit_and_result_neutral(tmp_path):
+    """The launch configuration of the step kernel (configurations per warp tile, warps per CTA, fused / unfused steps):
+      * user calls below 2^20 configurations never time candidates (no latency cliff for an SQP / RRT caller);
+      * ``tune()`` (skb_plan_tune) measures explicitly on scratch outputs and stores the choice under a CONTENT key, so a
+        structurally equal constraint built later -- another solver, another sticky state -- finds it (``tuned()``);
+      * whatever is chosen or forced, every mode returns the same bits;
+      * SKB_TUNE_CACHE persists the choice across processes."""
+    import ctypes as C
+    import os
+    import subprocess
+    import sys
+
     import bench
+    from skmp_b200 import _lib
     from skmp_b200.constraint import CollFreeConst
+    from skmp_b200.robot.pr2 import PR2Config
+    from skmp_b200.robot_model import PR2
+    from skmp_b200.sdf import Box
 
     torch = _torch()
-    pr2, colkin, grid = bench.make_problem()
+    pr2 = PR2(); pr2.reset_manip_pose()
+    # a structure no other test of this process evaluates at >= 2^20 configurations: dual arm + torso against a box
+    def make(closest=False):
+        kin = PR2Config(control_arm="dual", use_torso=True).get_collision_kin()
+        return CollFreeConst(kin, Box([0.7, 0.5, 1.2], pos=[0.85, -0.2, 0.9]).sdf, pr2, only_closest_feature=closest)
+
+    const, closest = make(), make(True)
     n = 70_001
-    qs = _device_samples(colkin, n, 11)
-    tuned = CollFreeConst(colkin, grid, pr2)
-    vals, jac = tuned.evaluate(qs, True)            # tunes on the first 70 001 rows
-    vals_b, jac_b = tuned.evaluate(qs, True)        # reuses the choice
-    assert torch.equal(vals, vals_b) and torch.equal(jac, jac_b)
-    valid = tuned.is_valid_batch(qs)
-    closest = CollFreeConst(colkin, grid, pr2, only_closest_feature=True)
+    qs = _device_samples(const.colkin, n, 11)
+    assert const.tuned() is None
+    launches0 = _lib.lib().skb_launch_count()
+    vals, jac = const.evaluate(qs, True)
+    assert _lib.lib().skb_launch_count() - launches0 == 1          # one launch: nothing was timed inside the call
+    assert const.tuned() is None
+    valid = const.is_valid_batch(qs)
     vc, jc = closest.evaluate(qs, True)
-    # a second solver: its plans carry no tuned entry, and 9 973 rows per call stay below the tuning threshold
-    pr2_f, colkin_f, grid_f = bench.make_problem()
-    fresh = CollFreeConst(colkin_f, grid_f, pr2_f)
-    fresh_closest = CollFreeConst(colkin_f, grid_f, pr2_f, only_closest_feature=True)
-    for a in range(0, n, 9_973):
-        b = min(n, a + 9_973)
-        v, j = fresh.evaluate(qs[a:b], True)
-        assert torch.equal(v, vals[a:b]) and torch.equal(j, jac[a:b])
-        assert torch.equal(fresh.is_valid_batch(qs[a:b]), valid[a:b])
-        v, j = fresh_closest.evaluate(qs[a:b], True)
-        assert torch.equal(v, vc[a:b]) and torch.equal(j, jc[a:b])
+    choice = const.tune(qs)                                         # values + Jacobians, all spheres
+    assert choice is not None and choice[1] in (1, 2, 4, 8) and 1 <= choice[2] <= 8
+    assert const.tuned() == choice
+    assert const.tuned(validity=True, values=False, with_jacobian=False) is None     # another kernel instantiation: its own key
+    assert const.tune(qs, with_jacobian=False, values=False, validity=True) is not None
+    assert closest.tune(qs) is not None
+    # a structurally equal constraint from a NEW solver in another sticky state finds the choice
+    pr2_b = PR2(); pr2_b.reset_manip_pose(); pr2_b.head_tilt_joint.joint_angle(0.1)
+    other = make()
+    other.reflect_skrobot_model(pr2_b)
+    assert other.tuned() == choice
+    # results are the same bits before and after tuning ...
+    v2, j2 = const.evaluate(qs, True)
+    assert torch.equal(v2, vals) and torch.equal(j2, jac)
+    assert torch.equal(const.is_valid_batch(qs), valid)
+    v3, j3 = closest.evaluate(qs, True)
+    assert torch.equal(v3, vc) and torch.equal(j3, jc)
+    # ... and under forced configurations (skb_plan_set_tuning: configurations per tile, warps per CTA)
+    for g, w in ((8, 8), (4, 6), (2, 4), (1, 2), (4, 7)):
+        forced = make()
+        plan = forced._plan()
+        _lib.check(_lib.lib().skb_plan_set_tuning(plan.handle, g, 0, w, 0))
+        vf, jf = forced.evaluate(qs[:30_011], True)
+        assert torch.equal(vf, vals[:30_011]) and torch.equal(jf, jac[:30_011]), (g, w)
+        assert torch.equal(forced.is_valid_batch(qs[:30_011]), valid[:30_011]), (g, w)
+    # persistence: a child process tunes into SKB_TUNE_CACHE, a second child finds the choice without measuring
+    cache = tmp_path / "tune.cache"
+    script = (
+        "import sys, json, numpy as np, torch\n"
+        "sys.path[:0] = [%r, %r, %r]\n"
+        "from skmp_b200.constraint import CollFreeConst\n"
+        "from skmp_b200.robot.pr2 import PR2Config\n"
+        "from skmp_b200.robot_model import PR2\n"
+        "from skmp_b200.sdf import Box\n"
+        "pr2 = PR2(); pr2.reset_manip_pose()\n"
+        "c = CollFreeConst(PR2Config().get_collision_kin(), Box([0.7, 0.5, 1.2], pos=[0.85, -0.2, 0.9]).sdf, pr2)\n"
+        "before = c.tuned()\n"
+        "if sys.argv[1] == 'tune':\n"
+        "    c.tune(torch.rand((70000, 7), device='cuda') - 0.5)\n"
+        "print(json.dumps({'before': before, 'after': c.tuned()}))\n"
+    ) % (str(bench.ROOT), str(bench.ROOT / "scikit-motionplan_b200"), str(bench.ROOT / "tests"))
+    env = dict(os.environ, SKB_TUNE_CACHE=str(cache))
+    import json
+    first = json.loads(subprocess.run([sys.executable, "-c", script, "tune"], env=env, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1])
+    assert first["before"] is None and first["after"] is not None and cache.exists() and len(cache.read_text().split()) == 6
+    second = json.loads(subprocess.run([sys.executable, "-c", script, "look"], env=env, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1])
+    assert second["before"] == first["after"]
 
 
 def test_cfg2_fetch_pairwise_1m():
@@ -142,7 +194,7 @@ def test_cfg2_fetch_pairwise_1m():
     sq, gr = oracle.inter_link_sqdists(tree, qs[sl][pick].cpu().numpy().astype(np.float64), np.array(full.check_sphere_id_pairs), jl, base)
     rv = sq - full.check_sphere_pair_sqdists
     assert (np.abs(va[pick].cpu().numpy() - rv) / np.maximum(1, np.abs(rv))).max() < 1e-5
-    assert (np.abs(ja[pick].cpu().numpy() - gr) / np.maximum(1, np.abs(gr))).max() < 2e-5
+    assert (np.abs(ja[pick].cpu().numpy() - gr) / np.maximum(1, np.abs(gr))).max() < 1e-5
 
 
 def test_cfg4_sqp_trajectory_batch():
@@ -216,14 +268,12 @@ def test_cfg5_jaxon_validity_10m():
     pick = np.arange(0, 200_000, 1000)
     q64 = qs[sl][pick].cpu().numpy().astype(np.float64)
     tree, feat, jl, base = oracle_args(colkin)
-    rv, rj, kink = oracle.collfree(tree, q64, feat, jl, oracle.Sdf(UnionSDF([ground, table]).primitives()), colkin.get_radius_list(),
-                                   base_type=base, with_kink=True)
-    assert (np.abs(vals[pick].cpu().numpy() - rv) / np.maximum(1, np.abs(rv))).max() < 2e-5
-    ok = kink > 2e-5
-    assert (np.abs(jac[pick].cpu().numpy() - rj) / np.maximum(1, np.abs(rj)))[ok].max() < 5e-5
+    rv, rj, kink, curv = oracle.collfree(tree, q64, feat, jl, oracle.Sdf(UnionSDF([ground, table]).primitives()), colkin.get_radius_list(),
+                                         base_type=base, with_kink=True, with_curv=True)
+    assert (np.abs(vals[pick].cpu().numpy() - rv) / np.maximum(1, np.abs(rv))).max() < TOL[np.float32]
+    assert collfree_jac_excess(jac[pick].cpu().numpy(), rj, kink, curv, np.float32)[0] <= 1.0
     tree, feat, jl, base = oracle_args(efkin)
     rp, rpj = oracle.solve_fk(tree, q64[:50], feat, jl, base, ROT[RotationType.XYZW])
-    got = pv[pick[:50]].cpu().numpy() if False else None
     pv2, pj2 = pose.evaluate(qs[sl][pick[:50]], True)
-    assert (np.abs(pv2.cpu().numpy() - rp.reshape(50, -1))).max() < 5e-5
-    assert (np.abs(pj2.cpu().numpy() - rpj.reshape(50, 28, 37))).max() < 2e-4
+    ev, ej = pose_excess(pv2.cpu().numpy(), pj2.cpu().numpy(), rp, rpj, RotationType.XYZW, np.float32)
+    assert ev <= 1.0 and ej <= 1.0
