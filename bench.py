@@ -416,7 +416,7 @@ class Cfg4(Workload):
         self.out = None
 
     def tune(self):
-        self.ineq.tune(self.trajs.reshape(-1, 7))
+        self.ineq.tune(self.trajs.reshape(-1, 7), csc=True)
 
     def step(self):
         self.out = None

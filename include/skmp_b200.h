@@ -123,7 +123,7 @@ SKB_API int skb_plan_set_tuning(skb_plan *p, int32_t chunk_features, int32_t n_b
                                 int32_t ctas_per_sm);
 /* Measures the launch configuration (configurations per warp tile, warps per CTA, fused / unfused row steps) of the step
  * kernel that serves skb_collfree (pass the SDF) or skb_pairwise (s = NULL) for this plan, dtype, mode and output set
- * (bit 0 values, bit 1 jacobians, bit 2 validity bytes), on up to 262 144 of the caller's sample configurations and on
+ * (bit 0 values, bit 1 jacobians, bit 2 validity bytes, bit 3 the transposed layout of skb_collfree_csc), on up to 262 144 of the caller's sample configurations and on
  * scratch outputs of its own; synchronous, 30-130 ms.  The choice is stored under a content key of the plan's structure:
  * every later launch of a structurally equal plan (same robot / features / joints, any sticky state) reuses it, and
  * SKB_TUNE_CACHE=<file> persists it across processes.  Without it, calls of fewer than 2^20 configurations use an

@@ -245,6 +245,8 @@ int skb_plan_tune(const skb_plan *p, const skb_sdf *s, int32_t dtype, const void
     if (!p || !q_dev || N <= 0) return set_error("plan_tune: bad arguments");
     if (dtype != SKB_F32 && dtype != SKB_F64) return set_error("plan_tune: bad dtype");
     if ((outputs & 7) == 0) return set_error("plan_tune: no output selected (1 values, 2 jacobians, 4 validity bytes)");
+    if ((outputs & 8) && (!s || !(outputs & 2) || (outputs & 4) || mode != SKB_MODE_ALL))
+        return set_error("plan_tune: the transposed (CSC) layout is the all-spheres CollFreeConst Jacobian (outputs 8 | 2 [| 1], an SDF)");
     if (!s && !p->pairs_set) return set_error("plan_tune: pass an SDF (CollFreeConst) or set the plan's pairs (PairWiseSelfCollFreeConst)");
     if (check_plan_device(p, "plan_tune") != 0) return -1;
     const int64_t n = std::min<int64_t>(N, 262144);
@@ -259,8 +261,9 @@ int skb_plan_tune(const skb_plan *p, const skb_sdf *s, int32_t dtype, const void
     int made = 0;
     if (rc == 0) {
         s2_tune_begin(0);
-        rc = s ? skb_collfree(p, s, dtype, q_dev, n, margin, mode, dv, dj, dvalid, stream)
-               : skb_pairwise(p, dtype, q_dev, n, mode, dv, dj, dvalid, stream);
+        rc = (outputs & 8) ? skb_collfree_csc(p, s, dtype, q_dev, n, margin, dv, dj, stream)
+             : s           ? skb_collfree(p, s, dtype, q_dev, n, margin, mode, dv, dj, dvalid, stream)
+                           : skb_pairwise(p, dtype, q_dev, n, mode, dv, dj, dvalid, stream);
         made = s2_tune_end(out_choice);
         if (cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)) != cudaSuccess && rc == 0) rc = set_error("plan_tune: the timed launches failed");
     }

@@ -305,6 +305,63 @@ __device__ __forceinline__ double lds_1(uint32_t a, double) { double v; asm vola
 __device__ __forceinline__ void sts_1(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_1(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 
+// PLANER / FLOATING base: the chain's last node (NODE_BASE_*, alone in level 1; skb_host.cpp::level_layout) in closed form from
+// the base columns col .. col + 2 / col + 5 -- row `row` of  [Rz(yaw) Ry(pitch) Rx(roll) A | x y z]  with the node constant A
+// (the z-normalising rotation of the chain's last axis), and the twists (omega, v = o x omega) of all base columns -- instead
+// of three / six almost empty passes of the level loop.  Everything below sees the frame the joint-by-joint walk would
+// produce.  Not inlined on purpose: robots with a fixed base never run it and must not pay registers for it (the fp32 voxel-
+// grid kernel sits exactly at its 64-register budget).
+template <typename T, bool WITH_JAC, bool PAIR>
+__device__ __noinline__ void fk_base_node(const int type, const int col, const int node3, const int row, const bool on,
+                                          const uint32_t a_q, const uint32_t a_sc, const uint32_t a_nodeF, const uint32_t a_nodeFr,
+                                          const uint32_t a_fr, const uint32_t a_tw) {
+    using V4 = Vec4<T>;
+    constexpr uint32_t ES = sizeof(T), VS = 4 * sizeof(T);
+    T bx = lds_1(a_q + col * ES, T()), by = lds_1(a_q + (col + 1) * ES, T()), bz = T(0);
+    T sy_, cy_, sp_ = T(0), cp_ = T(1), sr_ = T(0), cr_ = T(1);
+    if (type == NODE_BASE_FLOATING) {
+        bz = lds_1(a_q + (col + 2) * ES, T());
+        lds_sc(a_sc + 2 * (col + 3) * ES, sr_, cr_);
+        lds_sc(a_sc + 2 * (col + 4) * ES, sp_, cp_);
+        lds_sc(a_sc + 2 * (col + 5) * ES, sy_, cy_);
+    } else lds_sc(a_sc + 2 * (col + 2) * ES, sy_, cy_);
+    const T u = row == 0 ? cy_ : sy_, w = row == 0 ? -sy_ : cy_;           // rows 0 / 1 of Rz(yaw) are (u, w, 0)
+    V4 P;
+    if (row < 2) { P.x = u * cp_; P.y = u * sp_ * sr_ + w * cr_; P.z = u * sp_ * cr_ - w * sr_; P.w = row == 0 ? bx : by; }
+    else { P.x = -sp_; P.y = cp_ * sr_; P.z = cp_ * cr_; P.w = bz; }
+    const uint32_t ac = a_nodeF + node3 * VS;
+    const V4 c0 = lds_v4(ac, T()), c1 = lds_v4(ac + VS, T()), c2 = lds_v4(ac + 2 * VS, T());
+    V4 y;
+    y.x = P.x * c0.x + P.y * c1.x + P.z * c2.x;
+    y.y = P.x * c0.y + P.y * c1.y + P.z * c2.y;
+    y.z = P.x * c0.z + P.y * c1.z + P.z * c2.z;
+    y.w = P.w + P.x * c0.w + P.y * c1.w + P.z * c2.w;
+    if (!on) return;
+    sts_v4(a_fr + node3 * VS, y);
+    sts_v4(a_fr, lds_v4(a_nodeFr, T()));                                  // the world node (level 0): its constant row
+    if (!WITH_JAC) return;
+    auto put = [&](const int c, const T w_r, const T v_r) {
+        const uint32_t at = a_tw + (PAIR ? ((c >> 1) * 12 + (c & 1)) : c * 8) * ES;
+        sts_1(at, w_r);
+        sts_1(at + (PAIR ? 6 : 4) * ES, v_r);
+    };
+    const T e0 = row == 0 ? T(1) : T(0), e1 = row == 1 ? T(1) : T(0), e2 = row == 2 ? T(1) : T(0);
+    put(col, T(0), e0);                                               // x: translation along e_x
+    put(col + 1, T(0), e1);                                           // y
+    const T vyaw = row == 0 ? by : (row == 1 ? -bx : T(0));           // (x, y, z) x e_z = (y, -x, 0)
+    if (type == NODE_BASE_FLOATING) {
+        put(col + 2, T(0), e2);                                       // z
+        put(col + 5, e2, vyaw);                                       // yaw about e_z
+        // pitch about Rz(yaw) e_y = (-sy, cy, 0):  o x omega = (-z cy, -z sy, x cy + y sy)
+        put(col + 4, row == 0 ? -sy_ : (row == 1 ? cy_ : T(0)),
+            row == 0 ? -bz * cy_ : (row == 1 ? -bz * sy_ : bx * cy_ + by * sy_));
+        // roll about Rz(yaw) Ry(pitch) e_x = (cy cp, sy cp, -sp)
+        const T wx = cy_ * cp_, wy = sy_ * cp_, wz = -sp_;
+        put(col + 3, row == 0 ? wx : (row == 1 ? wy : wz),
+            row == 0 ? by * wz - bz * wy : (row == 1 ? bz * wx - bx * wz : bx * wy - by * wx));
+    } else put(col + 2, e2, vyaw);                                    // theta about e_z
+}
+
 template <typename T, bool WITH_JAC, bool PAIR>
 __device__ __forceinline__ void fk_phase(const int lane, const int G, const int logG, const int slots3, const int g_live,
                                          const int D, const int n_levels, const int4 *lvrec, const int32_t *levelI,
@@ -326,7 +383,18 @@ __device__ __forceinline__ void fk_phase(const int lane, const int G, const int 
     if (sizeof(T) == 4)      // the fp64 instantiations are register-bound: let the compiler re-derive there
         asm volatile("" : "+r"(src1), "+r"(src2), "+r"(a_lv), "+r"(a_lev), "+r"(a_nodeF), "+r"(a_nodeFr), "+r"(a_q), "+r"(a_sc),
                      "+r"(a_fr), "+r"(a_tw));
-    for (int lv = 0; lv < n_levels; ++lv) {
+    // PLANER / FLOATING base: the chain's last node (NODE_BASE_*, alone in level 1) is evaluated in closed form by fk_base_node
+    int lv_first = 0;
+    if (n_levels > 1) {
+        const int2 l1 = lds_i2(a_lev + 8u);
+        const int4 rec = lds_i4(a_lv + 16u * l1.x);
+        if (rec.x >= NODE_BASE_PLANER) {
+            lv_first = 2;
+            fk_base_node<T, WITH_JAC, PAIR>(rec.x, rec.y, rec.w, row, act && slot == 0, a_q, a_sc, a_nodeF, a_nodeFr, a_fr, a_tw);
+            __syncwarp();
+        }
+    }
+    for (int lv = lv_first; lv < n_levels; ++lv) {
         const int2 lrec = lds_i2(a_lev + 8u * lv);                          // {first entry of the level, count}
         const int lbeg = lrec.x, lcnt = lrec.y;
         for (int k0 = 0; k0 < lcnt; k0 += slots3) {

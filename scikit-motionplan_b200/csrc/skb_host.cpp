@@ -544,6 +544,80 @@ const skb_pair_program *get_pair_program(skb_plan *p) {
 }
 
 
+
+// ------------------------------------------------------------------ level layout of the warp-cooperative kernels
+// Node records {type, column, parent}, the per-level node lists and the row-form pre-transforms [R_r0 R_r1 R_r2 t_r] shared by
+// the sphere / step / centre-of-mass / pose programs.  A node's level is its depth below the world node -- except for the
+// chain of a PLANER / FLOATING base (skmp/robot/utils.py:45-56: three / six joints in a row, one node per level, i.e. three
+// / six almost empty passes of the level walk): its LAST node becomes one node of type NODE_BASE_PLANER / NODE_BASE_FLOATING
+// at level 1 that fk_phase evaluates in closed form from the base columns (frame = [Rz(yaw) Ry(pitch) Rx(roll) A | xyz], and
+// the twists of all base columns), the others (NODE_BASE_SKIP) appear in no level.  Everything below the base sees the
+// same frame as before.
+struct LevelLayout {
+    int n_levels = 0;
+    std::vector<int> type, col, parent;          // per node, as the kernels see them
+    std::vector<std::vector<int>> lv;            // node lists per level
+    std::vector<int> skipped;                    // NODE_BASE_SKIP nodes (appended after the last level so the list has n_nodes entries)
+    std::vector<double> rows;                    // 12 per node
+};
+
+static LevelLayout level_layout(const skb_plan *p) {
+    LevelLayout L;
+    const int n_nodes = (int)p->nodes.size(), D = p->D;
+    L.type.resize(n_nodes); L.col.resize(n_nodes); L.parent.resize(n_nodes);
+    for (int k = 0; k < n_nodes; ++k) { L.type[k] = p->nodes[k].type; L.col[k] = p->nodes[k].col; L.parent[k] = p->nodes[k].parent; }
+    L.rows.resize((size_t)n_nodes * 12);
+    for (int k = 0; k < n_nodes; ++k) {
+        double R[9];
+        quat_to_matrix(p->nodes[k].pre.q, R);
+        for (int r = 0; r < 3; ++r) { double *o = &L.rows[(size_t)k * 12 + 4 * r]; o[0] = R[3 * r]; o[1] = R[3 * r + 1]; o[2] = R[3 * r + 2]; o[3] = p->nodes[k].pre.t[r]; }
+    }
+    const int nb = p->base_type == SKB_BASE_PLANER ? 3 : (p->base_type == SKB_BASE_FLOATING ? 6 : 0);
+    const char *keep = getenv("SKB_BASE_CHAIN");                          // SKB_BASE_CHAIN=1: walk the base joint by joint
+    if (nb > 0 && !(keep && atoi(keep) != 0)) {
+        const int c0 = D - nb, last_col = nb == 3 ? c0 + 2 : c0 + 3;      // theta / roll close the chain (compile_tree)
+        std::vector<int> chain;
+        int last = -1;
+        for (int k = 1; k < n_nodes; ++k) if (p->nodes[k].col >= c0) chain.push_back(k);
+        for (int k : chain) if (p->nodes[k].col == last_col) last = k;
+        // the chain must be exactly world -> ... -> last, one child each
+        bool ok = (int)chain.size() == nb && last >= 0;
+        for (int k : chain) if (k != last && p->nodes[k].children.size() != 1) ok = false;
+        if (ok) {
+            for (int k : chain) if (k != last) { L.type[k] = NODE_BASE_SKIP; L.skipped.push_back(k); }
+            L.type[last] = nb == 3 ? NODE_BASE_PLANER : NODE_BASE_FLOATING;
+            L.col[last] = c0;
+            L.parent[last] = 0;
+            // frame = [R_base A | t_base]: the node's constant is the z-normalising rotation A of its own axis alone
+            const double ax[3] = {nb == 3 ? 0.0 : 1.0, 0.0, nb == 3 ? 1.0 : 0.0};
+            double R[9];
+            quat_to_matrix(xf_z_to_axis(ax).q, R);
+            for (int r = 0; r < 3; ++r) { double *o = &L.rows[(size_t)last * 12 + 4 * r]; o[0] = R[3 * r]; o[1] = R[3 * r + 1]; o[2] = R[3 * r + 2]; o[3] = 0.0; }
+        }
+    }
+    std::vector<int> level(n_nodes, 0);
+    for (int k = 0; k < n_nodes; ++k) {
+        if (L.type[k] == NODE_BASE_SKIP) { level[k] = -1; continue; }
+        level[k] = L.parent[k] < 0 ? 0 : level[L.parent[k]] + 1;
+        L.n_levels = std::max(L.n_levels, level[k] + 1);
+    }
+    L.lv.assign(L.n_levels, {});
+    for (int k = 0; k < n_nodes; ++k) if (level[k] >= 0) L.lv[level[k]].push_back(k);
+    return L;
+}
+
+// appends the node / level / level-node tables to I in the layout every level program uses
+static void pack_levels(const LevelLayout &L, std::vector<int32_t> &I, int &node_i, int &level_i, int &levelnode_i) {
+    node_i = (int)I.size();
+    for (size_t k = 0; k < L.type.size(); ++k) { I.push_back(L.type[k]); I.push_back(L.col[k]); I.push_back(L.parent[k]); I.push_back(0); }
+    level_i = (int)I.size();
+    int cursor = 0;
+    for (auto &l : L.lv) { I.push_back(cursor); I.push_back((int)l.size()); cursor += (int)l.size(); }
+    levelnode_i = (int)I.size();
+    for (auto &l : L.lv) for (int k : l) I.push_back(k);
+    for (int k : L.skipped) I.push_back(k);
+}
+
 // ------------------------------------------------------------------ sphere program (skb_sphere.cu)
 static int odd_quads(int words) {   // round up to a multiple of 4 words whose quotient is odd (bank-conflict-free rows)
     int q = (words + 3) / 4;
@@ -557,14 +631,10 @@ static int build_sphere_program(skb_plan *p, skb_sphere_program *sp) {
     const int n_nodes = (int)p->nodes.size(), nf = p->F, D = p->D;
     if (p->rot_type != SKB_ROT_IGNORE || D > 64 || D < 1 || n_nodes > 255 || nf > 32 * 32) return 0;
     // levels: node 0 (world) is level 0, a movable node with di controlled ancestors is level di + 1
-    int n_levels = 0;
-    std::vector<int> level(n_nodes, 0);
-    for (int k = 0; k < n_nodes; ++k) {
-        level[k] = p->nodes[k].parent < 0 ? 0 : level[p->nodes[k].parent] + 1;
-        n_levels = std::max(n_levels, level[k] + 1);
-    }
-    std::vector<std::vector<int>> lv(n_levels);
-    for (int k = 0; k < n_nodes; ++k) lv[level[k]].push_back(k);
+    const LevelLayout LL = level_layout(p);
+    const int n_levels = LL.n_levels;
+    const std::vector<std::vector<int>> &lv = LL.lv;
+    (void)lv;
     int max_level_nodes = 0;
     for (auto &l : lv) max_level_nodes = std::max(max_level_nodes, (int)l.size());
     // ancestor column masks per node
@@ -582,15 +652,7 @@ static int build_sphere_program(skb_plan *p, skb_sphere_program *sp) {
     sp->frame_stride = odd_quads(n_nodes * 12);
     sp->tw_stride = odd_quads(D * 8);
     I[S_FRAME_STRIDE] = sp->frame_stride; I[S_TW_STRIDE] = sp->tw_stride;
-    I[S_NODE_I] = (int)I.size();
-    for (int k = 0; k < n_nodes; ++k) {
-        I.push_back(p->nodes[k].type); I.push_back(p->nodes[k].col); I.push_back(p->nodes[k].parent); I.push_back(0);
-    }
-    I[S_LEVEL_I] = (int)I.size();
-    int cursor = 0;
-    for (auto &l : lv) { I.push_back(cursor); I.push_back((int)l.size()); cursor += (int)l.size(); }
-    I[S_LEVELNODE_I] = (int)I.size();
-    for (auto &l : lv) for (int k : l) I.push_back(k);
+    { int a, b, c; pack_levels(LL, I, a, b, c); I[S_NODE_I] = a; I[S_LEVEL_I] = b; I[S_LEVELNODE_I] = c; }
     while (I.size() % 4) I.push_back(0);
     I[S_ROUND_I] = (int)I.size();
     for (int r = 0; r < n_rounds; ++r) {
@@ -612,11 +674,7 @@ static int build_sphere_program(skb_plan *p, skb_sphere_program *sp) {
     I[S_I_TOTAL] = (int)I.size();
     Fv.clear();
     I[S_NODE_F] = 0;
-    for (int k = 0; k < n_nodes; ++k) {
-        double R[9];
-        quat_to_matrix(p->nodes[k].pre.q, R);
-        for (int r = 0; r < 3; ++r) { Fv.push_back(R[3 * r]); Fv.push_back(R[3 * r + 1]); Fv.push_back(R[3 * r + 2]); Fv.push_back(p->nodes[k].pre.t[r]); }
-    }
+    Fv.insert(Fv.end(), LL.rows.begin(), LL.rows.end());
     I[S_TABA_F] = (int)Fv.size();
     for (int r = 0; r < n_rounds; ++r)
         for (int l = 0; l < 32; ++l) {
@@ -673,14 +731,10 @@ static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp, bool allo
     if (pairs && nf > 4096) return 0;
     const char *force = getenv("SKB_KERNEL");
     if (force && (std::string(force) == "tree" || std::string(force) == "sphere1")) return 0;
-    int n_levels = 0;
-    std::vector<int> level(n_nodes, 0);
-    for (int k = 0; k < n_nodes; ++k) {
-        level[k] = p->nodes[k].parent < 0 ? 0 : level[p->nodes[k].parent] + 1;
-        n_levels = std::max(n_levels, level[k] + 1);
-    }
-    std::vector<std::vector<int>> lv(n_levels);
-    for (int k = 0; k < n_nodes; ++k) lv[level[k]].push_back(k);
+    const LevelLayout LL = level_layout(p);
+    const int n_levels = LL.n_levels;
+    const std::vector<std::vector<int>> &lv = LL.lv;
+    (void)lv;
     std::vector<uint64_t> nmask(n_nodes, 0);
     for (int k = 1; k < n_nodes; ++k) {
         nmask[k] = nmask[p->nodes[k].parent];
@@ -731,13 +785,7 @@ static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp, bool allo
     I.assign(QHDR_WORDS, 0);
     I[Q_N_NODES] = n_nodes; I[Q_N_LEVELS] = n_levels; I[Q_N_STEPS] = n_steps; I[Q_D] = D; I[Q_ROWS] = rows;
     I[Q_N_CEN] = pairs ? nf : 0;
-    I[Q_NODE_I] = (int)I.size();
-    for (int k = 0; k < n_nodes; ++k) { I.push_back(p->nodes[k].type); I.push_back(p->nodes[k].col); I.push_back(p->nodes[k].parent); I.push_back(0); }
-    I[Q_LEVEL_I] = (int)I.size();
-    int cursor = 0;
-    for (auto &l : lv) { I.push_back(cursor); I.push_back((int)l.size()); cursor += (int)l.size(); }
-    I[Q_LEVELNODE_I] = (int)I.size();
-    for (auto &l : lv) for (int k : l) I.push_back(k);
+    { int a, b, c; pack_levels(LL, I, a, b, c); I[Q_NODE_I] = a; I[Q_LEVEL_I] = b; I[Q_LEVELNODE_I] = c; }
     while (I.size() % 4) I.push_back(0);
     I[Q_TABB_I] = (int)I.size();
     for (int s = 0; s < n_steps; ++s)
@@ -774,11 +822,7 @@ static int build_s2_program(skb_plan *p, int kind, skb_s2_program *sp, bool allo
     I[Q_I_TOTAL] = (int)I.size();
     Fv.clear();
     I[Q_NODE_F] = 0;
-    for (int k = 0; k < n_nodes; ++k) {
-        double R[9];
-        quat_to_matrix(p->nodes[k].pre.q, R);
-        for (int r = 0; r < 3; ++r) { Fv.push_back(R[3 * r]); Fv.push_back(R[3 * r + 1]); Fv.push_back(R[3 * r + 2]); Fv.push_back(p->nodes[k].pre.t[r]); }
-    }
+    Fv.insert(Fv.end(), LL.rows.begin(), LL.rows.end());
     I[Q_TABA_F] = (int)Fv.size();
     if (!pairs)
         for (int s = 0; s < n_steps; ++s)
@@ -916,25 +960,15 @@ static int build_com_program(skb_plan *p, skb_com_program *cp) {
     std::stable_sort(pts.begin(), pts.end(), [&](int a, int b) { return pos[p->feat_node[a]] < pos[p->feat_node[b]]; });
     std::vector<int> ppos(nf);
     for (int i = 0; i < nf; ++i) ppos[i] = pos[p->feat_node[pts[i]]];
-    int n_levels = 0;
-    std::vector<int> level(n_nodes, 0);
-    for (int k = 0; k < n_nodes; ++k) {
-        level[k] = p->nodes[k].parent < 0 ? 0 : level[p->nodes[k].parent] + 1;
-        n_levels = std::max(n_levels, level[k] + 1);
-    }
-    std::vector<std::vector<int>> lv(n_levels);
-    for (int k = 0; k < n_nodes; ++k) lv[level[k]].push_back(k);
+    const LevelLayout LL = level_layout(p);
+    const int n_levels = LL.n_levels;
+    const std::vector<std::vector<int>> &lv = LL.lv;
+    (void)lv;
     std::vector<int32_t> &I = cp->I;
     std::vector<double> &Fv = cp->F;
     I.assign(CHDR_WORDS, 0);
     I[C_N_NODES] = n_nodes; I[C_N_LEVELS] = n_levels; I[C_N_POINTS] = nf; I[C_D] = D;
-    I[C_NODE_I] = (int)I.size();
-    for (int k = 0; k < n_nodes; ++k) { I.push_back(p->nodes[k].type); I.push_back(p->nodes[k].col); I.push_back(p->nodes[k].parent); I.push_back(0); }
-    I[C_LEVEL_I] = (int)I.size();
-    int cursor = 0;
-    for (auto &l : lv) { I.push_back(cursor); I.push_back((int)l.size()); cursor += (int)l.size(); }
-    I[C_LEVELNODE_I] = (int)I.size();
-    for (auto &l : lv) for (int k : l) I.push_back(k);
+    { int a, b, c; pack_levels(LL, I, a, b, c); I[C_NODE_I] = a; I[C_LEVEL_I] = b; I[C_LEVELNODE_I] = c; }
     I[C_PTNODE_I] = (int)I.size();
     for (int i = 0; i < nf; ++i) I.push_back(p->feat_node[pts[i]]);
     while (I.size() % 2) I.push_back(0);
@@ -953,11 +987,7 @@ static int build_com_program(skb_plan *p, skb_com_program *cp) {
     I[C_I_TOTAL] = (int)I.size();
     Fv.clear();
     I[C_NODE_F] = 0;
-    for (int k = 0; k < n_nodes; ++k) {
-        double R[9];
-        quat_to_matrix(p->nodes[k].pre.q, R);
-        for (int r = 0; r < 3; ++r) { Fv.push_back(R[3 * r]); Fv.push_back(R[3 * r + 1]); Fv.push_back(R[3 * r + 2]); Fv.push_back(p->nodes[k].pre.t[r]); }
-    }
+    Fv.insert(Fv.end(), LL.rows.begin(), LL.rows.end());
     I[C_PT_F] = (int)Fv.size();
     for (int i = 0; i < nf; ++i) { for (int j = 0; j < 3; ++j) Fv.push_back(p->feat_off[pts[i]].t[j]); Fv.push_back(p->weights[pts[i]]); }
     I[C_F_TOTAL] = (int)Fv.size();
@@ -998,14 +1028,10 @@ static int build_pose_program(skb_plan *p, skb_pose_program *pp) {
     if (p->rot_type == SKB_ROT_IGNORE || D < 1 || D > 64 || n_nodes > 255 || nf > 256) return 0;
     const char *force = getenv("SKB_KERNEL");
     if (force && std::string(force) == "tree") return 0;
-    int n_levels = 0;
-    std::vector<int> level(n_nodes, 0);
-    for (int k = 0; k < n_nodes; ++k) {
-        level[k] = p->nodes[k].parent < 0 ? 0 : level[p->nodes[k].parent] + 1;
-        n_levels = std::max(n_levels, level[k] + 1);
-    }
-    std::vector<std::vector<int>> lv(n_levels);
-    for (int k = 0; k < n_nodes; ++k) lv[level[k]].push_back(k);
+    const LevelLayout LL = level_layout(p);
+    const int n_levels = LL.n_levels;
+    const std::vector<std::vector<int>> &lv = LL.lv;
+    (void)lv;
     std::vector<uint64_t> nmask(n_nodes, 0);
     for (int k = 1; k < n_nodes; ++k) {
         nmask[k] = nmask[p->nodes[k].parent];
@@ -1015,30 +1041,49 @@ static int build_pose_program(skb_plan *p, skb_pose_program *pp) {
     std::vector<double> &Fv = pp->F;
     I.assign(EHDR_WORDS, 0);
     I[E_N_NODES] = n_nodes; I[E_N_LEVELS] = n_levels; I[E_N_FEAT] = nf; I[E_D] = D;
-    I[E_NODE_I] = (int)I.size();
-    for (int k = 0; k < n_nodes; ++k) { I.push_back(p->nodes[k].type); I.push_back(p->nodes[k].col); I.push_back(p->nodes[k].parent); I.push_back(0); }
-    I[E_LEVEL_I] = (int)I.size();
-    int cursor = 0;
-    for (auto &l : lv) { I.push_back(cursor); I.push_back((int)l.size()); cursor += (int)l.size(); }
-    I[E_LEVELNODE_I] = (int)I.size();
-    for (auto &l : lv) for (int k : l) I.push_back(k);
+    { int a, b, c; pack_levels(LL, I, a, b, c); I[E_NODE_I] = a; I[E_LEVEL_I] = b; I[E_LEVELNODE_I] = c; }
     while (I.size() % 4) I.push_back(0);
     I[E_FEAT_I] = (int)I.size();
     for (int f = 0; f < nf; ++f) {
         const uint64_t am = nmask[p->feat_node[f]];
         I.push_back(p->feat_node[f]); I.push_back((int32_t)(uint32_t)(am & 0xffffffffu)); I.push_back((int32_t)(uint32_t)(am >> 32)); I.push_back(0);
     }
+    // XYZW: the quaternion of a feature is the PRODUCT of the factors  Q_pre_k * Qz(q_k / 2)  along its chain, root first, like
+    // the reference's chain of link transforms (its sign is the chain's, not that of a matrix conversion).  Constant factors
+    // (fixed offsets folded by the plan compiler, prismatic joints) are merged into the next factor here; the chain is padded
+    // with identities to a multiple of 4 so that four lanes multiply a quarter each.
+    std::vector<std::vector<std::pair<int, Xf>>> chains(nf);
+    size_t chain_len = 4;
+    for (int f = 0; f < nf; ++f) {
+        std::vector<int> path;
+        for (int k = p->feat_node[f]; k > 0; k = p->nodes[k].parent) path.push_back(k);
+        std::reverse(path.begin(), path.end());
+        Xf acc = xf_identity();
+        for (int k : path) {
+            Xf pre = xf_identity();
+            for (int j = 0; j < 4; ++j) pre.q[j] = p->nodes[k].pre.q[j];
+            acc = xf_mul(acc, pre);                              // rotations only: the translations stay zero
+            if (p->nodes[k].type == NODE_REVOLUTE) { chains[f].push_back({p->nodes[k].col, acc}); acc = xf_identity(); }
+        }
+        chains[f].push_back({-1, acc});                           // trailing constant (identity when the chain ends in a revolute joint)
+        chain_len = std::max(chain_len, (chains[f].size() + 3) / 4 * 4);
+    }
+    I[E_CHAIN_LEN] = (int)chain_len;
+    I[E_CHAIN_I] = (int)I.size();
+    for (int f = 0; f < nf; ++f)
+        for (size_t k = 0; k < chain_len; ++k) I.push_back(k < chains[f].size() ? chains[f][k].first : -1);
     I[E_I_TOTAL] = (int)I.size();
     Fv.clear();
     I[E_NODE_F] = 0;
-    for (int k = 0; k < n_nodes; ++k) {
-        double R[9];
-        quat_to_matrix(p->nodes[k].pre.q, R);
-        for (int r = 0; r < 3; ++r) { Fv.push_back(R[3 * r]); Fv.push_back(R[3 * r + 1]); Fv.push_back(R[3 * r + 2]); Fv.push_back(p->nodes[k].pre.t[r]); }
-    }
+    Fv.insert(Fv.end(), LL.rows.begin(), LL.rows.end());
     I[E_NODEQ_F] = (int)Fv.size();
     for (int k = 0; k < n_nodes; ++k) for (int j = 0; j < 4; ++j) Fv.push_back(p->nodes[k].pre.q[j]);
+    I[E_CHAINQ_F] = (int)Fv.size();
+    for (int f = 0; f < nf; ++f)
+        for (size_t k = 0; k < chain_len; ++k)
+            for (int j = 0; j < 4; ++j) Fv.push_back(k < chains[f].size() ? chains[f][k].second.q[j] : (j == 3 ? 1.0 : 0.0));
     I[E_FEAT_F] = (int)Fv.size();
+
     for (int f = 0; f < nf; ++f) {
         double R[9];
         quat_to_matrix(p->feat_off[f].q, R);

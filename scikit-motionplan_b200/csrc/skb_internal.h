@@ -38,7 +38,10 @@ enum ChunkI { C_FEAT_BEGIN = 0, C_COUNT, C_OUT0, C_ACTIVE, C_ZERO_BEGIN, C_ZERO_
 enum { FEAT_F_POINT = 4, FEAT_F_POSE = 20 };
 enum { SRC_IDENTITY = -1, SRC_CURRENT = -2 };   // >= 0: restore from slot
 enum { MAX_SLOTS = 8 };
-enum { NODE_NONE = 0, NODE_REVOLUTE = 1, NODE_PRISMATIC = 2 };
+enum { NODE_NONE = 0, NODE_REVOLUTE = 1, NODE_PRISMATIC = 2,
+       // level programs only (skb_host.cpp::level_layout): the chain of a PLANER / FLOATING base -- three / six single-node
+       // levels -- is ONE node evaluated in closed form; its other nodes appear in no level
+       NODE_BASE_PLANER = 3, NODE_BASE_FLOATING = 4, NODE_BASE_SKIP = 5 };
 
 // pairwise program (separate upload): all-node evaluation order + per-feature node binding
 // PI header (enum PHdr), node records reuse NodeI/NodeF (chunk fields unused),
@@ -224,6 +227,9 @@ enum EHdr {
     E_N_NODES = 0, E_N_LEVELS, E_N_FEAT, E_D,
     E_NODE_I, E_LEVEL_I, E_LEVELNODE_I, E_FEAT_I, E_I_TOTAL,
     E_NODE_F, E_NODEQ_F, E_FEAT_F, E_F_TOTAL,
+    E_CHAIN_I,     // XYZW: per feature, the quaternion factors of its chain root -> node: CHAIN_LEN columns (-1: constant factor)
+    E_CHAINQ_F,    //       and CHAIN_LEN constant quaternions; factor k = chainQ[k] * Qz(q[col_k] / 2), padded with identities
+    E_CHAIN_LEN,   //       factors per feature, a multiple of 4 (four lanes multiply a quarter of the chain each)
     EHDR_WORDS = 16
 };
 struct skb_pose_program {

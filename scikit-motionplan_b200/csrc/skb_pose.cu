@@ -6,8 +6,8 @@
 //
 // One warp owns a tile of G configurations.
 //   phase 1   frames + twists, three lanes per (configuration, node)                     -> fk_phase (skb_device.cuh)
-//   phase 1q  (XYZW) node quaternions by the same level walk, Q = Q_parent * Q_pre * Qz(theta / 2): the quaternion is
-//             the PRODUCT along the chain like the reference's, not a conversion of the rotation matrix (sign!)
+//   phase 1q  (XYZW) feature quaternions: the PRODUCT of the factors Q_pre * Qz(theta / 2) along the feature's chain like the
+//             reference's, not a conversion of the rotation matrix (sign!); four lanes per (configuration, feature)
 //   phase 1c  lane per (configuration, feature): position, rpy angles / quaternion -> values out, and the few scalars the
 //             rotational Jacobian rows need into a small shared record
 //   phase 2   lane per (configuration, column) of the tile, flattened: the lane keeps ITS joint twist (omega, v) in
@@ -77,7 +77,9 @@ __global__ void __launch_bounds__(256) pose_kernel(const PoseParams<T> prm) {
     __syncthreads();
     const int4 *featI = reinterpret_cast<const int4 *>(sI + sI[E_FEAT_I]);
     const V4 *nodeF = reinterpret_cast<const V4 *>(sF + sI[E_NODE_F]);
-    const V4 *nodeQ = reinterpret_cast<const V4 *>(sF + sI[E_NODEQ_F]);
+    const int32_t *chainI = sI + sI[E_CHAIN_I];
+    const V4 *chainQ = reinterpret_cast<const V4 *>(sF + sI[E_CHAINQ_F]);
+    const int chain_len = sI[E_CHAIN_LEN];
     const T *featF = sF + sI[E_FEAT_F];                 // 20 per feature: off(3) pad | R(9) pad(3) | quat(4)
 
     T *wbase = reinterpret_cast<T *>(smem + prm.off_warp) + (size_t)warp * prm.warp_elems;
@@ -109,38 +111,46 @@ __global__ void __launch_bounds__(256) pose_kernel(const PoseParams<T> prm) {
         fk_phase<T, true, false>(lane, G, logG, prm.slots3, g_live, D, n_levels, lvrec, levelI, nodeF, wq, wsc,
                                  wframes, fstride, wtw, tstride);
 
-        // ------------------------------------------------------------ phase 1q: node quaternions (XYZW)
+        // ------------------------------------------------------------ phase 1q: feature quaternions (XYZW)
+        // Four lanes per (configuration, feature): each multiplies a quarter of the chain's factors  Q_k = C_k * Qz(q_k / 2)
+        // (constants merged on the host), two shuffle rounds combine the partial products in chain order (the quaternion
+        // product is associative), lane 0 of the group appends the feature's own offset.
         if (ROT == SKB_ROT_XYZW) {
-            const int cfg = lane & (G - 1), slot = lane >> logG, slots = 32 >> logG;
-            const int ccfg = min(cfg, g_live - 1);
-            V4 *qd = reinterpret_cast<V4 *>(wquat + cfg * qstride);
-            for (int lv = 0; lv < n_levels; ++lv) {
-                const int lbeg = levelI[2 * lv], lcnt = levelI[2 * lv + 1];
-                for (int k0 = 0; k0 < lcnt; k0 += slots) {
-                    const int k = k0 + slot;
-                    if (k < lcnt) {
-                        const int node = levelNodes[lbeg + k];
-                        const int type = nodeI[4 * node], col = nodeI[4 * node + 1], par = nodeI[4 * node + 2];
-                        const V4 pre = nodeQ[node];
-                        T y[4] = {pre.x, pre.y, pre.z, pre.w};
-                        if (par >= 0) {
-                            const V4 pq = qd[par];
-                            const T a[4] = {pq.x, pq.y, pq.z, pq.w}, b[4] = {pre.x, pre.y, pre.z, pre.w};
-                            qmul<T>(a, b, y);
-                        }
-                        if (type == NODE_REVOLUTE) {
-                            const T sh = wsch[2 * (ccfg * D + col)], ch = wsch[2 * (ccfg * D + col) + 1];
-                            const T qz[4] = {T(0), T(0), sh, ch};
-                            T o[4];
-                            qmul<T>(y, qz, o);
-                            y[0] = o[0]; y[1] = o[1]; y[2] = o[2]; y[3] = o[3];
-                        }
-                        V4 out; out.x = y[0]; out.y = y[1]; out.z = y[2]; out.w = y[3];
-                        qd[node] = out;
-                    }
+            const int L4 = chain_len >> 2;
+            for (int i0 = 0; i0 < g_live * F * 4; i0 += 32) {
+                const int i = i0 + lane;
+                const bool act = i < g_live * F * 4;
+                const int part = i & 3, cf = act ? i >> 2 : 0, c = cf / F, f = cf - c * F;
+                T acc[4] = {T(0), T(0), T(0), T(1)};
+                const int32_t *cc = chainI + f * chain_len + part * L4;
+                const V4 *cq = chainQ + f * chain_len + part * L4;
+                for (int k = 0; k < L4; ++k) {
+                    const int col = cc[k];
+                    const V4 C4 = cq[k];
+                    T sh = T(0), ch = T(1);
+                    if (col >= 0) { sh = wsch[2 * (c * D + col)]; ch = wsch[2 * (c * D + col) + 1]; }
+                    // C * Qz(theta / 2) = (x c + y s, y c - x s, z c + w s, w c - z s)
+                    const T b[4] = {C4.x * ch + C4.y * sh, C4.y * ch - C4.x * sh, C4.z * ch + C4.w * sh, C4.w * ch - C4.z * sh};
+                    T o[4];
+                    qmul<T>(acc, b, o);
+                    acc[0] = o[0]; acc[1] = o[1]; acc[2] = o[2]; acc[3] = o[3];
                 }
-                __syncwarp();
+#pragma unroll
+                for (int step = 1; step <= 2; step <<= 1) {                  // (P0 P1)(P2 P3)
+                    T nb[4], o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) nb[j] = __shfl_down_sync(0xffffffffu, acc[j], step);
+                    qmul<T>(acc, nb, o);
+                    if ((part & (2 * step - 1)) == 0) { acc[0] = o[0]; acc[1] = o[1]; acc[2] = o[2]; acc[3] = o[3]; }
+                }
+                if (act && part == 0) {
+                    T qf[4];
+                    qmul<T>(acc, featF + f * 20 + 16, qf);
+                    V4 out; out.x = qf[0]; out.y = qf[1]; out.z = qf[2]; out.w = qf[3];
+                    reinterpret_cast<V4 *>(wquat + c * qstride)[f] = out;
+                }
             }
+            __syncwarp();
         }
 
         // ------------------------------------------------------------ phase 1c: feature poses -> values + Jacobian scalars
@@ -174,12 +184,9 @@ __global__ void __launch_bounds__(256) pose_kernel(const PoseParams<T> prm) {
                 Rl::sincos(yaw, &sy, &cy);
                 fb[3] = cy; fb[4] = sy; fb[5] = T(1) / cp; fb[6] = sp;
             } else {
-                const V4 nq = reinterpret_cast<const V4 *>(wquat + c * qstride)[node];
-                const T a[4] = {nq.x, nq.y, nq.z, nq.w};
-                T qf[4];
-                qmul<T>(a, ff + 16, qf);
-                vr[3] = qf[0]; vr[4] = qf[1]; vr[5] = qf[2]; vr[6] = qf[3];
-                fb[3] = qf[0]; fb[4] = qf[1]; fb[5] = qf[2]; fb[6] = qf[3];
+                const V4 qf = reinterpret_cast<const V4 *>(wquat + c * qstride)[f];       // phase 1q
+                vr[3] = qf.x; vr[4] = qf.y; vr[5] = qf.z; vr[6] = qf.w;
+                fb[3] = qf.x; fb[4] = qf.y; fb[5] = qf.z; fb[6] = qf.w;
             }
         }
         __syncwarp();
@@ -251,7 +258,7 @@ static int launch_pose_inst(const skb_plan *p, const skb_pose_program *pp, const
     const int al = 16 / (int)sizeof(T);
     prm.fstride = odd_quads(pp->n_nodes * 12);
     prm.tstride = odd_quads(D * 8);
-    prm.qstride = ROT == SKB_ROT_XYZW ? odd_quads(pp->n_nodes * 4) : 0;
+    prm.qstride = ROT == SKB_ROT_XYZW ? odd_quads(F * 4) : 0;          // one quaternion per feature
     prm.featstride = 8;
     const size_t smem_limit = 227 * 1024;
     auto layout = [&](int g, int warps) {

@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
                 if (sizeof(T) == 4) asm volatile("" : "+r"(cntA), "+r"(cntB));
                 // output addresses of the step, formed once per (tile, step): configuration c adds c * R (* D) to them
                 T *step_vals = tile_vals + (unsigned)(s0 + lane);
-                T *step_jac = JAC ? (CSC ? tile_jac + (unsigned)(s0 + lane) : tile_jac + (unsigned)(s0 * D)) : nullptr;
+                T *step_jac = JAC ? (CSC ? tile_jac + (unsigned)s0 : tile_jac + (unsigned)(s0 * D)) : nullptr;
                 if (sizeof(T) == 4) asm volatile("" : "+l"(step_vals), "+l"(step_jac));
                 const int4 B0 = tabB[slot * 32 + lane];
                 const int4 B1 = tabB[(slot + (cntB > 0 ? 1 : 0)) * 32 + lane];
@@ -374,8 +374,10 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
                     }
                     if (!JAC) return;
                     if (CSC) {
-                        // transposed block: element (row, col) of configuration c at  c R D + col R + row
-                        T *gA = step_jac + (unsigned)(c * R * D);          // step_jac already points at row s0 + lane of column 0
+                        // transposed block: element (row, col) of configuration c at  c R D + col R + row.  One warp-uniform
+                        // 64-bit base per (configuration, step) and a 32-bit per-lane offset that advances by 2 R per column pair
+                        T *g0 = step_jac + (unsigned)(c * R * D) + lane;   // column 0, row s0 + lane of configuration c
+                        if (sizeof(T) == 4) asm volatile("" : "+l"(g0));   // opaque: formed once, then advanced by 2 R per column pair
                         const V4 *t4 = reinterpret_cast<const V4 *>(tw);
                         const bool inA = lane < cntA, inB = HAS_B && lane < cntB;
 #pragma unroll
@@ -388,13 +390,14 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
                                     a = contract(t0, t1, t2, ra, col);
                                     if (HAS_B) b = contract(t0, t1, t2, rb, col);
                                 }
-                                T *g0 = gA + (unsigned)(col * R);
                                 if (inA) st_stream(g0, a.x);
                                 if (inB) st_stream(g0 + 32, b.x);
-                                if (col + 1 < D) {
-                                    if (inA) st_stream(g0 + R, a.y);
-                                    if (inB) st_stream(g0 + R + 32, b.y);
+                                if (VW == 2 || col + 1 < D) {              // VW == 2: D is even
+                                    T *g1 = g0 + (unsigned)R;
+                                    if (inA) st_stream(g1, a.y);
+                                    if (inB) st_stream(g1 + 32, b.y);
                                 }
+                                g0 += 2u * (unsigned)R;
                             }
                         }
                         return;
@@ -960,7 +963,8 @@ static int launch_s2_mode(S2_SIG, int mode) {
     const int NP = (p->D + 1) / 2;
     if (mode == S2_MODE_ALL_CSC) {              // transposed Jacobian blocks (CollFreeConst rows of an SQP trajectory stack)
         if (KIND != KIND_COLLFREE || NP > 16) return set_error("csc output: CollFreeConst with at most 32 columns");
-#define S2_CSC(NPM) launch_s2_inst<T, KIND_COLLFREE, (KIND == KIND_COLLFREE ? SDFK : SDF_SINGLE), 1, unsigned, false, true, NPM, true>(S2_ARGS)
+#define S2_CSC(NPM) (even ? launch_s2_inst<T, KIND_COLLFREE, (KIND == KIND_COLLFREE ? SDFK : SDF_SINGLE), 2, unsigned, false, true, NPM, true>(S2_ARGS) \
+                          : launch_s2_inst<T, KIND_COLLFREE, (KIND == KIND_COLLFREE ? SDFK : SDF_SINGLE), 1, unsigned, false, true, NPM, true>(S2_ARGS))
         if (NP <= 4) return S2_CSC(4);
         if (NP <= 8) return S2_CSC(8);
         return S2_CSC(16);

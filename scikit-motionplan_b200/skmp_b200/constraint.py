@@ -355,7 +355,7 @@ class CollFreeConst(AbstractIneqConst):
         out = b.out(valid)
         return out.bool() if _is_torch(out) else out.astype(bool)
 
-    def tune(self, qs, with_jacobian: bool = True, values: bool = True, validity: bool = False):
+    def tune(self, qs, with_jacobian: bool = True, values: bool = True, validity: bool = False, csc: bool = False):
         """Measure the kernel launch configuration for this constraint's (mode, dtype, outputs) once, explicitly, on up to
         262 144 of the sample configurations ``qs`` (a CUDA tensor) and on scratch outputs of the library's own
         (``skb_plan_tune``).  The choice is keyed by the plan's structure: it survives ``reflect_skrobot_model`` and is
@@ -370,7 +370,7 @@ class CollFreeConst(AbstractIneqConst):
         if not b.on_device:
             raise ValueError("tune() needs sample configurations on the GPU (a CUDA tensor)")
         plan = self._plan(b.device_index)
-        outputs = (1 if values else 0) | (2 if with_jacobian else 0) | (4 if validity else 0)
+        outputs = (1 if values else 0) | (2 if with_jacobian else 0) | (4 if validity else 0) | (8 if csc else 0)   # csc: evaluate_csc's kernel
         mode = _lib.MODE_CLOSEST if self.only_closest_feature else _lib.MODE_ALL
         choice = (C.c_int32 * 3)()
         sdf = getattr(self, "sdf", None)
