@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <string>
 
 #include "skb_internal.h"
@@ -50,7 +52,14 @@ struct skb_stream_ctx {
     void *dj[NS] = {nullptr, nullptr, nullptr};
     uint8_t *dvalid[NS] = {nullptr, nullptr, nullptr};
     size_t cap_q = 0, cap_v = 0, cap_j = 0, cap_valid = 0;
+    // small batches (the planners' N = 1 calls): one pinned, device-mapped staging block -- the kernel reads q from it and
+    // writes its results into it directly, so the call is one launch + one stream synchronisation, no copy engine
+    void *pin = nullptr;
+    size_t pin_cap = 0;
 };
+
+static const int64_t SMALL_N = 64;
+static const size_t SMALL_BYTES = 1u << 20;
 
 static int ensure_ctx(skb_plan *p, size_t bq, size_t bv, size_t bj, size_t bvalid) {
     if (!p->hostpipe) {
@@ -79,6 +88,7 @@ static int ensure_ctx(skb_plan *p, size_t bq, size_t bv, size_t bj, size_t bvali
 extern "C" void skb_plan_destroy_hostpipe(skb_plan *p) {
     if (!p || !p->hostpipe) return;
     skb_stream_ctx *c = p->hostpipe;
+    if (c->pin) cudaFreeHost(c->pin);
     for (int i = 0; i < skb_stream_ctx::NS; ++i) {
         if (c->st[i]) { cudaStreamSynchronize(c->st[i]); cudaStreamDestroy(c->st[i]); }
         if (c->dq[i]) cudaFree(c->dq[i]);
@@ -100,6 +110,31 @@ static int host_pipeline(skb_plan *p, int dtype, const void *q_host, int64_t N, 
     std::lock_guard<std::mutex> host_lock(p->host_mu);
     const size_t es = esize(dtype);
     const size_t per_cfg = (out_vals ? vals_per_cfg : 0) + (out_jac ? jac_per_cfg : 0) + (size_t)p->D;
+    // ---- small batch: zero-copy through one mapped, pinned block (see skb_stream_ctx)
+    static const bool zero_copy = !(getenv("SKB_HOST_ZEROCOPY") && atoi(getenv("SKB_HOST_ZEROCOPY")) == 0);
+    auto up16 = [](size_t b) { return (b + 15) / 16 * 16; };
+    const size_t bq = up16(N * p->D * es), bv = out_vals ? up16(N * vals_per_cfg * es) : 0, bj = out_jac ? up16(N * jac_per_cfg * es) : 0,
+                 bvalid = out_valid ? up16((size_t)N) : 0;
+    if (zero_copy && N <= SMALL_N && bq + bv + bj + bvalid <= SMALL_BYTES) {
+        if (ensure_ctx(p, 0, 0, 0, 0)) return -1;
+        skb_stream_ctx *c = p->hostpipe;
+        if (c->pin_cap < SMALL_BYTES) {
+            CUDA_OK(cudaHostAlloc(&c->pin, SMALL_BYTES, cudaHostAllocMapped | cudaHostAllocPortable));
+            c->pin_cap = SMALL_BYTES;
+        }
+        char *hp = reinterpret_cast<char *>(c->pin), *dp = nullptr;
+        CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&dp), c->pin, 0));
+        memcpy(hp, q_host, N * p->D * es);
+        const size_t ov = bq, oj = bq + bv, ovalid = bq + bv + bj;
+        int rc = launch(dp, N, out_vals ? dp + ov : nullptr, out_jac ? dp + oj : nullptr,
+                        out_valid ? reinterpret_cast<uint8_t *>(dp + ovalid) : nullptr, c->st[0]);
+        if (cudaStreamSynchronize(c->st[0]) != cudaSuccess && rc == 0) rc = set_error("host call: the launch failed");
+        if (rc != 0) return rc;
+        if (out_vals) memcpy(out_vals, hp + ov, N * vals_per_cfg * es);
+        if (out_jac) memcpy(out_jac, hp + oj, N * jac_per_cfg * es);
+        if (out_valid) memcpy(out_valid, hp + ovalid, (size_t)N);
+        return 0;
+    }
     int64_t chunk = (int64_t)std::max<size_t>(1024, (48u << 20) / std::max<size_t>(1, per_cfg * es));
     chunk = std::min<int64_t>(chunk, N);
     chunk = (chunk + 31) / 32 * 32;

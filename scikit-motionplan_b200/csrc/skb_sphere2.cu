@@ -23,6 +23,7 @@
 #include <cstdlib>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -719,6 +720,33 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
         return 90.0 * it / g;
     };
     L.G = 0; L.score = -1.0;
+    // The choice below costs two occupancy queries per candidate (tens of microseconds in all): it depends only on the
+    // program's structure, the kernel instantiation and the tuning knobs, so it is made once and cached -- a planner's
+    // N = 1 call pays a map lookup.
+    static std::mutex shape_mu;
+    static std::map<std::tuple<unsigned long long, const void *, int, int, int, int>, std::tuple<int, int, int, int, double>> shape_cache;
+    static const int env_g = getenv("SKB_S2_G") ? atoi(getenv("SKB_S2_G")) : 0, env_w = getenv("SKB_S2_WARPS") ? atoi(getenv("SKB_S2_WARPS")) : 0;
+    const int want_g = force_g > 0 ? force_g : (p->tune_chunk > 0 ? p->tune_chunk : env_g);      // tuning knobs
+    const int want_w = force_w > 0 ? force_w : (p->tune_warps > 0 ? p->tune_warps : env_w);
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    const auto shape_key = std::make_tuple(sp->hash, (const void *)kern, want_g, want_w, p->tune_ctas, cur_dev);
+    {
+        std::lock_guard<std::mutex> lk(shape_mu);
+        auto it = shape_cache.find(shape_key);
+        if (it != shape_cache.end()) {
+            std::tie(L.G, L.warps, L.per_sm, L.fstride, L.score) = it->second;
+            if (L.G == 0) return force_g > 0 ? -1 : set_error("step kernel: shared-memory footprint exceeds 227 KB");
+            prm.fstride = L.fstride;
+            L.smem = layout(L.G, L.warps);
+            prm.G = L.G;
+            prm.logG = 0;
+            while ((1 << prm.logG) < L.G) ++prm.logG;
+            prm.slots3 = 32 / (3 * L.G);
+            prm.n_tiles = (N + L.G - 1) / L.G;
+            return 0;
+        }
+    }
     // Frame stride of the FK walk: lane -> (row = lane % 3, configuration = lane / 3 % G) reads / writes the 16-byte row
     // `3 node + row` of its configuration's frame block.  Eight consecutive lanes (one pass of a 128-bit shared-memory
     // access) cover configurations c, c+1, c+2: with a stride of 3 (mod 8) quads their rows fall into eight different
@@ -731,9 +759,6 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
     int fs_pad = fs_min / 4;
     while (fs_pad % 8 != 3) ++fs_pad;
     fs_pad *= 4;
-    static const int env_g = getenv("SKB_S2_G") ? atoi(getenv("SKB_S2_G")) : 0, env_w = getenv("SKB_S2_WARPS") ? atoi(getenv("SKB_S2_WARPS")) : 0;
-    const int want_g = force_g > 0 ? force_g : (p->tune_chunk > 0 ? p->tune_chunk : env_g);      // tuning knobs
-    const int want_w = force_w > 0 ? force_w : (p->tune_warps > 0 ? p->tune_warps : env_w);
     for (auto &c : cand) {
         if (want_g > 0 && c[0] != want_g) continue;
         if (want_w > 0 && c[1] != want_w) continue;
@@ -755,6 +780,10 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
         if (p->tune_ctas > 0) occ = std::min(occ, p->tune_ctas);
         const double score = std::pow((double)std::min(c[1] * occ, 48), 0.75) / (fk_slots(c[0]) + phase2);
         if (score > L.score * 1.0001) { L.score = score; L.G = c[0]; L.warps = c[1]; L.per_sm = occ; L.fstride = fs; }
+    }
+    {
+        std::lock_guard<std::mutex> lk(shape_mu);
+        shape_cache[shape_key] = std::make_tuple(L.G, L.warps, L.per_sm, L.fstride, L.score);
     }
     if (L.G == 0) return force_g > 0 ? -1 : set_error("step kernel: shared-memory footprint exceeds 227 KB");
     prm.fstride = L.fstride;
@@ -825,7 +854,15 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
                           const void *host_prims, int n_prims, double margin, void *out_vals, void *out_jac, uint8_t *out_valid,
                           cudaStream_t stream) {
     auto kern = s2_kernel<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX, CSC>;
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    {
+        static std::atomic<unsigned> attr_done{0};                      // bit per device: set once, not on every launch
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 32 || !(attr_done.load(std::memory_order_relaxed) & (1u << dev))) {
+            CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            if (dev < 32) attr_done.fetch_or(1u << dev);
+        }
+    }
     static const bool verbose = getenv("SKB_S2_VERBOSE") != nullptr;
     auto configure = [&](const skb_s2_program *prog, int64_t n, S2Launch<T> &out, int fg, int fw) {
         return configure_s2<T, KIND, SDFK, VW, MaskT, RED, JAC, NPMAX, CSC>(p, prog, q, n, dev_prims, host_prims, n_prims, margin, out_vals,
@@ -868,7 +905,8 @@ static int launch_s2_inst(const skb_plan *p, const skb_s2_program *sp, const voi
     // forced configurations use the issue-slot model.
     static const int tune_min = getenv("SKB_S2_AUTOTUNE_MIN") ? atoi(getenv("SKB_S2_AUTOTUNE_MIN")) : (1 << 20);
     static const bool autotune = getenv("SKB_S2_AUTOTUNE") == nullptr || atoi(getenv("SKB_S2_AUTOTUNE")) != 0;
-    const bool forced = p->tune_chunk > 0 || p->tune_warps > 0 || p->tune_ctas > 0 || getenv("SKB_S2_G") || getenv("SKB_S2_WARPS");
+    static const bool env_forced = getenv("SKB_S2_G") || getenv("SKB_S2_WARPS");
+    const bool forced = p->tune_chunk > 0 || p->tune_warps > 0 || p->tune_ctas > 0 || env_forced;
     const bool explicit_tune = tl_tune_request != 0;
     if ((autotune || explicit_tune) && !forced) {
         constexpr unsigned inst = (unsigned)sizeof(T) | (unsigned)KIND << 4 | (unsigned)SDFK << 8 | (unsigned)VW << 12 |

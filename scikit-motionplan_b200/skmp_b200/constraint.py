@@ -63,6 +63,34 @@ def _cat(arrays, axis: int):
     return np.concatenate(list(arrays), axis=axis)
 
 
+class _SingleCall:
+    """Pre-bound state of the planners' call shape -- ONE configuration as a 1-D numpy array, a blocking answer
+    (skmp/solver/ompl_solver.py:74-80, motion_step_box.py:50-56, satisfy.py:67-82) -- so that a call is: copy q into a
+    scratch row, one ``skb_*_host`` call with pre-built ctypes arguments (the library serves a batch this small through one
+    mapped, pinned block: one launch, one stream synchronisation), read the scratch outputs.  One instance per
+    (constraint, dtype, device, solver version)."""
+
+    __slots__ = ("fn", "head", "q", "qp", "vals", "vp", "jac", "jp", "valid", "bp", "tail_all", "mode_closest_min", "m")
+
+    def __init__(self, fn, head, dtype, d, m, tail_mode, closest_mode):
+        import ctypes as C
+
+        self.fn, self.head, self.m = fn, head, m
+        self.q = np.zeros((1, d), dtype=dtype)
+        self.vals = np.zeros((1, m), dtype=dtype)
+        self.jac = np.zeros((1, m, d), dtype=dtype)
+        self.valid = np.zeros(1, dtype=np.uint8)
+        self.qp, self.vp, self.jp, self.bp = (C.c_void_p(a.ctypes.data) for a in (self.q, self.vals, self.jac, self.valid))
+        self.tail_all = tail_mode               # (N, [margin,] mode) arguments between q and the outputs
+        self.mode_closest_min = closest_mode
+
+    def run(self, q, tail, vp, jp, bp):
+        self.q[0] = q
+        rc = self.fn(*self.head, self.qp, *tail, vp, jp, bp)
+        if rc != 0:
+            _lib.check(rc)
+
+
 class AbstractConst(ABC):
     reflect_robot_flag: bool = False
     id_value: str
@@ -71,6 +99,7 @@ class AbstractConst(ABC):
         # native plan handles are per-object caches: never copied or pickled (copy.deepcopy / ParallelSolver forks)
         d = dict(self.__dict__)
         d.pop("_plan_cache", None)
+        d.pop("_single_cache", None)
         return d
 
     def assign_id_value(self):
@@ -168,7 +197,12 @@ class IneqCompositeConst(AbstractIneqConst, _CompositeConst[AbstractIneqConst]):
     """Order matters: ``is_valid`` returns at the first violated member."""
 
     def is_valid(self, q) -> bool:
+        lean = type(q) is np.ndarray and q.ndim == 1
         for const in self.const_list:
+            if lean and hasattr(const, "_min_value_single") and const.reflect_robot_flag:
+                if const._min_value_single(q) < 0.0:         # the collision kernels reduce to the row minimum themselves
+                    return False
+                continue
             values, _ = const.evaluate_single(q, False)
             if bool((values < 0.0).any()):
                 return False
@@ -318,6 +352,44 @@ class CollFreeConst(AbstractIneqConst):
     def _evaluate(self, qs, with_jacobian: bool):
         b, vals, jac, _ = self._run(qs, True, with_jacobian, False)
         return b.out(vals), (b.out(jac) if with_jacobian else self.dummy_jacobian())
+
+    # ---- one configuration per call (numpy 1-D in, numpy / bool out): the planners' call shape, kept lean
+    def _single(self, q):
+        dt = q.dtype.type if q.dtype.type in (np.float32, np.float64) else np.float64
+        dev = current_device_index()
+        key = (dt, dev)
+        cache = self.__dict__.setdefault("_single_cache", {})
+        sc = cache.get(key)
+        solver = self.colkin.fksolver
+        if sc is None or sc[1] != solver._version or sc[2] is not solver or sc[3] != (self.distance_margin, self.only_closest_feature):
+            plan = self._plan(dev)
+            code = _lib.F32 if dt == np.float32 else _lib.F64
+            mode = _lib.MODE_CLOSEST if self.only_closest_feature else _lib.MODE_ALL
+            m = 1 if self.only_closest_feature else plan.n_feature
+            call = _SingleCall(_lib.lib().skb_collfree_host, (plan.handle, self.sdf.native(dev), code), dt, plan.dim_cspace, m,
+                               (1, float(self.distance_margin), mode), (1, float(self.distance_margin), _lib.MODE_CLOSEST))
+            sc = cache[key] = (call, solver._version, solver, (self.distance_margin, self.only_closest_feature), plan)
+        return sc[0]
+
+    def evaluate_single(self, q, with_jacobian: bool):
+        if type(q) is not np.ndarray or q.ndim != 1 or not self.reflect_robot_flag:
+            return AbstractConst.evaluate_single(self, q, with_jacobian)      # (no zero-argument super: shared with the pairwise class)
+        sc = self._single(q)
+        sc.run(q, sc.tail_all, sc.vp, sc.jp if with_jacobian else None, None)
+        return sc.vals[0].copy(), (sc.jac[0].copy() if with_jacobian else self.dummy_jacobian()[0])
+
+    def is_valid(self, q) -> bool:
+        if type(q) is not np.ndarray or q.ndim != 1 or not self.reflect_robot_flag:
+            return AbstractIneqConst.is_valid(self, q)
+        sc = self._single(q)
+        sc.run(q, sc.tail_all, None, None, sc.bp)          # the validity byte: all(values > 0), computed by the kernel
+        return bool(sc.valid[0])
+
+    def _min_value_single(self, q) -> float:
+        """min over the rows for one configuration (what a composite's ``is_valid`` compares with 0)."""
+        sc = self._single(q)
+        sc.run(q, sc.mode_closest_min, sc.vp, None, None)
+        return float(sc.vals[0, 0])
 
     def evaluate_csc(self, qs):
         """values (N, M) and the Jacobian block of every configuration TRANSPOSED, (N, D, M): the order in which the SQP
@@ -612,6 +684,27 @@ class PairWiseSelfCollFreeConst(AbstractIneqConst):
     def _evaluate(self, qs, with_jacobian: bool):
         b, vals, jac, _ = self._run(qs, True, with_jacobian, False)
         return b.out(vals), (b.out(jac) if with_jacobian else self.dummy_jacobian())
+
+    def _single(self, q):
+        dt = q.dtype.type if q.dtype.type in (np.float32, np.float64) else np.float64
+        dev = current_device_index()
+        key = (dt, dev)
+        cache = self.__dict__.setdefault("_single_cache", {})
+        sc = cache.get(key)
+        solver = self.colkin.fksolver
+        if (sc is None or sc[1] != solver._version or sc[2] is not solver or sc[3] != self.only_closest_feature
+                or sc[5] is not self.check_sphere_id_pairs):
+            plan = self._plan(dev)
+            code = _lib.F32 if dt == np.float32 else _lib.F64
+            mode = _lib.MODE_CLOSEST if self.only_closest_feature else _lib.MODE_ALL
+            m = 1 if self.only_closest_feature else len(self.check_sphere_id_pairs)
+            call = _SingleCall(_lib.lib().skb_pairwise_host, (plan.handle, code), dt, plan.dim_cspace, m, (1, mode), (1, _lib.MODE_CLOSEST))
+            sc = cache[key] = (call, solver._version, solver, self.only_closest_feature, plan, self.check_sphere_id_pairs)
+        return sc[0]
+
+    evaluate_single = CollFreeConst.evaluate_single
+    is_valid = CollFreeConst.is_valid
+    _min_value_single = CollFreeConst._min_value_single
 
     _min_values = CollFreeConst._min_values
     tune = CollFreeConst.tune
