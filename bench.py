@@ -647,9 +647,10 @@ def reference_pair_list(kin):
 
 
 def bind_to_gpu_numa_node(local: int):
-    """Pin this rank's host threads (and therefore its first-touch pinned buffers) to the NUMA node its GPU hangs on, so
-    that the D2H streams of several ranks do not all land in one socket's memory.  /sys first, `nvidia-smi topo` when the
-    PCI device reports no node.  Best effort; returns a description."""
+    """Pin this rank's host threads (and therefore its first-touch pinned buffers) to the CPUs next to its GPU, so that the
+    D2H streams of several ranks do not all land in one socket's memory.  /sys first (PCI device -> NUMA node -> cpulist), the
+    "CPU Affinity" column of `nvidia-smi topo -m` when the PCI device reports no node.  Never narrows the affinity to fewer
+    than 4 CPUs (a single-node box reports every CPU for every GPU: nothing to do).  Best effort; returns a description."""
     try:
         import torch
 
@@ -660,25 +661,34 @@ def bind_to_gpu_numa_node(local: int):
             node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text().strip())
         except Exception:
             pass
+
+        def parse(cpulist):
+            cpus = []
+            for part in cpulist.strip().split(","):
+                a, _, b = part.strip().partition("-")
+                if a.isdigit():
+                    cpus.extend(range(int(a), int(b or a) + 1))
+            return cpus
+
         cpus, how = [], "sysfs"
         if node >= 0:
-            for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
-                a, _, b = part.partition("-")
-                cpus.extend(range(int(a), int(b or a) + 1))
+            cpus = parse(Path(f"/sys/devices/system/node/node{node}/cpulist").read_text())
         else:
-            how = "nvidia-smi topo"
-            out = subprocess.run(["nvidia-smi", "topo", "-C", "-i", str(local)], capture_output=True, text=True, timeout=10).stdout
-            for line in out.splitlines():          # "CPU Affinity of GPU 0: 0-15,32-47"  (older drivers: not supported)
-                if ":" in line and any(ch.isdigit() for ch in line.split(":")[-1]):
-                    for part in line.split(":")[-1].strip().split(","):
-                        a, _, b = part.strip().partition("-")
-                        if a.isdigit():
-                            cpus.extend(range(int(a), int(b or a) + 1))
+            how = "nvidia-smi topo -m"
+            out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=10).stdout
+            import re
+            for line in out.splitlines():
+                clean = re.sub(r"\x1b\[[0-9;]*m", "", line)
+                if clean.startswith(f"GPU{local}\t") or clean.startswith(f"GPU{local} "):
+                    for field in clean.split("\t"):                       # the affinity column looks like 0-23 or 0-15,32-47
+                        if re.fullmatch(r"\s*\d+(-\d+)?(,\d+(-\d+)?)*\s*", field) and ("-" in field or "," in field):
+                            cpus = parse(field)
+                            break
         allowed = sorted(set(cpus) & os.sched_getaffinity(0))
-        if allowed:
+        if len(allowed) >= 4 and len(allowed) < len(os.sched_getaffinity(0)):
             os.sched_setaffinity(0, allowed)
             return f"gpu {bus} -> {len(allowed)} cpus ({how}, node {node})"
-        return f"gpu {bus}: no NUMA information ({how})"
+        return f"gpu {bus}: not bound ({how}: {len(allowed)} of {len(os.sched_getaffinity(0))} cpus, node {node})"
     except Exception as e:      # pragma: no cover
         return f"not bound ({type(e).__name__})"
 

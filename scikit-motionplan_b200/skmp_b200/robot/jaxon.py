@@ -98,6 +98,25 @@ class JaxonConfig:
         base_bounds = np.array([-1.0, -1.0, 0.0, -1.0, -1.0, -1.0]), np.array([2.0, 1.0, 3.0, 1.0, 1.0, 1.0])
         return BoxConst.from_urdf(self.urdf_path(), self._get_control_joint_names(), base_bounds=base_bounds)
 
+    def get_close_box_const(self, q: Optional[np.ndarray] = None, joint_margin: float = 1.0, base_pos_margin: float = 0.8,
+                            base_rot_margin: float = 1.0) -> BoxConst:
+        """skmp/robot/jaxon.py:346-372: the joint box shrunk to a neighbourhood of ``q`` (joints and base rotation clipped to
+        the global box, base position not)."""
+        box_const = self.get_box_const()
+        if q is None:
+            return box_const
+        q = np.asarray(q, dtype=np.float64)
+        q_max, q_min = np.zeros(q.shape), np.zeros(q.shape)
+        for sl, margin, do_clip in ((slice(None, -6), joint_margin, True), (slice(-6, -3), base_pos_margin, False),
+                                    (slice(-3, None), base_rot_margin, True)):
+            if do_clip:
+                q_max[sl] = np.minimum(q[sl] + margin, box_const.ub[sl])
+                q_min[sl] = np.maximum(q[sl] - margin, box_const.lb[sl])
+            else:
+                q_max[sl] = q[sl] + margin
+                q_min[sl] = q[sl] - margin
+        return BoxConst(q_min, q_max)
+
     def get_motion_step_box(self) -> np.ndarray:
         width = {jn: 0.2 for jn in self._get_control_joint_names()}
         for limb in ("RARM", "LARM", "RLEG", "LLEG", "CHEST"):

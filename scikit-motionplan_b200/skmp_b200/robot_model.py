@@ -57,12 +57,19 @@ class RobotModel:
     def joint_names(self) -> List[str]:
         return [j.name for j in self.joint_list]
 
-    def newcoords(self, pos, rot=None) -> None:
-        """``robot.newcoords(Coordinates(pos, rot))`` -- takes the two parts directly."""
-        if rot is None and hasattr(pos, "worldpos"):
-            pos, rot = pos.worldpos(), pos.worldrot()
-        self.translation = np.asarray(pos, dtype=np.float64).copy()
-        self.rotation = np.eye(3) if rot is None else np.asarray(rot, dtype=np.float64).copy()
+    def newcoords(self, c, pos=None) -> None:
+        """``robot.newcoords(c, pos=None)`` as in skrobot: ``c`` is a coordinates object, or a 3x3 rotation with ``pos`` the
+        translation; a 3-vector first (and optionally a 3x3 rotation second) is understood as well."""
+        if hasattr(c, "worldpos") and hasattr(c, "worldrot"):
+            p, r = c.worldpos(), c.worldrot()
+        else:
+            a = np.asarray(c, dtype=np.float64)
+            if a.shape == (3, 3):
+                r, p = a, (np.zeros(3) if pos is None else pos)
+            else:
+                p, r = a, (np.eye(3) if pos is None else pos)
+        self.translation = np.asarray(p, dtype=np.float64).reshape(3).copy()
+        self.rotation = np.asarray(r, dtype=np.float64).reshape(3, 3).copy()
 
     def angle_vector(self, av=None) -> np.ndarray:
         if av is not None:
@@ -76,7 +83,8 @@ class RobotModel:
 
 
 class Coordinates:
-    """``skrobot.coordinates.Coordinates(pos=, rot=)`` stand-in for pose targets (constraint.py:474-498)."""
+    """``skrobot.coordinates.Coordinates(pos=, rot=)`` stand-in for pose targets (constraint.py:474-498) with the methods the
+    reference's examples chain on it (translate / rotate / copy_worldcoords)."""
 
     def __init__(self, pos=None, rot=None):
         self._pos = np.zeros(3) if pos is None else np.asarray(pos, dtype=np.float64).copy()
@@ -87,6 +95,22 @@ class Coordinates:
 
     def worldrot(self):
         return self._rot.copy()
+
+    def translate(self, vec, wrt: str = "local"):
+        vec = np.asarray(vec, dtype=np.float64)
+        self._pos = self._pos + (self._rot @ vec if wrt == "local" else vec)
+        return self
+
+    def rotate(self, theta: float, axis, wrt: str = "local"):
+        from .rotmath import rotation_matrix
+
+        ax = {"x": [1.0, 0.0, 0.0], "y": [0.0, 1.0, 0.0], "z": [0.0, 0.0, 1.0]}[axis] if isinstance(axis, str) else axis
+        mat = rotation_matrix(float(theta), np.asarray(ax, dtype=np.float64))
+        self._rot = self._rot @ mat if wrt == "local" else mat @ self._rot
+        return self
+
+    def copy_worldcoords(self):
+        return Coordinates(self._pos, self._rot)
 
 
 class PR2(RobotModel):

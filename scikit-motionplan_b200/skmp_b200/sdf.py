@@ -122,19 +122,41 @@ class _Posed(SignedDistanceFunction):
         return self
 
     def rotate_with_matrix(self, mat, wrt: str = "local"):
+        """``skrobot.coordinates.Coordinates.rotate_with_matrix``: local -> R <- R mat, world -> R <- mat R; the position
+        stays where it is in both cases."""
         mat = np.asarray(mat, dtype=np.float64)
         self._rot = self._rot @ mat if wrt == "local" else mat @ self._rot
-        if wrt != "local":
-            self._pos = mat @ self._pos
         self.invalidate()
         return self
 
-    def newcoords(self, pos, rot=None):
-        self._pos = np.asarray(pos, dtype=np.float64).copy()
-        if rot is not None:
-            self._rot = np.asarray(rot, dtype=np.float64).copy()
+    def rotate(self, theta: float, axis, wrt: str = "local"):
+        """``Coordinates.rotate(theta, axis)``: axis 'x' / 'y' / 'z' or a 3-vector (example/humanoid_dualarm.py:34)."""
+        from .rotmath import rotation_matrix
+
+        ax = {"x": [1.0, 0.0, 0.0], "y": [0.0, 1.0, 0.0], "z": [0.0, 0.0, 1.0]}.get(axis, axis) if isinstance(axis, str) else axis
+        return self.rotate_with_matrix(rotation_matrix(float(theta), np.asarray(ax, dtype=np.float64)), wrt)
+
+    def newcoords(self, c, pos=None):
+        """``Coordinates.newcoords(c, pos=None)``: ``c`` is a coordinates object (anything with worldpos / worldrot), or a
+        3x3 rotation with ``pos`` the translation.  (A 3-vector first and a 3x3 matrix second -- this package's earlier
+        argument order -- is still understood: the shapes are unambiguous.)"""
+        if hasattr(c, "worldpos") and hasattr(c, "worldrot"):
+            p, r = c.worldpos(), c.worldrot()
+        else:
+            a = np.asarray(c, dtype=np.float64)
+            if a.shape == (3, 3):
+                r, p = a, (self._pos if pos is None else pos)
+            else:
+                p, r = a, (self._rot if pos is None else pos)
+        self._pos = np.asarray(p, dtype=np.float64).reshape(3).copy()
+        self._rot = np.asarray(r, dtype=np.float64).reshape(3, 3).copy()
         self.invalidate()
         return self
+
+    def copy_worldcoords(self):
+        from .robot_model import Coordinates
+
+        return Coordinates(self._pos, self._rot)
 
     def worldpos(self) -> np.ndarray:
         return self._pos.copy()

@@ -158,3 +158,56 @@ def test_satisfy_shortcuts_and_no_cpu_fallback():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             satisfy_by_optimization_batch(None, box, None, np.zeros((2, 3)))
+
+
+def test_skrobot_coordinate_api_of_primitives_and_targets():
+    """The slice of skrobot's Coordinates API the reference's scenes use on primitives and pose targets
+    (example/humanoid_dualarm.py:31-42,63; constrained_dualarm_planning.py:47-60): translate (local / world), rotate by an
+    axis name, rotate_with_matrix in the world frame leaves the position alone, newcoords takes a coordinates object or
+    (rotation, position)."""
+    from skmp_b200.robot_model import Coordinates, PR2
+    from skmp_b200.rotmath import rotation_matrix
+    from skmp_b200.sdf import Box
+
+    Rz = rotation_matrix(np.pi * 0.5, [0.0, 0.0, 1.0])
+    table = Box([0.6, 1.0, 0.8])
+    table.rotate(np.pi * 0.5, "z")
+    table.translate([0.7, 0.0, 0.4])                       # local frame: x is now the world's y
+    assert np.allclose(table.worldrot(), Rz) and np.allclose(table.worldpos(), Rz @ [0.7, 0.0, 0.4])
+    table.translate([0.0, 0.0, 0.1], wrt="world")
+    assert np.allclose(table.worldpos(), Rz @ [0.7, 0.0, 0.4] + [0.0, 0.0, 0.1])
+    pos = table.worldpos()
+    table.rotate_with_matrix(Rz, wrt="world")
+    assert np.allclose(table.worldpos(), pos) and np.allclose(table.worldrot(), Rz @ Rz)
+    co = Coordinates([0.6, -0.25, 0.25]).rotate(np.pi * 0.5, "z")
+    assert np.allclose(co.worldrot(), Rz) and np.allclose(co.worldpos(), [0.6, -0.25, 0.25])
+    other = Box([0.1, 0.1, 0.1])
+    other.newcoords(co.copy_worldcoords())
+    assert np.allclose(other.worldpos(), co.worldpos()) and np.allclose(other.worldrot(), Rz)
+    other.newcoords(np.eye(3), [1.0, 2.0, 3.0])            # skrobot's (rotation, position)
+    assert np.allclose(other.worldrot(), np.eye(3)) and np.allclose(other.worldpos(), [1.0, 2.0, 3.0])
+    prims = other.primitives()
+    assert prims[0][0] == "box" and np.allclose(prims[0][1], [1.0, 2.0, 3.0])
+    robot = PR2()
+    robot.newcoords(co)
+    assert np.allclose(robot.translation, co.worldpos()) and np.allclose(robot.rotation, Rz)
+    robot.newcoords(Rz.T, [0.1, 0.2, 0.0])
+    assert np.allclose(robot.rotation, Rz.T) and np.allclose(robot.translation, [0.1, 0.2, 0.0])
+    robot.newcoords([0.3, -0.2, 0.0])                      # position only (this package's earlier call shape)
+    assert np.allclose(robot.translation, [0.3, -0.2, 0.0]) and np.allclose(robot.rotation, np.eye(3))
+
+
+def test_jaxon_close_box_const():
+    """skmp/robot/jaxon.py:346-372."""
+    from skmp_b200.robot.jaxon import JaxonConfig
+
+    conf = JaxonConfig()
+    full = conf.get_box_const()
+    assert conf.get_close_box_const().lb.shape == (37,)
+    q = 0.5 * (full.lb + full.ub)
+    q[-6:-3] = [5.0, -5.0, 9.0]                                  # base position far outside the global box: not clipped
+    close = conf.get_close_box_const(q, joint_margin=0.3, base_pos_margin=0.8, base_rot_margin=10.0)
+    assert np.allclose(close.ub[:-6], np.minimum(q[:-6] + 0.3, full.ub[:-6])) and np.allclose(close.lb[:-6], np.maximum(q[:-6] - 0.3, full.lb[:-6]))
+    assert np.allclose(close.lb[-6:-3], q[-6:-3] - 0.8) and np.allclose(close.ub[-6:-3], q[-6:-3] + 0.8)
+    assert np.allclose(close.lb[-3:], full.lb[-3:]) and np.allclose(close.ub[-3:], full.ub[-3:])     # clipped to the global box
+    assert close.is_valid(q)
