@@ -394,6 +394,12 @@ __device__ __forceinline__ void fk_phase(const int lane, const int G, const int 
             __syncwarp();
         }
     }
+    // level 0 is the world node alone (its frame is its constant): stored once, so every node of the loop below has a parent
+    if (lv_first == 0) {
+        if (act && slot == 0) sts_v4(a_fr, lds_v4(a_nodeFr, T()));
+        lv_first = 1;
+        __syncwarp();
+    }
     for (int lv = lv_first; lv < n_levels; ++lv) {
         const int2 lrec = lds_i2(a_lev + 8u * lv);                          // {first entry of the level, count}
         const int lbeg = lrec.x, lcnt = lrec.y;
@@ -402,31 +408,32 @@ __device__ __forceinline__ void fk_phase(const int lane, const int G, const int 
             const bool on = act && k < lcnt;
             const int4 rec = lds_i4(a_lv + 16u * (lbeg + (on ? k : 0)));    // {type, column, 3 parent, 3 node}
             const int type = rec.x, col = rec.y, par3 = rec.z, node3 = rec.w;
-            V4 y = lds_v4(a_nodeFr + node3 * VS, T());
-            if (par3 >= 0) {
-                const uint32_t ac = a_nodeF + node3 * VS;
-                const V4 c0 = lds_v4(ac, T()), c1 = lds_v4(ac + VS, T()), c2 = lds_v4(ac + 2 * VS, T());
-                const V4 P = lds_v4(a_fr + par3 * VS, T());
-                y.x = P.x * c0.x + P.y * c1.x + P.z * c2.x;
-                y.y = P.x * c0.y + P.y * c1.y + P.z * c2.y;
-                y.z = P.x * c0.z + P.y * c1.z + P.z * c2.z;
-                y.w = P.w + P.x * c0.w + P.y * c1.w + P.z * c2.w;
-            }
+            const uint32_t ac = a_nodeF + node3 * VS;
+            const V4 c0 = lds_v4(ac, T()), c1 = lds_v4(ac + VS, T()), c2 = lds_v4(ac + 2 * VS, T());
+            const V4 P = lds_v4(a_fr + par3 * VS, T());
+            V4 y;
+            y.x = P.x * c0.x + P.y * c1.x + P.z * c2.x;
+            y.y = P.x * c0.y + P.y * c1.y + P.z * c2.y;
+            y.z = P.x * c0.z + P.y * c1.z + P.z * c2.z;
+            y.w = P.w + P.x * c0.w + P.y * c1.w + P.z * c2.w;
             // (o, omega) entries of the two other rows: joint axis = local +z = third column, origin = fourth
             const T o1 = __shfl_sync(0xffffffffu, y.w, src1), o2 = __shfl_sync(0xffffffffu, y.w, src2);
             const T w1 = __shfl_sync(0xffffffffu, y.z, src1), w2 = __shfl_sync(0xffffffffu, y.z, src2);
-            T wr = T(0), vr = T(0);
-            if (type == NODE_REVOLUTE) {
-                T s, c;
-                lds_sc(a_sc + 2 * col * ES, s, c);
-                wr = y.z;
-                vr = o1 * w2 - o2 * w1;                       // v = o x omega, component `row`
-                const T a = y.x, b = y.y;
-                y.x = c * a + s * b; y.y = c * b - s * a;
-            } else if (type == NODE_PRISMATIC) {
-                vr = y.z;
-                y.w += lds_1(a_q + col * ES, T()) * y.z;
-            }
+            // joint motion without branches: a revolute joint turns (x, y) by its (sin, cos), a prismatic one slides along z
+            // by q, anything else is the identity -- (s, c, d) = (0, 1, 0) leaves the row bit for bit as it is
+            const bool rev = type == NODE_REVOLUTE, pri = type == NODE_PRISMATIC;
+            const int colc = max(col, 0);
+            T s, c;
+            lds_sc(a_sc + 2 * colc * ES, s, c);
+            const T d = pri ? T(1) : T(0);                                       // (selects, not branches: the loads below are unconditional)
+            const T qv = lds_1(a_q + colc * ES, T());
+            s = rev ? s : T(0);
+            c = rev ? c : T(1);
+            const T wr = rev ? y.z : T(0);
+            const T vr = rev ? o1 * w2 - o2 * w1 : (pri ? y.z : T(0));       // v = o x omega, component `row` / the sliding axis
+            const T a = y.x, b = y.y;
+            y.x = c * a + s * b; y.y = c * b - s * a;
+            y.w += (d * qv) * y.z;
             if (on) {
                 sts_v4(a_fr + node3 * VS, y);
                 if (WITH_JAC && col >= 0) {
