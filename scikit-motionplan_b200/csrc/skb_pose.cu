@@ -44,6 +44,7 @@ struct PoseParams {
     int fstride, tstride, qstride, featstride;
     int G, logG, slots3;
     int D, n_feat, n_levels, rot_type, tdim;
+    unsigned div_magic;                  // ceil(2^32 / D): i / D == __umulhi(i, div_magic) for i < 2^16
 };
 
 template <typename T>
@@ -99,13 +100,16 @@ __global__ void __launch_bounds__(256) pose_kernel(const PoseParams<T> prm) {
         for (int i = lane; i < g_live * D; i += 32) {
             const T th = prm.q[n0 * D + i];
             T sn, cs;
-            Rl::sincos(th, &sn, &cs);
             wq[i] = th;
-            wsc[2 * i] = sn; wsc[2 * i + 1] = cs;
             if (ROT == SKB_ROT_XYZW) {
-                Rl::sincos(T(0.5) * th, &sn, &cs);
-                wsch[2 * i] = sn; wsch[2 * i + 1] = cs;
-            }
+                // one sincos per joint value: the quaternion factors need the half angle, the frames get
+                // sin = 2 sh ch, cos = (ch - sh)(ch + sh) from it (each within 2 ulp of the direct evaluation)
+                T sh, ch;
+                Rl::sincos(T(0.5) * th, &sh, &ch);
+                wsch[2 * i] = sh; wsch[2 * i + 1] = ch;
+                sn = T(2) * sh * ch; cs = (ch - sh) * (ch + sh);
+            } else Rl::sincos(th, &sn, &cs);
+            wsc[2 * i] = sn; wsc[2 * i + 1] = cs;
         }
         __syncwarp();
         fk_phase<T, true, false>(lane, G, logG, prm.slots3, g_live, D, n_levels, lvrec, levelI, nodeF, wq, wsc,
@@ -194,32 +198,32 @@ __global__ void __launch_bounds__(256) pose_kernel(const PoseParams<T> prm) {
 
         // ------------------------------------------------------------ phase 2: lane per (configuration, column)
         for (int i = lane; i < g_live * D; i += 32) {
-            const int c = i / D, d = i - c * D;
+            const int c = (int)__umulhi((unsigned)i, prm.div_magic), d = i - c * D;       // i / D, exact for i < 2^16
             const T *tw = wtw + c * tstride + d * 8;
             const V4 w = *reinterpret_cast<const V4 *>(tw), v = *reinterpret_cast<const V4 *>(tw + 4);
-            T *g = prm.out_jac + (n0 + c) * FTD + d;
+            T *row = prm.out_jac + ((n0 + c) * FTD + d);            // row 0 of feature 0; every further row is D elements on
+            const V4 *fb4 = reinterpret_cast<const V4 *>(wfeat + c * F * featstride);
             for (int f = 0; f < F; ++f) {
                 const int4 fi = featI[f];
                 const unsigned long long am = ((unsigned long long)(unsigned)fi.z << 32) | (unsigned)fi.y;
                 const bool mine = (am >> d) & 1ull;
-                const T *fb = wfeat + (c * F + f) * featstride;
-                const T px = fb[0], py = fb[1], pz = fb[2], a0 = fb[3], a1 = fb[4], a2 = fb[5], a3 = fb[6];
+                const V4 fa = fb4[2 * f], fb = fb4[2 * f + 1];       // {px py pz a0} {a1 a2 a3 .}
+                const T px = fa.x, py = fa.y, pz = fa.z, a0 = fa.w, a1 = fb.x, a2 = fb.y, a3 = fb.z;
                 const T wx = mine ? w.x : T(0), wy = mine ? w.y : T(0), wz = mine ? w.z : T(0);
                 const T vx = mine ? v.x : T(0), vy = mine ? v.y : T(0), vz = mine ? v.z : T(0);
-                T *row = g + (long long)f * TD * D;
-                row[0] = wy * pz - wz * py + vx;
-                row[D] = wz * px - wx * pz + vy;
-                row[2 * D] = wx * py - wy * px + vz;
+                *row = wy * pz - wz * py + vx; row += D;
+                *row = wz * px - wx * pz + vy; row += D;
+                *row = wx * py - wy * px + vz; row += D;
                 if (ROT == SKB_ROT_RPY) {
                     const T rr = (a0 * wx + a1 * wy) * a2;          // (cy wx + sy wy) / cp
-                    row[3 * D] = rr;
-                    row[4 * D] = a0 * wy - a1 * wx;
-                    row[5 * D] = wz + a3 * rr;
+                    *row = rr; row += D;
+                    *row = a0 * wy - a1 * wx; row += D;
+                    *row = wz + a3 * rr; row += D;
                 } else {
-                    row[3 * D] = T(0.5) * (a3 * wx + (wy * a2 - wz * a1));
-                    row[4 * D] = T(0.5) * (a3 * wy + (wz * a0 - wx * a2));
-                    row[5 * D] = T(0.5) * (a3 * wz + (wx * a1 - wy * a0));
-                    row[6 * D] = T(-0.5) * (wx * a0 + wy * a1 + wz * a2);
+                    *row = T(0.5) * (a3 * wx + (wy * a2 - wz * a1)); row += D;
+                    *row = T(0.5) * (a3 * wy + (wz * a0 - wx * a2)); row += D;
+                    *row = T(0.5) * (a3 * wz + (wx * a1 - wy * a0)); row += D;
+                    *row = T(-0.5) * (wx * a0 + wy * a1 + wz * a2); row += D;
                 }
             }
         }
@@ -250,6 +254,7 @@ static int launch_pose_inst(const skb_plan *p, const skb_pose_program *pp, const
     prm.i_total = (int)pp->I.size();
     prm.f_total = (int)pp->F.size();
     const int D = p->D, F = p->F;
+    prm.div_magic = (unsigned)((0x100000000ull + (unsigned long long)D - 1) / (unsigned long long)D);
     prm.D = D; prm.n_feat = F; prm.n_levels = pp->n_levels; prm.rot_type = ROT; prm.tdim = ROT == SKB_ROT_RPY ? 6 : 7;
     prm.off_F = align_up(prm.i_total * 4, 16);
     prm.off_lv = align_up(prm.off_F + prm.f_total * (int)sizeof(T), 16);
