@@ -237,10 +237,17 @@ class TrajectoryBatchStack:
         nnz = len(indices)
         groups = self._groups()
         values = data = None
-        if len(groups) == 1 and list(self.table) == list(range(self.n_wp)):
-            # one constraint on every waypoint in order: its outputs ARE the stacked arrays
-            const = groups[0][0]
-            v, d = self._block(const, trajs.reshape(B * self.n_wp, self.n_dof))
+        if len(groups) == 1 and list(self.table) == sorted(self.table):
+            # one constraint on waypoints in ascending order: its outputs ARE the stacked arrays (rows follow the table,
+            # columns the waypoints -- the same order here); every waypoint: not even a gather of the rows
+            const, idxs = groups[0]
+            if len(idxs) == self.n_wp:
+                rows = trajs.reshape(B * self.n_wp, self.n_dof)
+            elif len(idxs) == 1:
+                rows = trajs[:, idxs[0], :].contiguous()
+            else:
+                rows = trajs[:, idxs, :].reshape(B * len(idxs), self.n_dof)
+            v, d = self._block(const, rows)
             values, data = v.reshape(B, m_total), d.reshape(B, nnz)
         else:
             values = torch.empty((B, m_total), dtype=t.dtype, device=t.device)
@@ -254,7 +261,14 @@ class TrajectoryBatchStack:
                 values.index_copy_(1, vcols, v.reshape(B, len(order) * m))
                 data.index_copy_(1, dcols, d.reshape(B, len(order) * m * self.n_dof))
         if is_np:
-            return values.cpu().numpy(), data.cpu().numpy()
+            # device -> pinned host, both copies in flight together, one synchronisation (a pageable destination would be
+            # staged through the driver's bounce buffer at a few GB/s)
+            hv = torch.empty(values.shape, dtype=values.dtype, pin_memory=True)
+            hd = torch.empty(data.shape, dtype=data.dtype, pin_memory=True)
+            hv.copy_(values, non_blocking=True)
+            hd.copy_(data, non_blocking=True)
+            torch.cuda.current_stream(values.device).synchronize()
+            return hv.numpy(), hd.numpy()
         return values, data
 
     def _block(self, const, rows):
