@@ -810,6 +810,16 @@ def run_b200(args):
         cfg["timed_call"] = ("the device-timed loop calls the C ABI (skb_collfree) directly on resident buffers" if args.workload == "cfg3"
                              else "the device-timed loop calls the Python API on resident CUDA tensors (outputs allocated per step from torch's caching allocator)")
         cfg["sphere_evals_per_s" if args.workload in ("cfg3", "cfg4") else "rows_per_s"] = value * {"cfg3": S, "cfg4": 76, "cfg2": getattr(w, "P", 0), "cfg5": 85 + 28}.get(args.workload, 1)
+        # the e2e leg is a D2H stream: compare its per-rank rate with the box's raw pinned-copy ceiling at this rank count
+        # (profiles/r2_d2h.json, measured once with tools/d2h_bench.py -- a static reference, not measured in this run)
+        pcie = None
+        dp = ROOT / "profiles" / "r2_d2h.json"
+        if dp.exists():
+            per_n = json.loads(dp.read_text()).get("per_n", {})
+            if str(world) in per_n:
+                raw = per_n[str(world)]["d2h_gbs_per_rank_3stream"]
+                pcie = {"raw_d2h_gbs_per_rank": raw, "frac_of_pcie": (d2h * e2e_steps / float(te[0]) / 1e9) / raw,
+                        "source": "profiles/r2_d2h.json (static)"}
         line = {
             "metric": w.metric, "value": value, "unit": "configs/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -821,7 +831,7 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "configs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "configs_per_step": n_e2e, "host_affinity_rank0": numa, "api": api,
-                    "d2h_gbs_per_rank": d2h * e2e_steps / float(te[0]) / 1e9},
+                    "d2h_gbs_per_rank": d2h * e2e_steps / float(te[0]) / 1e9, "pcie": pcie},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
