@@ -6,8 +6,13 @@ bench.py stays the contract benchmark (cfg3); this script feeds DESIGN.md / prof
 """
 import argparse
 import json
+import os
 import sys
 from pathlib import Path
+
+# This script measures kernels: the first (warm-up) call of every workload may time its launch candidates inside the call,
+# whatever the batch size -- what a product caller does explicitly with `constraint.tune(qs)` / skb_plan_tune.
+os.environ.setdefault("SKB_S2_AUTOTUNE_MIN", "32768")
 
 import numpy as np
 
