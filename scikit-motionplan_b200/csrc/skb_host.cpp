@@ -1138,6 +1138,7 @@ static int upload_prims(skb_sdf *s, void **dst) {
         }
         d.flags = (ident ? PF_IDENTITY : 0) | (h.grid_is_f64 ? PF_GRID_F64 : 0) | (h.dev_cells ? PF_GRID_CELLS : 0);
         d.cells = h.dev_cells;
+        d.cells_tex = h.cells_tex;
         for (int k = 0; k < 3; ++k) { d.pos[k] = (T)h.pos[k]; d.dims[k] = h.dims[k]; }
         for (int k = 0; k < 8; ++k) d.par[k] = (T)h.par[k];
         if (h.type == PRIM_GRID) for (int k = 0; k < 3; ++k) d.par[3 + k] = (T)(1.0 / h.par[3 + k]);
@@ -1322,6 +1323,25 @@ int skb_sdf_add_grid(skb_sdf *s, const double pos[3], const double rot[9], const
         if (!(en && en[0] == '0') && cell_bytes <= (size_t)(max_mb * 1048576.0)) {
             if (cudaMalloc(&h.dev_cells, cell_bytes) == cudaSuccess) {
                 if (launch_expand_cells(h.dev_grid, h.grid_is_f64, dims, h.dev_cells) != 0) { cudaFree(h.dev_cells); h.dev_cells = nullptr; }
+                // fp32 packs are also reachable as a linear texture of float4 texels (two per cell): the step kernel's voxel
+                // lookups then travel the TEX pipe of the L1 instead of the LSU data pipe its shared-memory traffic saturates
+                const char *tx = getenv("SKB_GRID_TEX");
+                if (h.dev_cells && !h.grid_is_f64 && !(tx && tx[0] == '0') && 2 * n_cells <= (size_t)1 << 27) {
+                    cudaResourceDesc rd;
+                    memset(&rd, 0, sizeof(rd));
+                    rd.resType = cudaResourceTypeLinear;
+                    rd.res.linear.devPtr = h.dev_cells;
+                    rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+                    rd.res.linear.sizeInBytes = cell_bytes;
+                    cudaTextureDesc td;
+                    memset(&td, 0, sizeof(td));
+                    td.readMode = cudaReadModeElementType;
+                    td.filterMode = cudaFilterModePoint;
+                    td.addressMode[0] = cudaAddressModeClamp;
+                    cudaTextureObject_t tex = 0;
+                    if (cudaCreateTextureObject(&tex, &rd, &td, nullptr) == cudaSuccess) h.cells_tex = (unsigned long long)tex;
+                    else cudaGetLastError();
+                }
             } else {
                 h.dev_cells = nullptr;
                 cudaGetLastError();
@@ -1340,7 +1360,11 @@ int skb_sdf_num_prims(const skb_sdf *s, int32_t *out) {
 
 void skb_sdf_destroy(skb_sdf *s) {
     if (!s) return;
-    for (auto &h : s->prims) { if (h.dev_grid) cudaFree(h.dev_grid); if (h.dev_cells) cudaFree(h.dev_cells); }
+    for (auto &h : s->prims) {
+        if (h.cells_tex) cudaDestroyTextureObject((cudaTextureObject_t)h.cells_tex);
+        if (h.dev_grid) cudaFree(h.dev_grid);
+        if (h.dev_cells) cudaFree(h.dev_cells);
+    }
     if (s->dev_f32) cudaFree(s->dev_f32);
     if (s->dev_f64) cudaFree(s->dev_f64);
     delete s;

@@ -68,6 +68,7 @@ struct DevPrim {
     const void *grid;    // device pointer (float or double values), C order [nx][ny][nz]
     const void *cells;   // device pointer or NULL: per-cell polynomial packs [(nx-1)][(ny-1)][(nz-1)][8]
                          // {a0 .. a7} of trilinear_poly (skb_device.cuh), same value type as `grid`
+    unsigned long long cells_tex;   // cudaTextureObject_t over `cells` as float4 texels (fp32 packs only), or 0
 };
 enum { PRIM_BOX = 0, PRIM_CYLINDER = 1, PRIM_SPHERE = 2, PRIM_GRID = 3 };
 enum { PF_IDENTITY = 1, PF_GRID_F64 = 2, PF_GRID_CELLS = 4 };
@@ -94,6 +95,7 @@ struct skb_host_prim {
     double pos[3], rot[9], par[8];
     void *dev_grid = nullptr;
     void *dev_cells = nullptr;       // per-cell polynomial packs (one 32/64-byte gather per lookup), may be NULL
+    unsigned long long cells_tex = 0;   // texture object over the fp32 packs (two float4 fetches per lookup on the TEX pipe), or 0
     int32_t grid_is_f64 = 0;
     size_t grid_bytes = 0;
 };

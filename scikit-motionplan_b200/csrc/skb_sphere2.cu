@@ -56,6 +56,7 @@ struct GridFast {
     unsigned sy, sz;           // cells per x step = (ny - 1)(nz - 1) is sy * sz; sy = ny - 1, sz = nz - 1
     float fill;
     const float *cells;
+    unsigned long long tex;    // texture object over `cells` (float4 texels), or 0: plain 32-byte global loads
 };
 
 template <typename T>
@@ -114,7 +115,11 @@ __device__ __forceinline__ float s2_grid_fast(const GridFast &gr, float px, floa
     const float fx = ux - float(ix), fy = uy - float(iy), fz = uz - float(iz);
     const unsigned cell = ((unsigned)ix * gr.sy + (unsigned)iy) * gr.sz + (unsigned)iz;
     float a[8], hx, hy, hz;
-    ldg_cell(gr.cells + (size_t)cell * 8, a);
+    if (gr.tex != 0ull) {       // (warp-uniform) two 16-byte texel fetches: TEX pipe instead of the LSU data pipe
+        const float4 lo = tex1Dfetch<float4>((cudaTextureObject_t)gr.tex, (int)(2u * cell));
+        const float4 hi = tex1Dfetch<float4>((cudaTextureObject_t)gr.tex, (int)(2u * cell + 1u));
+        a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+    } else ldg_cell(gr.cells + (size_t)cell * 8, a);
     const float val = trilinear_poly<float>(a, fx, fy, fz, hx, hy, hz);
     gx = inside ? hx * gr.ix_ : 0.f;
     gy = inside ? hy * gr.iy_ : 0.f;
@@ -666,6 +671,7 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
         g.sy = (unsigned)(pr.dims[1] - 1); g.sz = (unsigned)(pr.dims[2] - 1);
         g.fill = pr.par[6];
         g.cells = reinterpret_cast<const float *>(pr.cells);
+        g.tex = pr.cells_tex;
     }
     const int D = p->D, R = sp->rows, NP = (D + 1) / 2;
     prm.D = D; prm.NP = NP; prm.R = R; prm.n_steps = (int)sp->steps.size(); prm.n_levels = sp->n_levels; prm.n_cen = sp->n_cen;

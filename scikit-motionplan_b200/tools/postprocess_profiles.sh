@@ -16,9 +16,9 @@ for m in cfg3:collfree_cfg3 cfg2_all:pairwise_cfg2 cfg4_409600:collfree_cfg4 cfg
          cfg5_self_valid:pairwise_jaxon_validity cfg5_pose:pose cfg5_com:com; do
     python $T/ncu_summary.py $O/prof_${m%%:*}_raw.csv > $P/${TAG}_${m##*:}_ncu_full.json
 done
-python $T/ncu_sections.py $O/prof_cfg3_src.csv $W/s2.sass fLi1ELi2ELi2EjLb0ELb1ELi8E 1250000 > $P/${TAG}_collfree_cfg3_sections.txt
-python $T/ncu_sections.py $O/prof_cfg4_409600_src.csv $W/s2.sass fLi1ELi1ELi1EjLb0ELb1ELi4E 409600 > $P/${TAG}_collfree_cfg4_sections.txt
-python $T/ncu_sections.py $O/prof_cfg5_env_all_src.csv $W/s2.sass fLi1ELi0ELi1EyLb0ELb1ELi32E 1000000 > $P/${TAG}_collfree_jaxon_env_sections.txt
+python $T/ncu_sections.py $O/prof_cfg3_src.csv $W/s2.sass fLi1ELi2ELi2EjLb0ELb1ELi8ELb0EE 1250000 > $P/${TAG}_collfree_cfg3_sections.txt
+python $T/ncu_sections.py $O/prof_cfg4_409600_src.csv $W/s2.sass fLi1ELi1ELi1EjLb0ELb1ELi4ELb0EE 409600 > $P/${TAG}_collfree_cfg4_sections.txt
+python $T/ncu_sections.py $O/prof_cfg5_env_all_src.csv $W/s2.sass fLi1ELi0ELi1EyLb0ELb1ELi32ELb0EE 1000000 > $P/${TAG}_collfree_jaxon_env_sections.txt
 python - "$TAG" <<'PY'
 import json, sys
 tag = sys.argv[1]
