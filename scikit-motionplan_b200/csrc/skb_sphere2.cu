@@ -39,6 +39,15 @@
 
 namespace skb {
 
+#ifndef SKB_S2_PIPE
+#define SKB_S2_PIPE 1           // 0: voxel lookups issued and consumed inside the same configuration (round-1 behaviour)
+#endif
+#ifndef SKB_S2_GRID_BLOCKS
+#define SKB_S2_GRID_BLOCKS 3    // launch bounds of the fp32 voxel-grid all-mode kernels
+#endif
+#ifndef SKB_S2_GRID_THREADS
+#define SKB_S2_GRID_THREADS 256
+#endif
 #ifndef SKB_S2_THREADS
 #define SKB_S2_THREADS 256      // max threads per CTA
 #define SKB_S2_BLOCKS 3         // min CTAs per SM (register cap = 65536 / product); the fp32 grid all-mode kernels take 4:
@@ -108,23 +117,40 @@ enum { SDF_UNION = 0, SDF_SINGLE = 1, SDF_GRID_FAST = 2 };
 // Branch-free: the cell index is clamped and the gather always issued, the fill value / zero gradient are selected
 // afterwards -- so the two gathers of a lane's two rows are in flight together instead of being serialised by a
 // divergent branch.  Value and gradient are Horner evaluations of the cell's polynomial pack (trilinear_poly).
-__device__ __forceinline__ float s2_grid_fast(const GridFast &gr, float px, float py, float pz, float &gx, float &gy, float &gz) {
+// The lookup is split in two so that the full-output kernel can issue the NEXT configuration's lookups before it runs
+// the current configuration's column loop (the fetch latency then hides behind ~250 issue slots of FFMA2 work).
+struct GridPend {              // a lookup in flight: the cell's pack, the in-cell coordinates, the inside flag
+    float a[8];
+    float fx, fy, fz;
+    bool inside;
+};
+__device__ __forceinline__ void tex_cell(unsigned long long tex, unsigned texel, float &x, float &y, float &z, float &w) {
+    // volatile: stays where it is written, ahead of the column loop, instead of being sunk to its first use
+    asm volatile("tex.1d.v4.f32.s32 {%0,%1,%2,%3}, [%4, {%5}];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "l"(tex), "r"(texel));
+}
+__device__ __forceinline__ void s2_grid_issue(const GridFast &gr, float px, float py, float pz, GridPend &pd) {
     const float ux = (px - gr.ox) * gr.ix_, uy = (py - gr.oy) * gr.iy_, uz = (pz - gr.oz) * gr.iz_;
-    const bool inside = ux >= 0.f && ux <= gr.tx && uy >= 0.f && uy <= gr.ty && uz >= 0.f && uz <= gr.tz;
+    pd.inside = ux >= 0.f && ux <= gr.tx && uy >= 0.f && uy <= gr.ty && uz >= 0.f && uz <= gr.tz;
     const int ix = max(0, min((int)floorf(ux), gr.mx)), iy = max(0, min((int)floorf(uy), gr.my)), iz = max(0, min((int)floorf(uz), gr.mz));
-    const float fx = ux - float(ix), fy = uy - float(iy), fz = uz - float(iz);
+    pd.fx = ux - float(ix); pd.fy = uy - float(iy); pd.fz = uz - float(iz);
     const unsigned cell = ((unsigned)ix * gr.sy + (unsigned)iy) * gr.sz + (unsigned)iz;
-    float a[8], hx, hy, hz;
     if (gr.tex != 0ull) {       // (warp-uniform) two 16-byte texel fetches: TEX pipe instead of the LSU data pipe
-        const float4 lo = tex1Dfetch<float4>((cudaTextureObject_t)gr.tex, (int)(2u * cell));
-        const float4 hi = tex1Dfetch<float4>((cudaTextureObject_t)gr.tex, (int)(2u * cell + 1u));
-        a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
-    } else ldg_cell(gr.cells + (size_t)cell * 8, a);
-    const float val = trilinear_poly<float>(a, fx, fy, fz, hx, hy, hz);
-    gx = inside ? hx * gr.ix_ : 0.f;
-    gy = inside ? hy * gr.iy_ : 0.f;
-    gz = inside ? hz * gr.iz_ : 0.f;
-    return inside ? val : gr.fill;
+        tex_cell(gr.tex, 2u * cell, pd.a[0], pd.a[1], pd.a[2], pd.a[3]);
+        tex_cell(gr.tex, 2u * cell + 1u, pd.a[4], pd.a[5], pd.a[6], pd.a[7]);
+    } else ldg_cell(gr.cells + (size_t)cell * 8, pd.a);
+}
+__device__ __forceinline__ float s2_grid_finish(const GridFast &gr, const GridPend &pd, float &gx, float &gy, float &gz) {
+    float hx, hy, hz;
+    const float val = trilinear_poly<float>(pd.a, pd.fx, pd.fy, pd.fz, hx, hy, hz);
+    gx = pd.inside ? hx * gr.ix_ : 0.f;
+    gy = pd.inside ? hy * gr.iy_ : 0.f;
+    gz = pd.inside ? hz * gr.iz_ : 0.f;
+    return pd.inside ? val : gr.fill;
+}
+__device__ __forceinline__ float s2_grid_fast(const GridFast &gr, float px, float py, float pz, float &gx, float &gy, float &gz) {
+    GridPend pd;
+    s2_grid_issue(gr, px, py, pz, pd);
+    return s2_grid_finish(gr, pd, gx, gy, gz);
 }
 
 // two adjacent columns of a Jacobian row: packed f32x2 arithmetic for float, two scalar chains for double -- the same
@@ -151,6 +177,7 @@ __device__ __forceinline__ double grid_fast_or_generic(const S2Params<double> &p
     return sdf_prim_world<double>(prm.prim0, px, py, pz, gx, gy, gz);
 }
 
+template <typename T> struct PendRowT { GridPend g; T px, py, pz; };   // a row whose voxel lookup is in flight
 template <typename T, typename MaskT> struct RowState {   // what phase 2 keeps of one output row
     T gx, gy, gz, mx, my, mz;
     MaskT pm, mm;
@@ -166,11 +193,14 @@ template <typename T, typename MaskT> struct RowState {   // what phase 2 keeps 
 // layout the rows of a step are consecutive addresses of ONE column, i.e. lane-per-row stores are coalesced as they are:
 // no staging block, no bulk store, one 128-byte store per (column, half).
 template <typename T, int KIND, int SDFK, int VW, typename MaskT, bool RED, bool JAC, int NPMAX, bool CSC = false>
-__global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIND_COLLFREE && SDFK == SDF_GRID_FAST && JAC && !RED) ? 4 : SKB_S2_BLOCKS) s2_kernel(const __grid_constant__ S2Params<T> prm) {
+__global__ void __launch_bounds__((sizeof(T) == 4 && KIND == KIND_COLLFREE && SDFK == SDF_GRID_FAST && JAC && !RED) ? SKB_S2_GRID_THREADS : SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIND_COLLFREE && SDFK == SDF_GRID_FAST && JAC && !RED) ? SKB_S2_GRID_BLOCKS : SKB_S2_BLOCKS) s2_kernel(const __grid_constant__ S2Params<T> prm) {
     using V4 = Vec4<T>;
     using Rl = Real<T>;
     using P2 = Pair2<T>;
     using V2 = typename P2::type;
+    using PendRow = PendRowT<T>;
+    // full-output fp32 voxel-grid launches run the lookups one configuration ahead of the column loop
+    constexpr bool PIPE = KIND == KIND_COLLFREE && SDFK == SDF_GRID_FAST && !RED && sizeof(T) == 4 && SKB_S2_PIPE;
     extern __shared__ __align__(16) unsigned char smem[];
     int32_t *sI = reinterpret_cast<int32_t *>(smem);
     T *sF = reinterpret_cast<T *>(smem + prm.off_F);
@@ -344,6 +374,29 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
                 if (KIND == KIND_COLLFREE) { A0 = tabA[slot * 32 + lane]; A1 = tabA[(slot + (cntB > 0 ? 1 : 0)) * 32 + lane]; }
                 slot += cntB > 0 ? 2 : 1;
 
+                // grid lookups split into issue / finish (PIPE): the same arithmetic as front(), in the same order
+                auto front_issue = [&](const int c, const V4 &A, const int4 &B, PendRow &pr) {
+                    if constexpr (PIPE) {
+                        const V4 *fr = reinterpret_cast<const V4 *>(wframes + c * fstride);
+                        const V4 f0 = fr[3 * B.x], f1 = fr[3 * B.x + 1], f2 = fr[3 * B.x + 2];
+                        pr.px = f0.w + f0.x * A.x + f0.y * A.y + f0.z * A.z;
+                        pr.py = f1.w + f1.x * A.x + f1.y * A.y + f1.z * A.z;
+                        pr.pz = f2.w + f2.x * A.x + f2.y * A.y + f2.z * A.z;
+                        s2_grid_issue(prm.grid, pr.px, pr.py, pr.pz, pr.g);
+                    }
+                };
+                auto front_finish = [&](const PendRow &pr, const V4 &A, const int4 &B, RowState<T, MaskT> &rs) -> T {
+                    T val = T(0);
+                    if constexpr (PIPE) {
+                        const T d = s2_grid_finish(prm.grid, pr.g, rs.gx, rs.gy, rs.gz);
+                        val = d - A.w - prm.margin;
+                        if (JAC) wrench_moment<T>(pr.px, pr.py, pr.pz, rs.gx, rs.gy, rs.gz, rs.mx, rs.my, rs.mz);
+                        rs.pm = sizeof(MaskT) == 8 ? (MaskT)(((unsigned long long)(unsigned)B.z << 32) | (unsigned)B.y) : (MaskT)(unsigned)B.y;
+                        rs.mm = 0;
+                    }
+                    return val;
+                };
+
                 // twist pair x wrench for the columns (col, col + 1), masked / signed
                 auto contract = [&](const V4 &t0, const V4 &t1, const V4 &t2, const RowState<T, MaskT> &rs, const int col) -> V2 {
                     V2 a = P2::mul(P2::make(t0.x, t0.y), rs.mx);
@@ -364,15 +417,26 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
                     return a;
                 };
 
-                auto body = [&](auto has_b, const int c) {
+                auto body = [&](auto has_b, const int c, PendRow &pa, PendRow &pb) {
                     constexpr bool HAS_B = decltype(has_b)::value;
                     int tw_off = c * tstride;                      // opaque: one address register for the whole unrolled loop
                     asm volatile("" : "+r"(tw_off));
                     const T *tw = wtw + tw_off;
                     RowState<T, MaskT> ra, rb;
-                    const T va = front(c, A0, B0, slotA, ra);
-                    T vb = T(0);
-                    if (HAS_B) vb = front(c, A1, B1, slotB, rb);
+                    T va, vb = T(0);
+                    if constexpr (PIPE) {
+                        // this configuration's lookups were issued one configuration ago; the next one's go out now and stay
+                        // in flight during the column loop below
+                        va = front_finish(pa, A0, B0, ra);
+                        if (HAS_B) vb = front_finish(pb, A1, B1, rb);
+                        if (c + 1 < g_live) {
+                            front_issue(c + 1, A0, B0, pa);
+                            if (HAS_B) front_issue(c + 1, A1, B1, pb);
+                        }
+                    } else {
+                        va = front(c, A0, B0, slotA, ra);
+                        if (HAS_B) vb = front(c, A1, B1, slotB, rb);
+                    }
                     if (prm.out_vals != nullptr) {
                         T *gv = step_vals + (unsigned)(c * R);
                         if (lane < cntA) st_stream(gv, va);
@@ -467,8 +531,13 @@ __global__ void __launch_bounds__(SKB_S2_THREADS, (sizeof(T) == 4 && KIND == KIN
                     for (int i = lane; i < len16; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     __syncwarp();
                 }
-                if (cntB > 0) for (int c = 0; c < g_live; ++c) body(std::true_type{}, c);
-                else          for (int c = 0; c < g_live; ++c) body(std::false_type{}, c);
+                PendRow pa, pb;
+                if constexpr (PIPE) {
+                    front_issue(0, A0, B0, pa);
+                    if (cntB > 0) front_issue(0, A1, B1, pb);
+                }
+                if (cntB > 0) for (int c = 0; c < g_live; ++c) body(std::true_type{}, c, pa, pb);
+                else          for (int c = 0; c < g_live; ++c) body(std::false_type{}, c, pa, pb);
             }
         } else if (KIND == KIND_PAIRWISE) {
             // ---- per-configuration reduction over the pairs, lean form: an 8-byte table entry and two centre loads per
