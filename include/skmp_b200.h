@@ -194,6 +194,11 @@ SKB_API int skb_segment_all(const uint8_t *valid_dev, const int64_t *offsets_dev
 /* Measurement aid: FMA-pipe peak of the current device in TFLOP/s, the roofline denominator of the
  * compute-bound modes (closest row, validity bytes).  kind 0: fp32 FFMA, 1: packed fma.rn.f32x2, 2: fp64 DFMA. */
 SKB_API int skb_fma_peak(int32_t kind, int32_t iters, double *tflops_out);
+/* Measurement aid: GB/s a write-only stream of `bytes` reaches on the current device -- the practical ceiling of the
+ * write-dominated collision kernels (MEASURED_PEAKS.json's HBM figure is a read + write copy).  kind 0: 16-byte streaming
+ * stores from registers; kind 1: the step kernel's store path, `block_bytes` blocks staged in shared memory and shipped by
+ * cp.async.bulk (TMA 1-D) with the L2 evict-first policy.  No reference counterpart. */
+SKB_API int skb_store_peak(int32_t kind, int64_t bytes, int32_t block_bytes, double *gbs_out);
 
 /* ---------------------------------------------------------------- hot path (host pointers)
  * Same semantics with host buffers: what a numpy caller of the reference sees.  Chunked

@@ -366,13 +366,23 @@ template <typename T, bool WITH_JAC, bool PAIR>
 __device__ __forceinline__ void fk_phase(const int lane, const int G, const int logG, const int slots3, const int g_live,
                                          const int D, const int n_levels, const int4 *lvrec, const int32_t *levelI,
                                          const Vec4<T> *nodeF, const T *wq, const T *wsc,
-                                         T *wframes, const int fstride, T *wtw, const int tstride) {
+                                         T *wframes, const int fstride, T *wtw, const int tstride,
+                                         const unsigned *lanemap = nullptr) {
     using V4 = Vec4<T>;
     constexpr uint32_t ES = sizeof(T), VS = 4 * sizeof(T);     // element / 4-vector size in bytes
-    const int row = lane % 3, t = lane / 3;
-    const int cfg = t & (G - 1), slot = t >> logG;
-    const bool act = slot < slots3;
+    int row = lane % 3, t = lane / 3;
+    int cfg = t & (G - 1), slot = t >> logG;
     int src1 = lane - row + (row == 2 ? 0 : row + 1), src2 = lane - row + (row == 0 ? 2 : row - 1);
+    // Optional lane permutation (fk_lane_map, host): WHICH lane carries which (row, configuration) of a node is free, and the
+    // eight lanes of one 128-bit shared-memory pass should hit eight different 16-byte bank groups of the frame blocks --
+    // the plain order does not for most frame strides (PR2 dual arm, 45 quads: 8 wavefronts per parent-row load against 4).
+    // Entry: row | cfg << 2 | slot << 5 | lane of row + 1 << 8 | lane of row + 2 << 16.
+    if (lanemap != nullptr) {
+        const unsigned m = lanemap[lane];
+        row = (int)(m & 3u); cfg = (int)((m >> 2) & 7u); slot = (int)((m >> 5) & 7u);
+        src1 = (int)((m >> 8) & 31u); src2 = (int)((m >> 16) & 31u);
+    }
+    const bool act = slot < slots3;
     const int ccfg = min(cfg, g_live - 1);          // dead configurations of a ragged last tile recompute a live one
     // lane-constant shared-window addresses, made opaque so that each is formed once per tile and held in a register
     uint32_t a_lv = smem_addr(lvrec), a_lev = smem_addr(levelI), a_nodeF = smem_addr(nodeF);

@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <iterator>
 #include <map>
 #include <mutex>
@@ -92,6 +93,8 @@ struct S2Params {
     int copy_vec;                                                     // 1: every step block is 16-byte aligned in out_jac
     // warp-uniform data of the hot loop lives in the kernel parameters (constant bank -> uniform datapath)
     skb_s2_step steps[S2_MAX_STEPS];
+    unsigned lanemap[32];                                             // FK walk: lane -> (row, configuration, slot), see fk_lane_map
+    int use_lanemap;
     DevPrim<T> prim0;
     GridFast grid;
 };
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__((sizeof(T) == 4 && KIND == KIND_COLLFREE && SD
 
         // ------------------------------------------------------------ phase 1: frames + twists
         fk_phase<T, JAC, true>(lane, G, logG, prm.slots3, g_live, D, n_levels, lvrec, levelI, nodeF, wq, wsc,
-                                    wframes, fstride, wtw, tstride);
+                                    wframes, fstride, wtw, tstride, prm.use_lanemap ? prm.lanemap : nullptr);
 
         // ------------------------------------------------------------ phase 1b: sphere centres (pairwise)
         if (KIND == KIND_PAIRWISE) {
@@ -696,6 +699,86 @@ static int carve_kb(size_t bytes_per_sm) {
     return 1 << 20;
 }
 
+// Lane order of the FK walk.  Lane p of a slot's 3 G lanes may carry any (configuration, row) of the slot's node; its frame
+// accesses go to quad  cfg * fsq + 3 node + row  (16-byte units) of the warp's frame area, and a 128-bit shared-memory access
+// is processed eight lanes at a time: the order is chosen so that the (cfg * fsq + row) mod 8 of the lanes of one slot inside
+// one pass are all different (depth-first search, a few hundred nodes at most; the plain order when none exists).
+// Returns false when the plain order is already conflict-free or no better order was found.
+static bool fk_lane_map_search(int G, int fsq, unsigned map[32]);
+static bool fk_lane_map(int G, int fsq, unsigned map[32]) {          // memoised: a launch pays a map lookup
+    struct Entry { bool ok; unsigned map[32]; };
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, Entry> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find({G, fsq});
+    if (it == cache.end()) {
+        Entry e;
+        memset(&e, 0, sizeof(e));
+        e.ok = fk_lane_map_search(G, fsq, e.map);
+        it = cache.emplace(std::make_pair(G, fsq), e).first;
+    }
+    if (it->second.ok) memcpy(map, it->second.map, sizeof(it->second.map));
+    return it->second.ok;
+}
+static bool fk_lane_map_search(int G, int fsq, unsigned map[32]) {
+    const int per = 3 * G, slots3 = 32 / per;
+    int lane_cfg[32], lane_row[32], lane_slot[32];
+    for (int l = 0; l < 32; ++l) { lane_row[l] = l % 3; lane_cfg[l] = (l / 3) % G; lane_slot[l] = (l / 3) / G; }
+    auto conflicts = [&](const int *cfgs, const int *rows) {
+        int bad = 0;
+        for (int g0 = 0; g0 < 32; g0 += 8)
+            for (int s = 0; s < slots3; ++s) {
+                int seen = 0;
+                for (int l = g0; l < g0 + 8; ++l) {
+                    if (l >= per * slots3 || l / per != s) continue;
+                    const int o = (cfgs[l] * fsq + rows[l]) & 7;
+                    if (seen & (1 << o)) ++bad;
+                    seen |= 1 << o;
+                }
+            }
+        return bad;
+    };
+    const int base_bad = conflicts(lane_cfg, lane_row);
+    if (base_bad == 0) return false;
+    int best_cfg[32], best_row[32];
+    bool found = true;
+    memcpy(best_cfg, lane_cfg, sizeof(best_cfg));
+    memcpy(best_row, lane_row, sizeof(best_row));
+    for (int s = 0; s < slots3 && found; ++s) {
+        const int l0 = s * per;
+        int used = 0, order[24], budget = 200000;
+        // depth-first: position i (lane l0 + i) takes an unused (cfg, row) whose bank group is free in its 8-lane pass
+        std::function<bool(int, int)> dfs = [&](int i, int seen) -> bool {
+            if (i == per) return true;
+            if (--budget < 0) return false;
+            if (((l0 + i) & 7) == 0) seen = 0;                       // a new pass starts
+            for (int k = 0; k < per; ++k) {
+                if (used & (1 << k)) continue;
+                const int o = ((k / 3) * fsq + (k % 3)) & 7;
+                if (seen & (1 << o)) continue;
+                used |= 1 << k; order[i] = k;
+                if (dfs(i + 1, seen | (1 << o))) return true;
+                used &= ~(1 << k);
+            }
+            return false;
+        };
+        if (!dfs(0, 0)) { found = false; break; }
+        for (int i = 0; i < per; ++i) { best_cfg[l0 + i] = order[i] / 3; best_row[l0 + i] = order[i] % 3; }
+    }
+    if (!found || conflicts(best_cfg, best_row) >= base_bad) return false;
+    for (int l = 0; l < 32; ++l) {
+        if (l >= per * slots3) { map[l] = 7u << 5; continue; }      // idle lane: slot 7 >= slots3
+        int s1 = l, s2 = l;
+        for (int m = 0; m < per * slots3; ++m)
+            if (lane_slot[m] == lane_slot[l] && best_cfg[m] == best_cfg[l]) {
+                if (best_row[m] == (best_row[l] + 1) % 3) s1 = m;
+                if (best_row[m] == (best_row[l] + 2) % 3) s2 = m;
+            }
+        map[l] = (unsigned)best_row[l] | (unsigned)best_cfg[l] << 2 | (unsigned)lane_slot[l] << 5 | (unsigned)s1 << 8 | (unsigned)s2 << 16;
+    }
+    return true;
+}
+
 template <typename T>
 struct S2Launch {
     S2Params<T> prm;
@@ -800,6 +883,7 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
     // N = 1 call pays a map lookup.
     static std::mutex shape_mu;
     static std::map<std::tuple<unsigned long long, const void *, int, int, int, int>, std::tuple<int, int, int, int, double>> shape_cache;
+    static const bool lanemap_on = !(getenv("SKB_S2_LANEMAP") && getenv("SKB_S2_LANEMAP")[0] == '0');
     static const int env_g = getenv("SKB_S2_G") ? atoi(getenv("SKB_S2_G")) : 0, env_w = getenv("SKB_S2_WARPS") ? atoi(getenv("SKB_S2_WARPS")) : 0;
     const int want_g = force_g > 0 ? force_g : (p->tune_chunk > 0 ? p->tune_chunk : env_g);      // tuning knobs
     const int want_w = force_w > 0 ? force_w : (p->tune_warps > 0 ? p->tune_warps : env_w);
@@ -819,6 +903,7 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
             while ((1 << prm.logG) < L.G) ++prm.logG;
             prm.slots3 = 32 / (3 * L.G);
             prm.n_tiles = (N + L.G - 1) / L.G;
+            prm.use_lanemap = (sizeof(T) == 4 && lanemap_on && fk_lane_map(L.G, L.fstride / 4, prm.lanemap)) ? 1 : 0;
             return 0;
         }
     }
@@ -868,6 +953,7 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
     while ((1 << prm.logG) < L.G) ++prm.logG;
     prm.slots3 = 32 / (3 * L.G);
     prm.n_tiles = (N + L.G - 1) / L.G;
+    prm.use_lanemap = (sizeof(T) == 4 && lanemap_on && fk_lane_map(L.G, L.fstride / 4, prm.lanemap)) ? 1 : 0;
     return 0;
 }
 

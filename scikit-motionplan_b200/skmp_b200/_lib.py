@@ -64,6 +64,7 @@ def _declare(lib):
         "skb_edge_samples": ([vp, vp, vp, i64, i32, i32, vp, i32, vp, vp], C.c_int),
         "skb_segment_all": ([vp, vp, i64, vp, vp], C.c_int),
         "skb_fma_peak": ([i32, i32, vp], C.c_int),
+        "skb_store_peak": ([i32, i64, i32, vp], C.c_int),
         "skb_lm_step": ([i32, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp], C.c_int),
         "skb_fk_host": ([vp, i32, vp, i64, i32, vp, vp], C.c_int),
         "skb_collfree_host": ([vp, vp, i32, vp, i64, dbl, i32, vp, vp, vp], C.c_int),

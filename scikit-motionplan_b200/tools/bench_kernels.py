@@ -215,6 +215,14 @@ def main():
             best = max(best, t.value)
         fma[key] = best
     print(json.dumps({"workload": "fma_peak", "desc": "FMA-pipe micro-benchmark (skb_fma_peak), TFLOP/s", **fma}), flush=True)
+    # write-only stream ceiling (skb_store_peak): plain streaming stores, and the step kernel's shared memory -> TMA bulk
+    # store path at its own block sizes (cfg3: 3 584-byte steps; cfg2: 2 048; cfg4: 1 792)
+    st = {}
+    for kind, blk, key in ((0, 0, "stg_v4"), (1, 3584, "bulk_3584"), (1, 2048, "bulk_2048"), (1, 1792, "bulk_1792"), (1, 8192, "bulk_8192")):
+        t = ctypes.c_double(0.0)
+        _lib.check(_lib.lib().skb_store_peak(kind, 8 << 30, blk, ctypes.byref(t)))
+        st[key] = t.value
+    print(json.dumps({"workload": "store_peak", "desc": "write-only stream of 8 GiB (skb_store_peak), GB/s", "hbm_copy_peak_gbs": peak, **st}), flush=True)
     for name in names:
         fn, n, bpc, desc, *rest = W[name]()
         mean_ms, min_ms, _ = timed(fn, args.reps)
