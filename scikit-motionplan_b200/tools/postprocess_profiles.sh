@@ -9,6 +9,8 @@ W=$(mktemp -d)
 (cd $W && cuobjdump -xelf all $OLDPWD/$LIB > /dev/null && nvdisasm -g -c skb_sphere2.sm_100a.cubin > s2.sass)
 cp $O/prof_bench.json $P/${TAG}_bench.json
 cp $O/prof_bench_reference_arm.json $P/${TAG}_bench_reference_arm.json
+[ -s $O/prof_bench_10m.json ] && cp $O/prof_bench_10m.json $P/${TAG}_bench_10m.json
+for w in cfg2 cfg4 cfg5; do [ -s $O/prof_bench_$w.json ] && cp $O/prof_bench_$w.json $P/${TAG}_bench_$w.json; done
 grep -v '^\[skb\]' $O/prof_kernels.jsonl > $P/${TAG}_kernels.jsonl
 cp $O/prof_launches.csv $P/${TAG}_launches.csv
 [ -s $O/prof_ik.json ] && cp $O/prof_ik.json $P/${TAG}_ik.json

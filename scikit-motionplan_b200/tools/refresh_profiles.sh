@@ -9,6 +9,9 @@ BK="python scikit-motionplan_b200/tools/bench_kernels.py"
 # 1. contract bench line and the reference arm, no profiler
 python bench.py --steps 10 --warmup 3 > $O/prof_bench.json 2> $O/prof_bench.err
 python bench.py --impl reference --steps 2 --warmup 1 > $O/prof_bench_reference_arm.json 2> $O/prof_bench_reference_arm.err
+# the named 10 M configurations on ONE GPU (92 GB of outputs), and the other named robots with their CPU baselines
+python bench.py --configs-per-gpu 10000000 --steps 5 --warmup 3 --no-cpu-baseline > $O/prof_bench_10m.json 2> $O/prof_bench_10m.err
+for w in cfg2 cfg4 cfg5; do python bench.py --workload $w --steps 10 --warmup 3 > $O/prof_bench_$w.json 2> $O/prof_bench_$w.err; done
 $BK --reps 8 > $O/prof_kernels.jsonl 2> $O/prof_kernels.err
 # 2. launch list of the bench command
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/prof_launches.csv \

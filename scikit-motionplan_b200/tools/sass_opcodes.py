@@ -3,7 +3,8 @@
     python scikit-motionplan_b200/tools/sass_opcodes.py > profiles/r2_sass_opcodes.txt
 
 For every kernel: target architecture, registers / spills from ptxas, the number of SASS instructions, the counts of the
-opcodes that carry the Blackwell-specific claims of DESIGN.md (packed fp32x2 arithmetic FFMA2 / FMUL2, 1-D TMA bulk stores
+opcodes that carry the Blackwell-specific claims of DESIGN.md (packed fp32x2 arithmetic FFMA2 / FMUL2, texture-pipe fetches TLD of the
+voxel cell packs, 1-D TMA bulk stores
 UBLKCP with the async-proxy fence, 256-bit global loads LDG.E.*.256 for the voxel cell packs, uniform-datapath branches,
 warp shuffles), and the 25 most frequent opcodes.
 """
@@ -30,7 +31,7 @@ KERNELS = [
     ("skb_sphere.o", "sphere_kernelIfLi0ELb1ELb0ELi1ELi2Ej", "KinematicsMap.map: sphere kernel, fp32, point features + Jacobian"),
     ("skb_com.o", "com_kernelIf", "COMStabilityConst: centre-of-mass kernel, fp32"),
 ]
-WATCH = ["FFMA2", "FMUL2", "FFMA", "UBLKCP", "FENCE", "LDG", "STG", "LDS", "STS", "SHFL", "MUFU", "BRA.U", "BRA", "CALL", "STL", "LDL", "DFMA"]
+WATCH = ["FFMA2", "FMUL2", "FFMA", "UBLKCP", "FENCE", "TLD", "TEX", "LDG", "STG", "LDS", "STS", "SHFL", "MUFU", "BRA.U", "BRA", "CALL", "STL", "LDL", "DFMA"]
 
 
 def functions(obj):
