@@ -6,6 +6,7 @@
   * the fallback kernels: lane-per-configuration ``tree_kernel`` / ``pairwise_kernel`` (SKB_KERNEL=tree; what robots with
     D > 64 or > 255 nodes get), the one-row-per-lane ``sphere_kernel`` for every collfree mode (SKB_KERNEL=sphere1) and voxel
     grids without cell packs (SKB_GRID_CELLS=0; what grids too large for the packs get)
+  * the two voxel-lookup paths of the step kernel (texture fetches / 256-bit global loads), bit for bit, on ragged tiles
   * the reference-held scene facts of tests/test_reference_pins.py, on the CUDA path.
 """
 import copy
@@ -291,6 +292,50 @@ def test_fallback_kernels(monkeypatch, env, dtype):
         rp, rjac = oracle.solve_fk(t3, q3, f3, jl3, b3, ROT[rt])
         ev, ej = pose_excess(pts.cpu().numpy(), jac.cpu().numpy(), rp, rjac, rt, dtype)
         assert ev <= 1.0 and ej <= 1.0
+
+
+# ------------------------------------------------------------------ voxel lookups: TEX pipe vs LDG.256
+@pytest.mark.parametrize("n", [1, 3, 501, 4099])
+def test_grid_lookup_paths_bit_identical(monkeypatch, n):
+    """The fp32 cell packs are read either by two texel fetches (default; the step kernel issues them one configuration
+    ahead of the column loop) or by one 256-bit global load (SKB_GRID_TEX=0, what grids beyond 2^27 texels get).  Both read
+    the same 32 bytes, so every mode returns the same bits -- on batch sizes that leave ragged last tiles (the look-ahead
+    must not run past the last live configuration of a tile) and on the dual-arm PR2 of BASELINE config 3."""
+    from skmp_b200.constraint import CollFreeConst
+    from skmp_b200.robot.pr2 import PR2Config
+    from skmp_b200.robot_model import PR2
+    from skmp_b200.sdf import Box, Cylinder, GridSDF, UnionSDF
+
+    pr2 = PR2(); pr2.reset_manip_pose()
+    rng = np.random.default_rng(7)
+    union = UnionSDF([Box([0.7, 0.5, 1.2], pos=[0.85, -0.2, 0.9]), Cylinder(0.15, 0.8)])
+    lb, ub, dims = np.array([-0.6, -1.5, 0.0]), np.array([1.5, 1.5, 2.0]), np.array([40, 56, 44])
+    spacing = (ub - lb) / (dims - 1)
+    axes = [lb[i] + spacing[i] * np.arange(dims[i]) for i in range(3)]
+    lattice = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, 3)
+    values = oracle.Sdf(union.primitives())(lattice).reshape(tuple(dims)).astype(np.float32)
+    colkin = PR2Config(control_arm="dual").get_collision_kin()
+    qs = dev(sample_q(colkin, n, rng), np.float32)
+    results = []
+    for tex in ("1", "0"):
+        monkeypatch.setenv("SKB_GRID_TEX", tex)              # read when the grid is uploaded (first use of the SDF object)
+        grid = GridSDF(values, lb, spacing, fill_value=2.5)
+        out = []
+        for closest in (False, True):
+            const = CollFreeConst(colkin, grid, pr2, only_closest_feature=closest)
+            v, j = const.evaluate(qs, True)
+            v2, _ = const.evaluate(qs, False)
+            out += [v.cpu().numpy(), j.cpu().numpy(), v2.cpu().numpy()]
+        out.append(CollFreeConst(colkin, grid, pr2).is_valid_batch(qs).cpu().numpy())
+        results.append(out)
+    for a, b in zip(*results):
+        assert a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+    # and the look-ahead changes nothing against the oracle: first and last configuration of the batch
+    tree, feat, jl, base = oracle_args(colkin)
+    pick = np.unique([0, n - 1])
+    rv, rj = oracle.collfree(tree, qs.cpu().numpy().astype(np.float64)[pick], feat, jl, oracle.Sdf(grid.primitives()),
+                             colkin.get_radius_list())
+    assert err(results[0][0][pick], rv) < TOL[np.float32]
 
 
 # ------------------------------------------------------------------ reference-held scene facts on the CUDA path
