@@ -133,9 +133,13 @@ __device__ __forceinline__ void tex_cell(unsigned long long tex, unsigned texel,
 }
 __device__ __forceinline__ void s2_grid_issue(const GridFast &gr, float px, float py, float pz, GridPend &pd) {
     const float ux = (px - gr.ox) * gr.ix_, uy = (py - gr.oy) * gr.iy_, uz = (pz - gr.oz) * gr.iz_;
-    pd.inside = ux >= 0.f && ux <= gr.tx && uy >= 0.f && uy <= gr.ty && uz >= 0.f && uz <= gr.tz;
     const int ix = max(0, min((int)floorf(ux), gr.mx)), iy = max(0, min((int)floorf(uy), gr.my)), iz = max(0, min((int)floorf(uz), gr.mz));
     pd.fx = ux - float(ix); pd.fy = uy - float(iy); pd.fz = uz - float(iz);
+    // inside the sample box  <=>  0 <= u <= dims - 1 on every axis  <=>  the in-cell coordinate of the CLAMPED cell lies in
+    // [0, 1] (u - cell is exact there): two 3-input min / max and two compares instead of six compares whose short-circuit
+    // form ptxas turned into predicated re-evaluations of u.  A NaN coordinate is decided by the other two axes and then
+    // yields NaN from the polynomial, as numpy's bounds test does.
+    pd.inside = fminf(pd.fx, fminf(pd.fy, pd.fz)) >= 0.f && fmaxf(pd.fx, fmaxf(pd.fy, pd.fz)) <= 1.f;
     const unsigned cell = ((unsigned)ix * gr.sy + (unsigned)iy) * gr.sz + (unsigned)iz;
     if (gr.tex != 0ull) {       // (warp-uniform) two 16-byte texel fetches: TEX pipe instead of the LSU data pipe
         tex_cell(gr.tex, 2u * cell, pd.a[0], pd.a[1], pd.a[2], pd.a[3]);

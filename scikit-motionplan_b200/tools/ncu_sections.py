@@ -31,7 +31,8 @@ def anchors():
     a = {}
     a["fma2_lo"], a["fma2_hi"] = find(s2, "__device__ __forceinline__ float2 fma2"), find(s2, "enum { SDF_UNION")
     a["pair_lo"], a["pair_hi"] = find(s2, "template <typename T> struct Pair2;"), find(s2, "the corner-pack fast path exists for fp32 only")
-    a["grid_lo"], a["grid_hi"] = find(s2, "float s2_grid_fast("), find(s2, "the corner-pack fast path exists for fp32 only")
+    a["grid_lo"], a["grid_hi"] = find(s2, "struct GridPend {"), find(s2, "the corner-pack fast path exists for fp32 only")
+    a["fsplit_lo"], a["fsplit_hi"] = find(s2, "auto front_issue = "), find(s2, "// twist pair x wrench for the columns")
     a["prologue_lo"], a["prologue_hi"] = find(s2, "extern __shared__"), find(s2, "auto fetch_q")
     a["q_lo"], a["q_hi"] = find(s2, "auto fetch_q"), find(s2, "phase 1: frames + twists")
     a["front_lo"], a["front_hi"] = find(s2, "auto front = "), find(s2, "if (!RED) {")
@@ -72,6 +73,8 @@ def main():
             if A["q_lo"] <= l < A["q_hi"]:
                 return "q fetch + sin/cos pass"
             if A["front_lo"] <= l < A["front_hi"]:
+                return "phase 2: sphere centre, value, masks"
+            if A["fsplit_lo"] <= l < A["fsplit_hi"]:
                 return "phase 2: sphere centre, value, masks"
             if A["contract_lo"] <= l < A["contract_hi"]:
                 return "phase 2: column-mask selects"
