@@ -338,6 +338,26 @@ def test_grid_lookup_paths_bit_identical(monkeypatch, n):
     assert err(results[0][0][pick], rv) < TOL[np.float32]
 
 
+# ------------------------------------------------------------------ measurement aids of the C ABI
+def test_peak_microbenchmarks_run():
+    """skb_fma_peak / skb_store_peak (the roofline denominators bench_kernels.py reports) return plausible figures and
+    reject bad arguments."""
+    import ctypes
+
+    from skmp_b200 import _lib
+
+    _torch().cuda.init()
+    lib = _lib.lib()
+    t = ctypes.c_double(0.0)
+    _lib.check(lib.skb_fma_peak(0, 512, ctypes.byref(t)))
+    assert 5.0 < t.value < 200.0                                    # TFLOP/s fp32
+    for kind, blk in ((0, 0), (1, 3584)):
+        _lib.check(lib.skb_store_peak(kind, 1 << 30, blk, ctypes.byref(t)))
+        assert 500.0 < t.value < 20000.0                            # GB/s written
+    assert lib.skb_store_peak(1, 1 << 30, 100, ctypes.byref(t)) != 0     # block size not a multiple of 16
+    assert lib.skb_store_peak(2, 1 << 30, 0, ctypes.byref(t)) != 0       # unknown kind
+
+
 # ------------------------------------------------------------------ reference-held scene facts on the CUDA path
 def test_reference_pins_on_gpu():
     """The facts of tests/test_reference_pins.py through the product API (numpy in, like the reference's callers)."""
