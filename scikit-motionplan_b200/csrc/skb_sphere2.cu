@@ -40,6 +40,10 @@
 
 namespace skb {
 
+#ifndef SKB_CEN_SOA
+#define SKB_CEN_SOA 1           // pairwise sphere centres as three planes x[] y[] z[] per configuration (12 bytes per centre through the
+                                // shared-memory pipe instead of a padded 16-byte vector)
+#endif
 #ifndef SKB_S2_PIPE
 #define SKB_S2_PIPE 1           // 0: voxel lookups issued and consumed inside the same configuration (round-1 behaviour)
 #endif
@@ -88,6 +92,7 @@ struct S2Params {
     int off_lv, n_nodes;                                              // per-CTA level-record table (bytes), node count
     int woff_q, woff_sc, woff_frames, woff_tw, woff_cen, woff_stage;  // element offsets inside a warp slab
     int fstride, tstride, cstride;                                    // elements of T per configuration: frames, twists, centres
+    int cplane;                                                       // centres: elements of T per coordinate plane (SKB_CEN_SOA)
     int G, logG, slots3;
     int D, NP, R, n_steps, n_levels, n_cen;                           // R = output rows per configuration
     int copy_vec;                                                     // 1: every step block is 16-byte aligned in out_jac
@@ -182,6 +187,15 @@ __device__ __forceinline__ float grid_fast_or_generic(const S2Params<float> &prm
 }
 __device__ __forceinline__ double grid_fast_or_generic(const S2Params<double> &prm, double px, double py, double pz, double &gx, double &gy, double &gz) {
     return sdf_prim_world<double>(prm.prim0, px, py, pz, gx, gy, gz);
+}
+
+// sphere centre `idx` of a configuration's centre block: three planes (SKB_CEN_SOA) or one padded 4-vector
+template <typename T>
+__device__ __forceinline__ Vec4<T> load_centre(const T *cc, const int cplane, const int idx) {
+    Vec4<T> x;
+    if (SKB_CEN_SOA) { x.x = cc[idx]; x.y = cc[cplane + idx]; x.z = cc[2 * cplane + idx]; x.w = T(0); }
+    else x = reinterpret_cast<const Vec4<T> *>(cc)[idx];
+    return x;
 }
 
 template <typename T> struct PendRowT { GridPend g; T px, py, pz; };   // a row whose voxel lookup is in flight
@@ -313,7 +327,8 @@ __global__ void __launch_bounds__((sizeof(T) == 4 && KIND == KIND_COLLFREE && SD
                     x.y = f1.w + f1.x * A.x + f1.y * A.y + f1.z * A.z;
                     x.z = f2.w + f2.x * A.x + f2.y * A.y + f2.z * A.z;
                     x.w = T(0);
-                    reinterpret_cast<V4 *>(wcen + c * cstride)[s] = x;
+                    if (SKB_CEN_SOA) { T *cc = wcen + c * cstride; cc[s] = x.x; cc[prm.cplane + s] = x.y; cc[2 * prm.cplane + s] = x.z; }
+                    else reinterpret_cast<V4 *>(wcen + c * cstride)[s] = x;
                 }
             }
             __syncwarp();
@@ -337,8 +352,8 @@ __global__ void __launch_bounds__((sizeof(T) == 4 && KIND == KIND_COLLFREE && SD
                 rs.pm = sizeof(MaskT) == 8 ? (MaskT)(((unsigned long long)(unsigned)B.z << 32) | (unsigned)B.y) : (MaskT)(unsigned)B.y;
                 rs.mm = 0;
             } else {
-                const V4 *cen = reinterpret_cast<const V4 *>(wcen + c * cstride);
-                const V4 xi = cen[B.x & 0xffff], xj = cen[(unsigned)B.x >> 16];
+                const T *cen = wcen + c * cstride;
+                const V4 xi = load_centre<T>(cen, prm.cplane, B.x & 0xffff), xj = load_centre<T>(cen, prm.cplane, (unsigned)B.x >> 16);
                 const T dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
                 val = Rl::fma(dz, dz, Rl::fma(dy, dy, Rl::mul(dx, dx))) - (sizeof(T) == 4 ? (T)__int_as_float(B.w) : tabThr[tslot * 32 + lane]);
                 rs.gx = T(2) * dx; rs.gy = T(2) * dy; rs.gz = T(2) * dz;
@@ -553,11 +568,12 @@ __global__ void __launch_bounds__((sizeof(T) == 4 && KIND == KIND_COLLFREE && SD
             const int n_hr = sI[Q_N_HR];
             for (int c = 0; c < g_live; ++c) {
                 const long long n = n0 + c;
-                const V4 *cen = reinterpret_cast<const V4 *>(wcen + c * cstride);
+                const T *cen = wcen + c * cstride;
+                const int cplane = prm.cplane;
                 auto pair_value = [&](const int row, V4 &xi, T &dx, T &dy, T &dz) -> T {
                     const int2 P = tabP[row];
-                    xi = cen[P.x & 0xffff];
-                    const V4 xj = cen[(unsigned)P.x >> 16];
+                    xi = load_centre<T>(cen, cplane, P.x & 0xffff);
+                    const V4 xj = load_centre<T>(cen, cplane, (unsigned)P.x >> 16);
                     dx = xi.x - xj.x; dy = xi.y - xj.y; dz = xi.z - xj.z;
                     const T thr = sizeof(T) == 4 ? (T)__int_as_float(P.y) : (row < R ? tabThr[row] : -Rl::max());
                     return Rl::fma(dz, dz, Rl::fma(dy, dy, Rl::mul(dx, dx))) - thr;
@@ -850,7 +866,8 @@ static int configure_s2(const skb_plan *p, const skb_s2_program *sp, const void 
     prm.off_warp = align_up(prm.off_lv + sp->n_nodes * 16, 128);
     prm.fstride = sp->frame_stride;
     prm.tstride = odd_quads(NP * 12);
-    prm.cstride = KIND == KIND_PAIRWISE ? odd_quads(4 * sp->n_cen) : 0;
+    prm.cplane = align_up(sp->n_cen, 4);
+    prm.cstride = KIND == KIND_PAIRWISE ? (SKB_CEN_SOA ? 3 * prm.cplane : odd_quads(4 * sp->n_cen)) : 0;
     const size_t smem_limit = 227 * 1024;
     auto layout = [&](int g, int warps) {
         int e = 0;
